@@ -1,0 +1,166 @@
+/*
+ * vectorlite_cuda.h — C ABI of the B200-native VectorLite search hot path.
+ *
+ * Drop-in boundary: the reference's `trait VectorIndex` (src/lib.rs:224-245) and the two
+ * implementations behind `enum VectorIndexWrapper` (src/lib.rs:270-327):
+ *   FlatIndex  (src/index/flat.rs:59-136)  → vl_flat_create  + vl_index_*
+ *   HNSWIndex  (src/index/hnsw.rs:197-518) → vl_hnsw_create  + vl_index_*
+ * A Rust `extern "C"` block binds exactly these symbols (INTEGRATION.md shows the shim that
+ * re-creates the reference's error strings / enum variants from the status codes).
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; every pointer argument is caller-owned and borrowed for
+ *    the duration of the call; outputs are caller-allocated.  No callbacks, no exceptions
+ *    cross the boundary, nothing aborts: every entry point returns a vl_status.
+ *  - Vectors cross the boundary as f32 (device storage format) or f64 (the reference's
+ *    interface type, src/lib.rs:232; narrowed to f32 on entry).  Scores are returned as f64
+ *    and are bit-identical to the reference formulae evaluated on the stored f32 values
+ *    widened to f64 (sequential accumulation, no FMA).
+ *  - Threading (src/client.rs:243-247: Arc<RwLock<VectorIndexWrapper>>): vl_index_search,
+ *    vl_index_get_vector, vl_index_len, ... are re-entrant on one handle (reader side);
+ *    vl_index_add*, vl_index_delete, vl_index_fill_synthetic may assume external exclusion
+ *    (writer side).  The last-error string is thread-local.
+ *  - There is NO CPU fallback: every search runs on the CUDA device the handle was created
+ *    on; if no device is usable vl_*_create fails with VL_ERR_CUDA.
+ */
+#ifndef VECTORLITE_CUDA_H
+#define VECTORLITE_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vl_index vl_index;
+
+/* SimilarityMetric, declaration order of src/lib.rs:364-378 */
+typedef enum vl_metric {
+    VL_METRIC_COSINE = 0,
+    VL_METRIC_EUCLIDEAN = 1,
+    VL_METRIC_MANHATTAN = 2,
+    VL_METRIC_DOT = 3
+} vl_metric;
+
+typedef enum vl_status {
+    VL_OK = 0,
+    VL_ERR_DIM = 1,             /* "Vector dimension mismatch" (flat.rs:84, hnsw.rs:365) /
+                                   VectorLiteError::DimensionMismatch (flat.rs:100, hnsw.rs:417) */
+    VL_ERR_DUP_ID = 2,          /* "Vector ID {} already exists" (flat.rs:87, hnsw.rs:369) */
+    VL_ERR_NOT_FOUND = 3,       /* "Vector ID {} does not exist" (hnsw.rs:402); get_vector → None */
+    VL_ERR_METRIC_MISMATCH = 4, /* VectorLiteError::MetricMismatch (hnsw.rs:426-429) */
+    VL_ERR_INVALID = 5,         /* bad argument (null pointer, dim == 0, unknown metric, ...) */
+    VL_ERR_CUDA = 6,            /* CUDA runtime failure, or no usable device */
+    VL_ERR_OOM = 7,             /* host or device allocation failed */
+    VL_ERR_NAN = 8,             /* a similarity is NaN: the reference panics (flat.rs:116) */
+    VL_ERR_UNSUPPORTED = 9
+} vl_status;
+
+typedef enum vl_index_type { VL_INDEX_FLAT = 0, VL_INDEX_HNSW = 1 } vl_index_type; /* lib.rs:248-268 */
+
+/* Search-path selector for vl_index_set_mode (flat indexes).
+ * AUTO: fp32 (B=1) / bf16 tensor-core (batched) scan → over-select → fp64 rescore in reference
+ *       summation order → optimality certificate; a query whose certificate fails is re-run on
+ *       the EXACT path.  Both paths return identical, oracle-exact results.
+ * EXACT: every row scored in f64 in reference order on the device, stable radix select. */
+typedef enum vl_mode { VL_MODE_AUTO = 0, VL_MODE_EXACT = 1, VL_MODE_FP32 = 2 } vl_mode;
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+/* FlatIndex::new(dim, vec![]) (flat.rs:68).  device = CUDA ordinal. */
+int vl_flat_create(uint32_t dim, int device, vl_index** out);
+/* HNSWIndex::new(dim, metric) (hnsw.rs:216-259).  The reference's compile-time profiles
+ * (hnsw.rs:95-109: M/M0 = 16/32 default, 8/16 memory-optimized, 32/64 high-accuracy) and the
+ * crate's ef_construction (400) are runtime parameters here; 0 selects the default. */
+int vl_hnsw_create(uint32_t dim, int metric, uint32_t M, uint32_t M0, uint32_t ef_construction,
+                   int device, vl_index** out);
+void vl_index_destroy(vl_index* h);
+
+/* ---- mutation (writer side) ----------------------------------------------------------- */
+/* VectorIndex::add (flat.rs:82-91, hnsw.rs:363-399): VL_ERR_DIM / VL_ERR_DUP_ID. */
+int vl_index_add(vl_index* h, uint64_t id, const float* values, uint32_t len);
+int vl_index_add_f64(vl_index* h, uint64_t id, const double* values, uint32_t len);
+/* Bulk load, == FlatIndex::new(dim, data) / the persistence load path (persistence.rs:149-176).
+ * rows is [n][dim] row-major.  All-or-nothing on VL_ERR_DUP_ID. */
+int vl_index_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint64_t n);
+/* VectorIndex::delete.  Flat: deleting a missing id is VL_OK (flat.rs:93-96), order of the
+ * remaining rows is preserved (it is the tie-break).  HNSW: VL_ERR_NOT_FOUND (hnsw.rs:401-403),
+ * soft delete. */
+int vl_index_delete(vl_index* h, uint64_t id);
+/* Bench / test utility: append n rows generated on the device by the counter-based generator
+ * (bit-identical to oracle vlo_synth_rows_f32), ids = first_id + i, generator row = first_row + i. */
+int vl_index_fill_synthetic(vl_index* h, uint64_t seed, uint64_t first_row, uint64_t n,
+                            uint32_t clusters, uint64_t first_id);
+/* HNSW only: (re)build / finish the device graph after bulk adds.  Called implicitly by search. */
+int vl_index_build(vl_index* h);
+
+/* ---- queries (reader side) ------------------------------------------------------------ */
+/* VectorIndex::search (flat.rs:98-119, hnsw.rs:415-496) for nq queries at once (nq = 1 is the
+ * reference call).  queries is [nq][qdim] row-major HOST memory.  out_ids / out_scores are
+ * [nq][k]; out_counts[q] = number of valid entries for query q (min(k, len); HNSW may return
+ * fewer after soft deletes); unused slots hold id = UINT64_MAX, score = 0.  Results are ordered
+ * by score descending, ties by insertion order (the stable sort of flat.rs:116).
+ * Flat: VL_ERR_DIM only when the index is non-empty (flat.rs:99).  HNSW: VL_ERR_DIM always,
+ * VL_ERR_METRIC_MISMATCH when metric != index metric.  ef: HNSW beam width; 0 = the reference's
+ * ef = min(k, len) (hnsw.rs:437); ignored by flat indexes. */
+int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k,
+                    int metric, uint32_t ef, uint64_t* out_ids, double* out_scores,
+                    uint32_t* out_counts);
+int vl_index_search_f64(vl_index* h, const double* queries, uint32_t nq, uint32_t qdim, uint32_t k,
+                        int metric, uint32_t ef, uint64_t* out_ids, double* out_scores,
+                        uint32_t* out_counts);
+/* Same computation with DEVICE-resident queries [nq][dim] and DEVICE outputs, enqueued on
+ * `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) without host synchronisation.
+ * d_out_pos (may be NULL) receives storage positions (+ the handle's position base, see
+ * vl_index_set_pos_base) — what a row-sharded merge tie-breaks on.  d_out_flags[q]: bit0 = the
+ * optimality certificate failed (caller must re-run that query through vl_index_search or in
+ * VL_MODE_EXACT), bit1 = non-finite fp32 score seen, bit2 = NaN similarity. */
+int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric,
+                           uint32_t ef, uint64_t* d_out_ids, double* d_out_scores,
+                           uint64_t* d_out_pos, uint32_t* d_out_counts, uint32_t* d_out_flags,
+                           void* cuda_stream);
+/* Merge G per-shard result lists (each [nq][k], device memory, laid out [G][nq][k] as an
+ * all-gather leaves them) into the global top-k ordered by (score desc, position asc).
+ * counts is [G][nq]. */
+int vl_merge_topk_device(int device, uint32_t G, uint32_t nq, uint32_t k, const uint64_t* d_ids,
+                         const double* d_scores, const uint64_t* d_pos, const uint32_t* d_counts,
+                         uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                         uint32_t* d_out_counts, void* cuda_stream);
+
+/* ---- accessors ------------------------------------------------------------------------ */
+uint64_t vl_index_len(const vl_index* h);          /* VectorIndex::len */
+uint32_t vl_index_dim(const vl_index* h);          /* VectorIndex::dimension */
+int vl_index_type_of(const vl_index* h);           /* VectorIndexWrapper::index_type */
+int vl_index_metric(const vl_index* h);            /* VectorIndexWrapper::metric: -1 for flat (None) */
+int vl_index_device(const vl_index* h);
+/* max_id() (flat.rs:76-78, hnsw.rs:267-269): VL_ERR_NOT_FOUND when empty. */
+int vl_index_max_id(const vl_index* h, uint64_t* out_id);
+/* VectorIndex::get_vector: the stored f32 values. */
+int vl_index_get_vector(const vl_index* h, uint64_t id, float* out_values);
+/* Bulk export in storage order (persistence / Clone): up to `cap` rows starting at storage
+ * position `first`; returns rows written through out_n. */
+int vl_index_export(const vl_index* h, uint64_t first, uint64_t cap, uint64_t* out_ids,
+                    float* out_rows, uint64_t* out_n);
+
+/* ---- tuning / introspection ------------------------------------------------------------ */
+int vl_index_set_mode(vl_index* h, int mode);
+/* Row-sharded deployments: global storage position = base + local position. */
+int vl_index_set_pos_base(vl_index* h, uint64_t base);
+/* Counters since creation: [0] kernels launched, [1] searches served by the certified fast path,
+ * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited. */
+int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n);
+/* Kernel timing for roofline reports: while enabled, vl_index_search_device brackets every launch
+ * of the dominant scan kernel with CUDA events on the launching stream (ring of 1024 pairs).
+ * vl_index_profile_read synchronises, returns the summed duration (ms) and number of the bracketed
+ * launches since the last read, and clears the ring. */
+int vl_index_set_profiling(vl_index* h, int enabled);
+int vl_index_profile_read(vl_index* h, double* out_ms_total, uint64_t* out_launches);
+/* Raw device pointers for profiling harnesses (rows, pitch in floats). */
+int vl_index_device_rows(const vl_index* h, const float** d_rows, uint32_t* pitch);
+
+const char* vl_last_error(void);
+const char* vl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,284 @@
+"""GPU parity tests proper: the CUDA flat path, called through the C ABI, against the CPU oracle.
+
+Bar: top-k ids identical to the oracle under the stable-sort tie-break
+(score desc, insertion order asc); scores BIT-IDENTICAL in f64 (stronger than the 1e-5 the
+north star asks for), all four metrics.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vl():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import vectorlite_b200
+    vectorlite_b200.lib()
+    return vectorlite_b200
+
+
+def _hex(a):
+    return [float(x).hex() for x in a]
+
+
+def _check(vl, oracle_mod, idx, rows, ids, queries, k, metric):
+    gi, gs, gc = idx.search_batch(queries, k, metric)
+    for qi in range(queries.shape[0]):
+        st, oi, os_ = oracle_mod.flat_search(rows, ids, queries[qi], k, int(metric))
+        assert st == 0
+        c = int(gc[qi])
+        assert c == len(oi), (metric, k, c, len(oi))
+        assert list(map(int, gi[qi, :c])) == list(map(int, oi)), (metric, k, qi)
+        assert _hex(gs[qi, :c]) == _hex(os_), (metric, k, qi)
+        assert all(int(x) == 2**64 - 1 for x in gi[qi, c:])
+
+
+def test_reference_kats(vl, kats):
+    """Every flat known-answer test of the reference's own suite (SURVEY §8c ①-⑩)."""
+    for case in kats["flat"]:
+        dim = len(case["query"])
+        idx = vl.FlatIndex(dim, [vl.Vector(r["id"], r["values"], "test") for r in case["rows"]])
+        res = idx.search(case["query"], case["k"], vl.SimilarityMetric(case["metric"]))
+        assert len(res) == case["expect_len"], case["name"]
+        assert [r.id for r in res] == case["exact_ids"], case["name"]
+        assert _hex([r.score for r in res]) == case["exact_scores_hex"], case["name"]
+        for a in case["asserts"]:
+            if "score" in a:
+                assert abs(res[a["index"]].score - a["score"]) < a["tol"]
+            if "score_gt" in a:
+                assert res[a["index"]].score > a["score_gt"]
+        assert res[0].text == "test"
+
+
+@pytest.mark.parametrize("dim", [1, 3, 17, 100, 384, 768, 1000])
+def test_random_parity_dims(vl, oracle_mod, dim):
+    rng = np.random.default_rng(dim)
+    for n in (1, 5, 63, 64, 65, 700, 5000):
+        rows = rng.standard_normal((n, dim)).astype(np.float32)
+        if n > 10:
+            rows[3] = 0.0          # zero row: cosine → 0.0 branch (lib.rs:439-440)
+            rows[7] = rows[6]      # exact duplicate: tie → earlier position wins
+        ids = (np.arange(n, dtype=np.uint64) * 3 + 11)
+        queries = rng.standard_normal((2, dim)).astype(np.float32)
+        idx = vl.FlatIndex(dim)
+        idx.add_batch(ids, rows)
+        assert idx.len() == n and idx.dimension() == dim and idx.max_id() == int(ids[-1])
+        for metric in vl.SimilarityMetric:
+            for k in (1, 10, 100):
+                _check(vl, oracle_mod, idx, rows, ids, queries, k, metric)
+        idx.close()
+
+
+def test_unit_norm_384_all_metrics_k(vl, oracle_mod):
+    n, dim = 20000, 384
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    queries = oracle_mod.synth_rows(43, 0, 4, dim)
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    for metric in vl.SimilarityMetric:
+        for k in (1, 10, 100, 256, 300):   # 300 > over-select capacity → exact path
+            _check(vl, oracle_mod, idx, rows, None, queries, k, metric)
+    st = idx.stats()
+    assert st["fast_queries"] > 0 and st["exact_queries"] > 0
+
+
+def test_exact_mode_equals_auto(vl, oracle_mod):
+    n, dim = 3000, 96
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((3, dim)).astype(np.float32)
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    idx.set_mode(vl.Mode.Exact)
+    for metric in vl.SimilarityMetric:
+        _check(vl, oracle_mod, idx, rows, None, queries, 10, metric)
+    assert idx.stats()["fast_queries"] == 0
+
+
+def test_heavy_ties_fall_back_to_exact_path(vl, oracle_mod):
+    """All-equal embeddings (the reference's mock embedder, client.rs:504-523): every score ties,
+    the answer is the first k inserted.  The certificate cannot hold → exact path, same answer."""
+    n, dim = 2000, 384
+    rows = np.tile(np.linspace(0.1, 1.0, dim, dtype=np.float32), (n, 1))
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    q = rows[:1].copy()
+    for metric in vl.SimilarityMetric:
+        _check(vl, oracle_mod, idx, rows, None, q, 10, metric)
+    assert idx.stats()["exact_queries"] >= 4
+    # near-ties: scores differ by ~1 ulp of f32 — ids must still be the oracle's
+    rng = np.random.default_rng(1)
+    base = rng.standard_normal(dim).astype(np.float32)
+    rows2 = np.tile(base, (500, 1))
+    rows2[:, 0] += (rng.integers(0, 4, 500) * 1e-7).astype(np.float32)
+    idx2 = vl.FlatIndex(dim)
+    idx2.add_batch(np.arange(500, dtype=np.uint64), rows2)
+    for metric in vl.SimilarityMetric:
+        _check(vl, oracle_mod, idx2, rows2, None, base[None, :], 10, metric)
+
+
+def test_zero_query_and_zero_rows(vl, oracle_mod):
+    dim = 8
+    rows = np.zeros((10, dim), dtype=np.float32)
+    rows[4, 2] = 1.0
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(10, dtype=np.uint64), rows)
+    qs = np.zeros((2, dim), dtype=np.float32)
+    qs[1, 2] = 2.0
+    for metric in vl.SimilarityMetric:
+        _check(vl, oracle_mod, idx, rows, None, qs, 3, metric)
+
+
+def test_flat_semantics(vl):
+    idx = vl.FlatIndex(3)
+    # flat.rs:99: no dimension check while empty
+    assert idx.search([1.0, 2.0], 5, vl.SimilarityMetric.Cosine) == []
+    idx.add(vl.Vector(1, [1.0, 0.0, 0.0], "a", {"k": 1}))
+    idx.add(vl.Vector(2, [0.0, 1.0, 0.0], "b"))
+    idx.add(vl.Vector(3, [0.0, 0.0, 1.0], "c"))
+    with pytest.raises(ValueError, match="dimension"):       # flat.rs:84
+        idx.add(vl.Vector(4, [1.0, 2.0]))
+    with pytest.raises(ValueError, match="already exists"):  # flat.rs:87
+        idx.add(vl.Vector(2, [1.0, 2.0, 3.0]))
+    with pytest.raises(vl.DimensionMismatch) as e:           # flat.rs:100-103
+        idx.search([1.0, 0.0], 1, vl.SimilarityMetric.Cosine)
+    assert e.value.expected == 3 and e.value.actual == 2
+    assert idx.len() == 3 and not idx.is_empty() and idx.max_id() == 3
+    r = idx.search([1.0, 0.0, 0.0], 10, vl.SimilarityMetric.Cosine)      # k > n → n results
+    assert [x.id for x in r] == [1, 2, 3] and r[0].text == "a" and r[0].metadata == {"k": 1}
+    assert idx.search([1.0, 0.0, 0.0], 0, vl.SimilarityMetric.Cosine) == []
+    v = idx.get_vector(2)
+    assert v is not None and list(v.values) == [0.0, 1.0, 0.0] and v.text == "b"
+    assert idx.get_vector(99) is None
+    idx.delete(99)                                            # flat.rs:93-96: missing id is Ok
+    idx.delete(2)                                             # order of the rest is preserved
+    assert idx.len() == 2 and idx.get_vector(2) is None
+    r = idx.search([0.0, 0.0, 0.0], 2, vl.SimilarityMetric.DotProduct)   # all tie → insertion order
+    assert [x.id for x in r] == [1, 3]
+    idx.add(vl.Vector(2, [0.0, 1.0, 0.0]))                    # re-add goes to the END
+    r = idx.search([0.0, 0.0, 0.0], 3, vl.SimilarityMetric.DotProduct)
+    assert [x.id for x in r] == [1, 3, 2]
+    idx.delete(3)
+    assert idx.max_id() == 2
+    w = vl.VectorIndexWrapper(idx)
+    assert w.metric() is None and w.index_type() == vl.IndexType.Flat and w.len() == 2
+
+
+def test_delete_preserves_order_large(vl, oracle_mod):
+    n, dim = 3000, 20
+    rng = np.random.default_rng(9)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    rows[100:200] = rows[100]        # a block of duplicates: ties expose any reordering
+    ids = np.arange(n, dtype=np.uint64) + 1000
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(ids, rows)
+    keep = np.ones(n, dtype=bool)
+    for d in (1000, 1105, 1150, 3999, 2500):
+        idx.delete(int(d))
+        keep[d - 1000] = False
+    rows2, ids2 = rows[keep], ids[keep]
+    eids, erows = idx.export()
+    assert np.array_equal(eids, ids2) and np.array_equal(erows, rows2)
+    q = rows[100:101]
+    for metric in vl.SimilarityMetric:
+        _check(vl, oracle_mod, idx, rows2, ids2, q, 20, metric)
+
+
+def test_nan_is_an_error_not_a_panic(vl):
+    idx = vl.FlatIndex(2)
+    idx.add(vl.Vector(1, [1.0, 0.0]))
+    idx.add(vl.Vector(2, [float("nan"), 1.0]))
+    with pytest.raises(vl.VectorLiteError) as e:
+        idx.search([1.0, 1.0], 1, vl.SimilarityMetric.DotProduct)
+    assert e.value.code == vl.VL_ERR_NAN
+
+
+def test_device_generator_matches_oracle(vl, oracle_mod):
+    for clusters in (0, 16):
+        idx = vl.FlatIndex(384)
+        idx.fill_synthetic(42, 3000, first_row=500, clusters=clusters)
+        ids, rows = idx.export()
+        assert np.array_equal(ids, np.arange(500, 3500, dtype=np.uint64))
+        assert np.array_equal(rows, oracle_mod.synth_rows(42, 500, 3000, 384, clusters))
+    idx = vl.FlatIndex(100)
+    idx.fill_synthetic(7, 257)
+    assert np.array_equal(idx.export()[1], oracle_mod.synth_rows(7, 0, 257, 100))
+
+
+def test_search_device_and_sharded_merge(vl, oracle_mod):
+    """Row-sharded flat index emulated on one GPU: two shards with position bases, device-side
+    search into the all-gather layout [G][nq][k], merge kernel → equals the unsharded oracle."""
+    import torch
+    n, dim, k, nq, G = 6000, 384, 10, 5, 2
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    rows[3000:3010] = rows[10]       # cross-shard duplicates: tie-break must stay global
+    queries = np.concatenate([oracle_mod.synth_rows(43, 0, nq - 1, dim), rows[10:11]])
+    dev = torch.device("cuda:0")
+    d_q = torch.from_numpy(queries).to(dev)
+    g_ids = torch.zeros((G, nq, k), dtype=torch.int64, device=dev)
+    g_sc = torch.zeros((G, nq, k), dtype=torch.float64, device=dev)
+    g_pos = torch.zeros((G, nq, k), dtype=torch.int64, device=dev)
+    g_cnt = torch.zeros((G, nq), dtype=torch.int32, device=dev)
+    g_flg = torch.zeros((G, nq), dtype=torch.int32, device=dev)
+    shards = []
+    per = n // G
+    stream = torch.cuda.current_stream().cuda_stream
+    for metric in vl.SimilarityMetric:
+        for g in range(G):
+            s = vl.FlatIndex(dim)
+            s.add_batch(np.arange(g * per, (g + 1) * per, dtype=np.uint64), rows[g * per:(g + 1) * per])
+            s.set_pos_base(g * per)
+            s.search_device(d_q.data_ptr(), nq, k, metric, g_ids[g].data_ptr(), g_sc[g].data_ptr(),
+                            g_pos[g].data_ptr(), g_cnt[g].data_ptr(), g_flg[g].data_ptr(), stream)
+            shards.append(s)
+        o_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        o_sc = torch.zeros((nq, k), dtype=torch.float64, device=dev)
+        o_pos = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        o_cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        st = vl.lib().vl_merge_topk_device(0, G, nq, k, g_ids.data_ptr(), g_sc.data_ptr(), g_pos.data_ptr(),
+                                           g_cnt.data_ptr(), o_ids.data_ptr(), o_sc.data_ptr(),
+                                           o_pos.data_ptr(), o_cnt.data_ptr(), stream)
+        assert st == 0
+        torch.cuda.synchronize()
+        assert int(g_flg.max()) == 0, "certificate failed on a shard"
+        for qi in range(nq):
+            st, oi, os_ = oracle_mod.flat_search(rows, None, queries[qi], k, int(metric))
+            assert o_ids[qi].tolist() == list(map(int, oi)), (metric, qi)
+            assert _hex(o_sc[qi].tolist()) == _hex(os_)
+            assert o_pos[qi].tolist() == list(map(int, oi))
+        shards.clear()
+
+
+def test_full_size_1m_properties_and_sampled_oracle(vl, oracle_mod):
+    """BASELINE config 2 size (1M × 384): size-independent properties on the device-generated
+    store + full-oracle check on sampled queries."""
+    n, dim, k = 1_000_000, 384, 10
+    idx = vl.FlatIndex(dim)
+    idx.fill_synthetic(42, n)
+    assert idx.len() == n
+    # property: a stored row queried back is its own top-1 with cosine == 1 (to 1e-6), L2/L1 sim == 1
+    probe_ids = [0, 1, 63, 64, 65, 12345, 999_999]
+    probes = np.stack([oracle_mod.synth_rows(42, r, 1, dim)[0] for r in probe_ids])
+    for metric in vl.SimilarityMetric:
+        gi, gs, gc = idx.search_batch(probes, k, metric)
+        assert [int(x) for x in gi[:, 0]] == probe_ids, metric
+        assert np.all(np.diff(gs, axis=1) <= 0)                      # non-increasing scores
+        if metric in (vl.SimilarityMetric.Euclidean, vl.SimilarityMetric.Manhattan):
+            assert np.all(gs[:, 0] == 1.0)
+        else:
+            assert np.allclose(gs[:, 0], 1.0, atol=1e-6)
+    # idempotence: same query twice → identical bits
+    q = oracle_mod.synth_rows(43, 0, 2, dim)
+    a = idx.search_batch(q, k, vl.SimilarityMetric.Cosine)
+    b = idx.search_batch(q, k, vl.SimilarityMetric.Cosine)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # sampled full oracle (regenerates the 1M rows on the host with the same counter-based recipe)
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    for metric in vl.SimilarityMetric:
+        _check(vl, oracle_mod, idx, rows, None, q, k, metric)
+    assert idx.stats()["exact_queries"] == 0, "certificate should hold on i.i.d. data"

@@ -1,0 +1,840 @@
+// api.cu — the C ABI (include/vectorlite_cuda.h): handle, device arena, workspace pool and the
+// search orchestration for the flat index.  Host-side semantics follow the reference's
+// FlatIndex (src/index/flat.rs:59-136) behind trait VectorIndex (src/lib.rs:224-245); the HNSW
+// half of the handle lives in hnsw_host.cpp / hnsw_search.cu.
+#include "../../include/vectorlite_cuda.h"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <unordered_map>
+#include <vector>
+
+#include "hnsw.h"
+#include "kernels.h"
+
+using namespace vl;
+
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (x);                                                                   \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(_e == cudaErrorMemoryAllocation ? VL_ERR_OOM : VL_ERR_CUDA, "%s: %s", #x, \
+                        cudaGetErrorString(_e));                                                \
+    } while (0)
+
+enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_N = 8 };
+
+namespace {
+
+constexpr uint32_t NQ_CHUNK = 32;  // queries per launch of the per-query scan
+
+struct Slot {  // one in-flight search: stream + scratch, all sized on demand
+    cudaStream_t stream = nullptr;
+    // queries
+    float* d_q = nullptr; float* h_q = nullptr; size_t q_cap = 0;  // floats
+    // scan scratch
+    uint64_t* cand = nullptr; size_t cand_cap = 0;
+    uint32_t* cand_count = nullptr; size_t cc_cap = 0;
+    QueryCtl* ctl = nullptr; size_t ctl_cap = 0;
+    // outputs (device + pinned mirrors), sized nq_cap × k_cap
+    uint64_t* d_ids = nullptr; double* d_scores = nullptr; uint32_t* d_counts = nullptr; uint32_t* d_flags = nullptr;
+    uint64_t* h_ids = nullptr; double* h_scores = nullptr; uint32_t* h_counts = nullptr; uint32_t* h_flags = nullptr;
+    size_t out_cap = 0, outq_cap = 0;
+    // exact path
+    double* d_exact = nullptr; size_t exact_cap = 0;
+    uint32_t* d_exflags = nullptr;
+    ExactScratch exs;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct vl_index {
+    int type = VL_INDEX_FLAT;
+    int device = 0;
+    uint32_t dim = 0, pitch = 0;
+    int mode = VL_MODE_AUTO;
+    uint64_t pos_base = 0;
+    // ---- arena ----
+    float* d_rows = nullptr;
+    float* d_inv_norm = nullptr;
+    uint64_t* d_ids = nullptr;   // only when !identity
+    ArenaStats* d_stats = nullptr;
+    uint64_t n = 0, cap = 0;
+    // ---- host id bookkeeping ----
+    bool identity = true;        // id == id_base + pos for every row (no map needed)
+    uint64_t id_base = 0;
+    bool have_max = false;
+    uint64_t max_id = 0;
+    std::vector<uint64_t> ids_host;
+    std::unordered_map<uint64_t, uint32_t> id_to_pos;
+    // ---- workspaces ----
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::unique_ptr<Slot>> slots;
+    Slot dev_slot;               // used by vl_index_search_device (caller-ordered)
+    cudaStream_t mut_stream = nullptr;
+    int max_grid_x = 148 * 4;
+    std::atomic<uint64_t> stats[ST_N];
+    // ---- profiling (roofline reports) ----
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    size_t prof_n = 0;                  // pairs recorded since last read
+    // ---- hnsw ----
+    HnswPtr hnsw;
+    int hnsw_metric = -1;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int grow_dev(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return VL_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CU(cudaMalloc(&p, need * sizeof(T)));
+    cap = need;
+    return VL_OK;
+}
+
+int slot_reserve(vl_index* h, Slot& s, uint32_t nq, uint32_t k, int Kp, int grid_x) {
+    int st;
+    const size_t qf = static_cast<size_t>(nq) * h->pitch;
+    if (qf > s.q_cap) {
+        if (s.d_q) cudaFree(s.d_q);
+        if (s.h_q) cudaFreeHost(s.h_q);
+        s.d_q = nullptr; s.h_q = nullptr; s.q_cap = 0;
+        CU(cudaMalloc(&s.d_q, qf * sizeof(float)));
+        CU(cudaMallocHost(&s.h_q, qf * sizeof(float)));
+        s.q_cap = qf;
+    }
+    if ((st = grow_dev(s.cand, s.cand_cap, static_cast<size_t>(nq) * grid_x * Kp))) return st;
+    if ((st = grow_dev(s.cand_count, s.cc_cap, static_cast<size_t>(nq) * grid_x))) return st;
+    if (nq > s.ctl_cap) {
+        if ((st = grow_dev(s.ctl, s.ctl_cap, nq))) return st;
+        CU(cudaMemsetAsync(s.ctl, 0, nq * sizeof(QueryCtl), s.stream));
+    }
+    const size_t on = static_cast<size_t>(nq) * std::max<uint32_t>(k, 1);
+    if (on > s.out_cap || nq > s.outq_cap) {
+        cudaFree(s.d_ids); cudaFree(s.d_scores); cudaFree(s.d_counts); cudaFree(s.d_flags);
+        cudaFreeHost(s.h_ids); cudaFreeHost(s.h_scores); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_flags);
+        s.d_ids = nullptr; s.d_scores = nullptr; s.d_counts = nullptr; s.d_flags = nullptr;
+        s.h_ids = nullptr; s.h_scores = nullptr; s.h_counts = nullptr; s.h_flags = nullptr;
+        s.out_cap = s.outq_cap = 0;
+        const size_t oc = std::max(on, s.out_cap), qc = std::max<size_t>(nq, s.outq_cap);
+        CU(cudaMalloc(&s.d_ids, oc * 8)); CU(cudaMalloc(&s.d_scores, oc * 8));
+        CU(cudaMalloc(&s.d_counts, qc * 4)); CU(cudaMalloc(&s.d_flags, qc * 4));
+        CU(cudaMallocHost(&s.h_ids, oc * 8)); CU(cudaMallocHost(&s.h_scores, oc * 8));
+        CU(cudaMallocHost(&s.h_counts, qc * 4)); CU(cudaMallocHost(&s.h_flags, qc * 4));
+        s.out_cap = oc; s.outq_cap = qc;
+    }
+    if (!s.d_exflags) CU(cudaMalloc(&s.d_exflags, 4));
+    return VL_OK;
+}
+
+void slot_free(Slot& s) {
+    cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.ctl);
+    cudaFree(s.d_ids); cudaFree(s.d_scores); cudaFree(s.d_counts); cudaFree(s.d_flags);
+    cudaFreeHost(s.h_ids); cudaFreeHost(s.h_scores); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_flags);
+    cudaFree(s.d_exact); cudaFree(s.d_exflags);
+    exact_scratch_free(s.exs);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+Slot* acquire_slot(vl_index* h) {
+    std::unique_lock<std::mutex> lk(h->mu);
+    for (;;) {
+        for (auto& s : h->slots)
+            if (!s->busy) {
+                s->busy = true;
+                return s.get();
+            }
+        if (h->slots.size() < 8) {
+            auto s = std::make_unique<Slot>();
+            if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            s->busy = true;
+            h->slots.push_back(std::move(s));
+            return h->slots.back().get();
+        }
+        h->cv.wait(lk);
+    }
+}
+void release_slot(vl_index* h, Slot* s) {
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        s->busy = false;
+    }
+    h->cv.notify_one();
+}
+
+int pick_kp(uint32_t k) {  // over-select size K'
+    uint32_t kp = k + std::max<uint32_t>(k, 32);
+    kp = (kp + 31) / 32 * 32;
+    return static_cast<int>(std::max<uint32_t>(kp, 64));
+}
+
+FlatView view_of(const vl_index* h) {
+    FlatView v;
+    v.rows = h->d_rows;
+    v.inv_norm = h->d_inv_norm;
+    v.ids = h->identity ? nullptr : h->d_ids;
+    v.stats = h->d_stats;
+    v.id_base = h->id_base;
+    v.pos_base = h->pos_base;
+    v.n = static_cast<uint32_t>(h->n);
+    v.dim = h->dim;
+    v.pitch = h->pitch;
+    return v;
+}
+
+int arena_reserve(vl_index* h, uint64_t need) {
+    if (need <= h->cap) return VL_OK;
+    if (need >= 0xFFFFFFFEull) return fail(VL_ERR_UNSUPPORTED, "a shard holds at most 2^32-2 rows");
+    uint64_t nc = std::max<uint64_t>(need, h->cap + h->cap / 2);
+    nc = std::max<uint64_t>(nc, 1024);
+    float* rows = nullptr; float* inv = nullptr; uint64_t* ids = nullptr;
+    CU(cudaMalloc(&rows, nc * h->pitch * sizeof(float)));
+    cudaError_t e = cudaMalloc(&inv, nc * sizeof(float));
+    if (e == cudaSuccess && !h->identity) e = cudaMalloc(&ids, nc * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        cudaFree(rows); cudaFree(inv); cudaFree(ids);
+        return fail(VL_ERR_OOM, "arena grow: %s", cudaGetErrorString(e));
+    }
+    if (h->n) {
+        CU(cudaMemcpyAsync(rows, h->d_rows, h->n * h->pitch * sizeof(float), cudaMemcpyDeviceToDevice, h->mut_stream));
+        CU(cudaMemcpyAsync(inv, h->d_inv_norm, h->n * sizeof(float), cudaMemcpyDeviceToDevice, h->mut_stream));
+        if (ids) CU(cudaMemcpyAsync(ids, h->d_ids, h->n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, h->mut_stream));
+        CU(cudaStreamSynchronize(h->mut_stream));
+    }
+    cudaFree(h->d_rows); cudaFree(h->d_inv_norm); cudaFree(h->d_ids);
+    h->d_rows = rows; h->d_inv_norm = inv; h->d_ids = ids;
+    h->cap = nc;
+    return VL_OK;
+}
+
+// leave identity mode: ids become an explicit array + hash map
+int materialize_ids(vl_index* h) {
+    if (!h->identity) return VL_OK;
+    h->ids_host.resize(h->n);
+    h->id_to_pos.reserve(h->n * 2 + 16);
+    for (uint64_t i = 0; i < h->n; ++i) {
+        h->ids_host[i] = h->id_base + i;
+        h->id_to_pos.emplace(h->id_base + i, static_cast<uint32_t>(i));
+    }
+    uint64_t* ids = nullptr;
+    if (h->cap) {
+        CU(cudaMalloc(&ids, h->cap * sizeof(uint64_t)));
+        if (h->n) CU(cudaMemcpy(ids, h->ids_host.data(), h->n * 8, cudaMemcpyHostToDevice));
+    }
+    h->d_ids = ids;
+    h->identity = false;
+    return VL_OK;
+}
+
+bool find_pos(const vl_index* h, uint64_t id, uint32_t* pos) {
+    if (h->identity) {
+        if (h->n == 0 || id < h->id_base || id - h->id_base >= h->n) return false;
+        *pos = static_cast<uint32_t>(id - h->id_base);
+        return true;
+    }
+    auto it = h->id_to_pos.find(id);
+    if (it == h->id_to_pos.end()) return false;
+    *pos = it->second;
+    return true;
+}
+
+int flat_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint64_t n) {
+    if (n == 0) return VL_OK;
+    // ---- id checks first: all-or-nothing (flat.rs:86-88) ----
+    bool seq = true;
+    if (h->identity) {
+        const uint64_t base = h->n ? h->id_base + h->n : ids[0];
+        for (uint64_t i = 0; i < n && seq; ++i) seq = ids[i] == base + i;
+    }
+    if (h->identity && !seq) {
+        int st = materialize_ids(h);
+        if (st) return st;
+    }
+    if (!h->identity) {
+        uint64_t i = 0;
+        for (; i < n; ++i) {
+            auto r = h->id_to_pos.emplace(ids[i], static_cast<uint32_t>(h->n + i));
+            if (!r.second) break;
+        }
+        if (i < n) {
+            const uint64_t dup = ids[i];
+            for (uint64_t j = 0; j < i; ++j) h->id_to_pos.erase(ids[j]);
+            return fail(VL_ERR_DUP_ID, "Vector ID %llu already exists", static_cast<unsigned long long>(dup));
+        }
+    }
+    int st = arena_reserve(h, h->n + n);
+    if (st) {
+        if (!h->identity) for (uint64_t j = 0; j < n; ++j) h->id_to_pos.erase(ids[j]);
+        return st;
+    }
+    if (h->identity && h->n == 0) h->id_base = ids[0];
+    // ---- upload rows (pad to pitch) ----
+    float* dst = h->d_rows + h->n * h->pitch;
+    if (h->pitch == h->dim) {
+        CU(cudaMemcpyAsync(dst, rows, n * h->dim * sizeof(float), cudaMemcpyHostToDevice, h->mut_stream));
+    } else {
+        CU(cudaMemsetAsync(dst, 0, n * h->pitch * sizeof(float), h->mut_stream));
+        CU(cudaMemcpy2DAsync(dst, h->pitch * sizeof(float), rows, h->dim * sizeof(float),
+                             h->dim * sizeof(float), n, cudaMemcpyHostToDevice, h->mut_stream));
+    }
+    if (!h->identity) {
+        CU(cudaMemcpyAsync(h->d_ids + h->n, ids, n * 8, cudaMemcpyHostToDevice, h->mut_stream));
+        h->ids_host.insert(h->ids_host.end(), ids, ids + n);
+    }
+    CU(launch_row_norms(h->d_rows, h->n, n, h->dim, h->pitch, h->d_inv_norm, h->d_stats, h->mut_stream));
+    CU(cudaStreamSynchronize(h->mut_stream));
+    h->stats[ST_LAUNCHES] += 1;
+    h->stats[ST_H2D] += n * h->dim * sizeof(float);
+    for (uint64_t i = 0; i < n; ++i)
+        if (!h->have_max || ids[i] > h->max_id) { h->max_id = ids[i]; h->have_max = true; }
+    h->n += n;
+    return VL_OK;
+}
+
+// order-preserving removal of one storage position (flat.rs:94 `retain` keeps order)
+int flat_remove_pos(vl_index* h, uint32_t pos) {
+    const uint64_t tail = h->n - pos - 1;
+    if (tail) {
+        const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / (h->pitch * sizeof(float)));
+        float* tmp = nullptr;
+        CU(cudaMalloc(&tmp, std::min(chunk_rows, tail) * h->pitch * sizeof(float)));
+        for (uint64_t off = 0; off < tail; off += chunk_rows) {
+            const uint64_t m = std::min(chunk_rows, tail - off);
+            const size_t bytes = m * h->pitch * sizeof(float);
+            cudaMemcpyAsync(tmp, h->d_rows + (pos + 1 + off) * h->pitch, bytes, cudaMemcpyDeviceToDevice, h->mut_stream);
+            cudaMemcpyAsync(h->d_rows + (pos + off) * h->pitch, tmp, bytes, cudaMemcpyDeviceToDevice, h->mut_stream);
+        }
+        // side arrays are small: bounce through tmp when it fits, else chunk as well
+        const uint64_t side_chunk = std::min<uint64_t>(tail, std::min(chunk_rows, tail) * h->pitch * sizeof(float) / 8);
+        for (uint64_t off = 0; off < tail; off += side_chunk) {
+            const uint64_t m = std::min(side_chunk, tail - off);
+            cudaMemcpyAsync(tmp, h->d_inv_norm + pos + 1 + off, m * 4, cudaMemcpyDeviceToDevice, h->mut_stream);
+            cudaMemcpyAsync(h->d_inv_norm + pos + off, tmp, m * 4, cudaMemcpyDeviceToDevice, h->mut_stream);
+            if (h->d_ids) {
+                cudaMemcpyAsync(tmp, h->d_ids + pos + 1 + off, m * 8, cudaMemcpyDeviceToDevice, h->mut_stream);
+                cudaMemcpyAsync(h->d_ids + pos + off, tmp, m * 8, cudaMemcpyDeviceToDevice, h->mut_stream);
+            }
+        }
+        cudaError_t e = cudaStreamSynchronize(h->mut_stream);
+        cudaFree(tmp);
+        CU(e);
+    }
+    const uint64_t id = h->ids_host[pos];
+    h->id_to_pos.erase(id);
+    h->ids_host.erase(h->ids_host.begin() + pos);
+    for (uint64_t i = pos; i < h->ids_host.size(); ++i) h->id_to_pos[h->ids_host[i]] = static_cast<uint32_t>(i);
+    h->n -= 1;
+    if (h->have_max && id == h->max_id) {  // max_id() recomputes (flat.rs:76-78)
+        h->have_max = !h->ids_host.empty();
+        if (h->have_max) h->max_id = *std::max_element(h->ids_host.begin(), h->ids_host.end());
+    }
+    return VL_OK;
+}
+
+// exact path for one query already resident at d_query; writes slot outputs at q_index
+int run_exact_one(vl_index* h, Slot& s, const FlatView& v, const float* d_query, int metric, uint32_t k,
+                  uint32_t q_index, cudaStream_t stream) {
+    int st = grow_dev(s.d_exact, s.exact_cap, static_cast<size_t>(v.n));
+    if (st) return st;
+    SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
+    CU(cudaMemsetAsync(s.d_exflags, 0, 4, stream));
+    CU(launch_exact_scores(v, d_query, metric, s.d_exact, s.d_exflags, stream));
+    CU(exact_select(v, s.d_exact, k, s.exs, out, q_index, stream));
+    CU(cudaMemcpyAsync(s.d_flags + q_index, s.d_exflags, 4, cudaMemcpyDeviceToDevice, stream));
+    h->stats[ST_LAUNCHES] += 4;
+    h->stats[ST_EXACT] += 1;
+    return VL_OK;
+}
+
+int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+    // flat.rs:99-104: the dimension is only checked when the index is non-empty
+    if (h->n != 0 && qdim != h->dim)
+        return fail(VL_ERR_DIM, "Dimension mismatch: expected %u, got %u", h->dim, qdim);
+    for (size_t i = 0; i < static_cast<size_t>(nq) * k; ++i) { out_ids[i] = ~0ull; out_scores[i] = 0.0; }
+    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+    if (h->n == 0 || k == 0 || nq == 0) return VL_OK;
+
+    DeviceGuard dg(h->device);
+    Slot* sp = acquire_slot(h);
+    if (!sp) return fail(VL_ERR_CUDA, "cannot create a CUDA stream");
+    Slot& s = *sp;
+    struct Rel { vl_index* h; Slot* s; ~Rel() { release_slot(h, s); } } rel{h, sp};
+
+    const FlatView v = view_of(h);
+    const bool fast = h->mode != VL_MODE_EXACT && k <= 256;
+    const int Kp = pick_kp(k);
+    const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
+    const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
+    int rc = VL_OK;
+    for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += NQ_CHUNK) {
+        const uint32_t m = std::min(NQ_CHUNK, nq - q0);
+        int st = slot_reserve(h, s, m, k, Kp, grid_x);
+        if (st) return st;
+        for (uint32_t q = 0; q < m; ++q) {
+            float* d = s.h_q + static_cast<size_t>(q) * h->pitch;
+            memcpy(d, queries + static_cast<size_t>(q0 + q) * qdim, h->dim * sizeof(float));
+            for (uint32_t c = h->dim; c < h->pitch; ++c) d[c] = 0.f;
+        }
+        const size_t qbytes = static_cast<size_t>(m) * h->pitch * sizeof(float);
+        CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
+        h->stats[ST_H2D] += qbytes;
+        if (fast) {
+            ScanWork w{s.cand, s.cand_count, s.ctl, grid_x, Kp};
+            SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
+            CU(launch_flat_scan(v, s.d_q, m, metric, w, s.stream));
+            CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, out, 1.0f, s.stream));
+            h->stats[ST_LAUNCHES] += 2;
+            CU(cudaMemcpyAsync(s.h_flags, s.d_flags, m * 4, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_counts, s.d_counts, m * 4, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_ids, s.d_ids, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_scores, s.d_scores, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            bool any_fail = false;
+            for (uint32_t q = 0; q < m; ++q) {
+                if (s.h_flags[q] & FLAG_CERT_FAIL) any_fail = true; else h->stats[ST_FAST] += 1;
+            }
+            if (any_fail) {
+                for (uint32_t q = 0; q < m; ++q)
+                    if (s.h_flags[q] & FLAG_CERT_FAIL) {
+                        st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
+                        if (st) return st;
+                    }
+                CU(cudaMemcpyAsync(s.h_flags, s.d_flags, m * 4, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(s.h_counts, s.d_counts, m * 4, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(s.h_ids, s.d_ids, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(s.h_scores, s.d_scores, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaStreamSynchronize(s.stream));
+            }
+        } else {
+            for (uint32_t q = 0; q < m; ++q) {
+                st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
+                if (st) return st;
+            }
+            CU(cudaMemcpyAsync(s.h_flags, s.d_flags, m * 4, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_counts, s.d_counts, m * 4, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_ids, s.d_ids, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_scores, s.d_scores, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+        }
+        h->stats[ST_D2H] += static_cast<size_t>(m) * (k * 16 + 8);
+        for (uint32_t q = 0; q < m; ++q) {
+            if (s.h_flags[q] & FLAG_NAN) {
+                // the reference panics (partial_cmp().unwrap(), flat.rs:116) as soon as n >= 2
+                if (h->n >= 2) rc = fail(VL_ERR_NAN, "similarity is NaN (the reference panics at flat.rs:116)");
+            }
+            memcpy(out_ids + static_cast<size_t>(q0 + q) * k, s.h_ids + static_cast<size_t>(q) * k, k * 8);
+            memcpy(out_scores + static_cast<size_t>(q0 + q) * k, s.h_scores + static_cast<size_t>(q) * k, k * 8);
+            out_counts[q0 + q] = s.h_counts[q];
+        }
+    }
+    return rc;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* vl_last_error(void) { return g_err; }
+const char* vl_version(void) { return "vectorlite-b200 0.1.0 (sm_100a)"; }
+
+static int create_common(uint32_t dim, int device, vl_index** out, int type) {
+    if (!out) return fail(VL_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dim == 0) return fail(VL_ERR_INVALID, "dimension cannot be 0");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(VL_ERR_CUDA, "no usable CUDA device (%s); there is no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(VL_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    vl_index* h = new (std::nothrow) vl_index();
+    if (!h) return fail(VL_ERR_OOM, "host allocation failed");
+    h->type = type;
+    h->device = device;
+    h->dim = dim;
+    h->pitch = (dim + 3) / 4 * 4;
+    for (auto& c : h->stats) c = 0;
+    DeviceGuard dg(device);
+    ArenaStats init{0ull, 0x7FF0000000000000ull, 0u, 0u};
+    if (cudaStreamCreateWithFlags(&h->mut_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&h->d_stats, sizeof(ArenaStats)) != cudaSuccess ||
+        cudaMemcpy(h->d_stats, &init, sizeof init, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->dev_slot.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        const char* msg = cudaGetErrorString(cudaGetLastError());
+        vl_index_destroy(h);
+        return fail(VL_ERR_CUDA, "device init failed: %s", msg);
+    }
+    h->max_grid_x = flat_scan_max_grid_x(device, h->pitch);
+    *out = h;
+    return VL_OK;
+}
+
+int vl_flat_create(uint32_t dim, int device, vl_index** out) {
+    return create_common(dim, device, out, VL_INDEX_FLAT);
+}
+
+int vl_hnsw_create(uint32_t dim, int metric, uint32_t M, uint32_t M0, uint32_t efc, int device,
+                   vl_index** out) {
+    if (metric < 0 || metric > 3) return fail(VL_ERR_INVALID, "unknown metric %d", metric);
+    int st = create_common(dim, device, out, VL_INDEX_HNSW);
+    if (st) return st;
+    (*out)->hnsw_metric = metric;
+    (*out)->hnsw.reset(hnsw_state_create(dim, metric, M ? M : 16, M0 ? M0 : 32, efc ? efc : 400));
+    if (!(*out)->hnsw) {
+        vl_index_destroy(*out);
+        *out = nullptr;
+        return fail(VL_ERR_INVALID, "invalid HNSW parameters (M=%u, M0=%u)", M, M0);
+    }
+    return VL_OK;
+}
+
+void vl_index_destroy(vl_index* h) {
+    if (!h) return;
+    DeviceGuard dg(h->device);
+    cudaDeviceSynchronize();
+    if (h->hnsw) hnsw_state_release_device(h->hnsw.get());
+    for (auto& s : h->slots) slot_free(*s);
+    slot_free(h->dev_slot);
+    cudaFree(h->d_rows); cudaFree(h->d_inv_norm); cudaFree(h->d_ids); cudaFree(h->d_stats);
+    for (auto& e : h->prof_ev) cudaEventDestroy(e);
+    if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
+    delete h;
+}
+
+int vl_index_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint64_t n) {
+    if (!h || (n && (!ids || !rows))) return fail(VL_ERR_INVALID, "null argument");
+    DeviceGuard dg(h->device);
+    if (h->type == VL_INDEX_HNSW) {
+        // hnsw.rs:363-399: dup check against live ids, then append to the arena and the graph
+        for (uint64_t i = 0; i < n; ++i)
+            if (hnsw_has_id(h->hnsw.get(), ids[i]))
+                return fail(VL_ERR_DUP_ID, "Vector ID %llu already exists", static_cast<unsigned long long>(ids[i]));
+        const uint64_t first = h->n;
+        // arena rows are addressed by internal index; ids are tracked by the HNSW state
+        std::vector<uint64_t> internal(n);
+        for (uint64_t i = 0; i < n; ++i) internal[i] = first + i;
+        const bool was_identity = h->identity;
+        int st = flat_add_batch(h, internal.data(), rows, n);
+        if (st) return st;
+        (void)was_identity;
+        st = hnsw_add_rows(h->hnsw.get(), ids, rows, n);
+        if (st) return fail(st, "hnsw insert failed");
+        return VL_OK;
+    }
+    return flat_add_batch(h, ids, rows, n);
+}
+
+int vl_index_add(vl_index* h, uint64_t id, const float* values, uint32_t len) {
+    if (!h || !values) return fail(VL_ERR_INVALID, "null argument");
+    if (len != h->dim) {
+        if (h->type == VL_INDEX_HNSW)  // hnsw.rs:365
+            return fail(VL_ERR_DIM, "Vector dimension mismatch: expected %u, got %u", h->dim, len);
+        return fail(VL_ERR_DIM, "Vector dimension mismatch");  // flat.rs:84
+    }
+    if (h->type == VL_INDEX_FLAT) {
+        uint32_t pos;
+        if (find_pos(h, id, &pos))
+            return fail(VL_ERR_DUP_ID, "Vector ID %llu already exists", static_cast<unsigned long long>(id));
+    }
+    return vl_index_add_batch(h, &id, values, 1);
+}
+
+int vl_index_add_f64(vl_index* h, uint64_t id, const double* values, uint32_t len) {
+    if (!h || !values) return fail(VL_ERR_INVALID, "null argument");
+    std::vector<float> f(len);
+    for (uint32_t i = 0; i < len; ++i) f[i] = static_cast<float>(values[i]);
+    return vl_index_add(h, id, f.data(), len);
+}
+
+int vl_index_delete(vl_index* h, uint64_t id) {
+    if (!h) return fail(VL_ERR_INVALID, "null handle");
+    DeviceGuard dg(h->device);
+    if (h->type == VL_INDEX_HNSW) {
+        if (!hnsw_soft_delete(h->hnsw.get(), id))  // hnsw.rs:401-403
+            return fail(VL_ERR_NOT_FOUND, "Vector ID %llu does not exist", static_cast<unsigned long long>(id));
+        return VL_OK;
+    }
+    uint32_t pos;
+    if (!find_pos(h, id, &pos)) return VL_OK;  // flat.rs:93-96: deleting a missing id is Ok
+    int st = materialize_ids(h);
+    if (st) return st;
+    return flat_remove_pos(h, pos);
+}
+
+int vl_index_fill_synthetic(vl_index* h, uint64_t seed, uint64_t first_row, uint64_t n, uint32_t clusters,
+                            uint64_t first_id) {
+    if (!h) return fail(VL_ERR_INVALID, "null handle");
+    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "fill_synthetic is a flat-index utility");
+    if (n == 0) return VL_OK;
+    DeviceGuard dg(h->device);
+    if (h->identity) {
+        if (h->n && first_id != h->id_base + h->n) {
+            int st = materialize_ids(h);
+            if (st) return st;
+        }
+    }
+    if (!h->identity) {
+        for (uint64_t i = 0; i < n; ++i)
+            if (h->id_to_pos.count(first_id + i))
+                return fail(VL_ERR_DUP_ID, "Vector ID %llu already exists", static_cast<unsigned long long>(first_id + i));
+    }
+    int st = arena_reserve(h, h->n + n);
+    if (st) return st;
+    if (h->identity && h->n == 0) h->id_base = first_id;
+    CU(launch_synth_fill(h->d_rows, h->n, n, h->dim, h->pitch, seed, first_row, clusters, h->mut_stream));
+    CU(launch_row_norms(h->d_rows, h->n, n, h->dim, h->pitch, h->d_inv_norm, h->d_stats, h->mut_stream));
+    if (!h->identity) {
+        std::vector<uint64_t> ids(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            ids[i] = first_id + i;
+            h->id_to_pos.emplace(ids[i], static_cast<uint32_t>(h->n + i));
+        }
+        h->ids_host.insert(h->ids_host.end(), ids.begin(), ids.end());
+        CU(cudaMemcpyAsync(h->d_ids + h->n, ids.data(), n * 8, cudaMemcpyHostToDevice, h->mut_stream));
+    }
+    CU(cudaStreamSynchronize(h->mut_stream));
+    h->stats[ST_LAUNCHES] += 2;
+    const uint64_t last = first_id + n - 1;
+    if (!h->have_max || last > h->max_id) { h->max_id = last; h->have_max = true; }
+    h->n += n;
+    return VL_OK;
+}
+
+int vl_index_build(vl_index* h) {
+    if (!h) return fail(VL_ERR_INVALID, "null handle");
+    if (h->type != VL_INDEX_HNSW) return VL_OK;
+    DeviceGuard dg(h->device);
+    int st = hnsw_upload(h->hnsw.get(), h->mut_stream);
+    if (st) return fail(st, "hnsw graph upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return VL_OK;
+}
+
+int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                    uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+    if (!h || (nq && (!queries || !out_counts)) || (nq && k && (!out_ids || !out_scores)))
+        return fail(VL_ERR_INVALID, "null argument");
+    if (metric < 0 || metric > 3) return fail(VL_ERR_INVALID, "unknown metric %d", metric);
+    if (h->type == VL_INDEX_HNSW) {
+        // hnsw.rs:416-434: dimension (always), metric, empty
+        if (qdim != h->dim) return fail(VL_ERR_DIM, "Dimension mismatch: expected %u, got %u", h->dim, qdim);
+        if (metric != h->hnsw_metric)
+            return fail(VL_ERR_METRIC_MISMATCH, "Metric mismatch: requested %d, index built for %d", metric, h->hnsw_metric);
+        for (size_t i = 0; i < static_cast<size_t>(nq) * k; ++i) { out_ids[i] = ~0ull; out_scores[i] = 0.0; }
+        for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+        if (hnsw_live(h->hnsw.get()) == 0 || k == 0 || nq == 0) return VL_OK;
+        DeviceGuard dg(h->device);
+        int st = hnsw_upload(h->hnsw.get(), h->mut_stream);
+        if (st) return fail(st, "hnsw graph upload failed");
+        uint64_t visited = 0, launches = 0;
+        st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, queries, nq, k, ef, out_ids, out_scores,
+                              out_counts, h->mut_stream, &visited, &launches);
+        h->stats[ST_HNSW_VISITED] = visited;
+        h->stats[ST_LAUNCHES] += launches;
+        if (st) return fail(st, "hnsw search failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return VL_OK;
+    }
+    return flat_search(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
+}
+
+int vl_index_search_f64(vl_index* h, const double* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                        uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+    if (!queries && nq) return fail(VL_ERR_INVALID, "null argument");
+    std::vector<float> f(static_cast<size_t>(nq) * qdim);
+    for (size_t i = 0; i < f.size(); ++i) f[i] = static_cast<float>(queries[i]);
+    return vl_index_search(h, f.data(), nq, qdim, k, metric, ef, out_ids, out_scores, out_counts);
+}
+
+int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric, uint32_t ef,
+                           uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                           uint32_t* d_out_counts, uint32_t* d_out_flags, void* cuda_stream) {
+    (void)ef;
+    if (!h || !d_queries || !d_out_ids || !d_out_scores || !d_out_counts || !d_out_flags)
+        return fail(VL_ERR_INVALID, "null argument");
+    if (metric < 0 || metric > 3) return fail(VL_ERR_INVALID, "unknown metric %d", metric);
+    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "search_device: flat indexes only");
+    if (h->n == 0 || k == 0 || nq == 0) return fail(VL_ERR_INVALID, "empty index, k == 0 or nq == 0");
+    if (k > 256) return fail(VL_ERR_UNSUPPORTED, "search_device supports k <= 256");
+    DeviceGuard dg(h->device);
+    Slot& s = h->dev_slot;
+    cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s.stream;
+    const FlatView v = view_of(h);
+    const int Kp = pick_kp(k);
+    const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
+    const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
+    for (uint32_t q0 = 0; q0 < nq; q0 += NQ_CHUNK) {
+        const uint32_t m = std::min(NQ_CHUNK, nq - q0);
+        // scratch only (no query / output staging): reserve with k = 0 sized outputs
+        int st;
+        if ((st = grow_dev(s.cand, s.cand_cap, static_cast<size_t>(m) * grid_x * Kp))) return st;
+        if ((st = grow_dev(s.cand_count, s.cc_cap, static_cast<size_t>(m) * grid_x))) return st;
+        if (m > s.ctl_cap) {
+            if ((st = grow_dev(s.ctl, s.ctl_cap, NQ_CHUNK))) return st;
+            CU(cudaMemsetAsync(s.ctl, 0, NQ_CHUNK * sizeof(QueryCtl), stream));
+        }
+        ScanWork w{s.cand, s.cand_count, s.ctl, grid_x, Kp};
+        SearchOut out{d_out_ids + static_cast<size_t>(q0) * k, d_out_scores + static_cast<size_t>(q0) * k,
+                      d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
+                      d_out_flags + q0};
+        const float* dq = d_queries + static_cast<size_t>(q0) * h->pitch;
+        const bool prof = h->profiling && h->prof_n < h->prof_ev.size() / 2;
+        if (prof) CU(cudaEventRecord(h->prof_ev[2 * h->prof_n], stream));
+        CU(launch_flat_scan(v, dq, m, metric, w, stream));
+        if (prof) {
+            CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
+            h->prof_n += 1;
+        }
+        CU(launch_flat_finalize(v, dq, m, k, metric, w, out, 1.0f, stream));
+        h->stats[ST_LAUNCHES] += 2;
+    }
+    return VL_OK;
+}
+
+int vl_merge_topk_device(int device, uint32_t G, uint32_t nq, uint32_t k, const uint64_t* d_ids,
+                         const double* d_scores, const uint64_t* d_pos, const uint32_t* d_counts,
+                         uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                         uint32_t* d_out_counts, void* cuda_stream) {
+    if (!d_ids || !d_scores || !d_pos || !d_counts || !d_out_ids || !d_out_scores || !d_out_counts)
+        return fail(VL_ERR_INVALID, "null argument");
+    DeviceGuard dg(device);
+    CU(launch_merge_topk(G, nq, k, d_ids, d_scores, d_pos, d_counts, d_out_ids, d_out_scores, d_out_pos,
+                         d_out_counts, static_cast<cudaStream_t>(cuda_stream)));
+    return VL_OK;
+}
+
+uint64_t vl_index_len(const vl_index* h) {
+    if (!h) return 0;
+    return h->type == VL_INDEX_HNSW ? hnsw_live(h->hnsw.get()) : h->n;
+}
+uint32_t vl_index_dim(const vl_index* h) { return h ? h->dim : 0; }
+int vl_index_type_of(const vl_index* h) { return h ? h->type : -1; }
+int vl_index_metric(const vl_index* h) { return h && h->type == VL_INDEX_HNSW ? h->hnsw_metric : -1; }
+int vl_index_device(const vl_index* h) { return h ? h->device : -1; }
+
+int vl_index_max_id(const vl_index* h, uint64_t* out_id) {
+    if (!h || !out_id) return fail(VL_ERR_INVALID, "null argument");
+    if (h->type == VL_INDEX_HNSW) {
+        if (!hnsw_max_id(h->hnsw.get(), out_id)) return fail(VL_ERR_NOT_FOUND, "index is empty");
+        return VL_OK;
+    }
+    if (!h->have_max || h->n == 0) return fail(VL_ERR_NOT_FOUND, "index is empty");
+    *out_id = h->max_id;
+    return VL_OK;
+}
+
+int vl_index_get_vector(const vl_index* h, uint64_t id, float* out_values) {
+    if (!h || !out_values) return fail(VL_ERR_INVALID, "null argument");
+    uint32_t pos;
+    if (h->type == VL_INDEX_HNSW) {
+        uint64_t ix;
+        if (!hnsw_index_of(h->hnsw.get(), id, &ix)) return fail(VL_ERR_NOT_FOUND, "Vector ID %llu does not exist", static_cast<unsigned long long>(id));
+        pos = static_cast<uint32_t>(ix);
+    } else if (!find_pos(h, id, &pos)) {
+        return fail(VL_ERR_NOT_FOUND, "Vector ID %llu does not exist", static_cast<unsigned long long>(id));
+    }
+    DeviceGuard dg(h->device);
+    CU(cudaMemcpy(out_values, h->d_rows + static_cast<size_t>(pos) * h->pitch, h->dim * sizeof(float), cudaMemcpyDeviceToHost));
+    return VL_OK;
+}
+
+int vl_index_export(const vl_index* h, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows,
+                    uint64_t* out_n) {
+    if (!h || !out_n) return fail(VL_ERR_INVALID, "null argument");
+    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "export: flat indexes only");
+    const uint64_t m = first >= h->n ? 0 : std::min(cap, h->n - first);
+    *out_n = m;
+    if (m == 0) return VL_OK;
+    DeviceGuard dg(h->device);
+    if (out_rows)
+        CU(cudaMemcpy2D(out_rows, h->dim * sizeof(float), h->d_rows + first * h->pitch, h->pitch * sizeof(float),
+                        h->dim * sizeof(float), m, cudaMemcpyDeviceToHost));
+    if (out_ids)
+        for (uint64_t i = 0; i < m; ++i) out_ids[i] = h->identity ? h->id_base + first + i : h->ids_host[first + i];
+    return VL_OK;
+}
+
+int vl_index_set_mode(vl_index* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(VL_ERR_INVALID, "bad mode");
+    h->mode = mode;
+    return VL_OK;
+}
+int vl_index_set_pos_base(vl_index* h, uint64_t base) {
+    if (!h) return fail(VL_ERR_INVALID, "null handle");
+    h->pos_base = base;
+    return VL_OK;
+}
+int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n) {
+    if (!h || !out) return fail(VL_ERR_INVALID, "null argument");
+    for (uint32_t i = 0; i < n; ++i) out[i] = i < ST_N ? h->stats[i].load() : 0;
+    return VL_OK;
+}
+int vl_index_set_profiling(vl_index* h, int enabled) {
+    if (!h) return fail(VL_ERR_INVALID, "null handle");
+    DeviceGuard dg(h->device);
+    if (enabled && h->prof_ev.empty()) {
+        h->prof_ev.resize(2048);
+        for (auto& e : h->prof_ev) CU(cudaEventCreate(&e));
+    }
+    h->profiling = enabled != 0;
+    h->prof_n = 0;
+    return VL_OK;
+}
+int vl_index_profile_read(vl_index* h, double* out_ms_total, uint64_t* out_launches) {
+    if (!h || !out_ms_total || !out_launches) return fail(VL_ERR_INVALID, "null argument");
+    DeviceGuard dg(h->device);
+    double tot = 0.0;
+    for (size_t i = 0; i < h->prof_n; ++i) {
+        CU(cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    *out_ms_total = tot;
+    *out_launches = h->prof_n;
+    h->prof_n = 0;
+    return VL_OK;
+}
+int vl_index_device_rows(const vl_index* h, const float** d_rows, uint32_t* pitch) {
+    if (!h || !d_rows || !pitch) return fail(VL_ERR_INVALID, "null argument");
+    *d_rows = h->d_rows;
+    *pitch = h->pitch;
+    return VL_OK;
+}
+
+}  // extern "C"

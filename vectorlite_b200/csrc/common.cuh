@@ -1,0 +1,86 @@
+// common.cuh — shared device/host helpers for the VectorLite B200 hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace vl {
+
+enum Metric : int { COSINE = 0, EUCLIDEAN = 1, MANHATTAN = 2, DOT = 3 };
+
+// flag bits written per query by the finalize kernels
+constexpr uint32_t FLAG_CERT_FAIL = 1u;   // optimality certificate failed → re-run exact
+constexpr uint32_t FLAG_NONFINITE = 2u;   // a non-finite approximate score was seen
+constexpr uint32_t FLAG_NAN = 4u;         // an exact similarity is NaN (reference panics)
+constexpr uint32_t FLAG_OVERFLOW = 8u;    // a candidate buffer overflowed → re-run exact
+
+constexpr uint32_t INVALID_POS = 0xFFFFFFFFu;
+
+// ---- order-preserving float ↔ unsigned maps (larger unsigned == larger float) -----------
+__host__ __device__ __forceinline__ uint32_t f32_orderable(float f) {
+#ifdef __CUDA_ARCH__
+    const uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float orderable_f32(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t f64_orderable(double d) {
+#ifdef __CUDA_ARCH__
+    const uint64_t u = static_cast<uint64_t>(__double_as_longlong(d));
+#else
+    uint64_t u;
+    memcpy(&u, &d, 8);
+#endif
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// 64-bit selection key of the approximate scan: high word = orderable fp32 score, low word =
+// ~position, so that "larger key" == "higher score, then EARLIER storage position" — the
+// stable-sort tie-break of src/index/flat.rs:116.  Key 0 is never a real key (pos <= 2^32-2).
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t pos) {
+    return (static_cast<uint64_t>(f32_orderable(score)) << 32) | (0xFFFFFFFFu - pos);
+}
+__host__ __device__ __forceinline__ uint32_t key_pos(uint64_t key) {
+    return 0xFFFFFFFFu - static_cast<uint32_t>(key);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+    return orderable_f32(static_cast<uint32_t>(key >> 32));
+}
+
+// per-(workspace slot, query) control block shared by the scan CTAs
+struct QueryCtl {
+    unsigned long long tau;  // running lower bound of the K'-th best key over the whole grid
+    unsigned int flags;
+    unsigned int done;
+};
+
+// per-index statistics maintained on the device at insert time (certificate inputs)
+struct ArenaStats {
+    unsigned long long max_norm_sq_bits;     // max  ‖row‖² (f64 bit pattern; positive ⇒ int-ordered)
+    unsigned long long min_nz_norm_sq_bits;  // min  ‖row‖² over rows with non-zero norm
+    unsigned int nonfinite_rows;
+    unsigned int pad;
+};
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (each byte is used once)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+}  // namespace vl

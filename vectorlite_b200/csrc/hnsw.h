@@ -1,0 +1,32 @@
+// hnsw.h — internal interface of the HNSW half of a vl_index handle (host graph builder +
+// device search).  Mirrors HNSWIndex (src/index/hnsw.rs:197-518) on top of the shared arena.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+
+namespace vl {
+
+struct HnswState;
+struct HnswDeleter {
+    void operator()(HnswState* s) const;
+};
+using HnswPtr = std::unique_ptr<HnswState, HnswDeleter>;
+
+HnswState* hnsw_state_create(uint32_t dim, int metric, uint32_t M, uint32_t M0, uint32_t ef_construction);
+void hnsw_state_release_device(HnswState* s);
+bool hnsw_has_id(const HnswState* s, uint64_t id);
+bool hnsw_index_of(const HnswState* s, uint64_t id, uint64_t* internal_index);
+bool hnsw_max_id(const HnswState* s, uint64_t* out);
+uint64_t hnsw_live(const HnswState* s);
+// append n rows (host f32 [n][dim]) to the graph; internal index == arena position
+int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n);
+bool hnsw_soft_delete(HnswState* s, uint64_t id);
+// flatten + upload the graph if it changed since the last upload
+int hnsw_upload(HnswState* s, cudaStream_t stream);
+int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,
+                     uint32_t k, uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
+                     cudaStream_t stream, uint64_t* visited, uint64_t* launches);
+
+}  // namespace vl

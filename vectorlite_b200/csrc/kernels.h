@@ -1,0 +1,85 @@
+// kernels.h — internal launch interface between the C ABI (api.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace vl {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_CTAS_PER_SM = 3;   // 85 regs/thread: no spills with 8 rows × float4 in flight
+constexpr int SCAN_ROWS_PER_WARP = 8;
+constexpr int SCAN_TILE_ROWS = (SCAN_THREADS / 32) * SCAN_ROWS_PER_WARP;  // 64
+constexpr int SCAN_CAP = 1024;            // candidate buffer entries per CTA
+constexpr int SCAN_TILES_PER_CHECK = 4;   // CTA-wide barrier every 4 tiles
+constexpr int SCAN_LIMIT = SCAN_CAP - SCAN_TILES_PER_CHECK * SCAN_TILE_ROWS;  // 768
+constexpr int KP_MAX = 512;               // max over-selected candidates per query (K')
+constexpr int FIN_THREADS = 512;
+
+struct FlatView {          // device-resident flat store (one shard)
+    const float* rows;     // [n][pitch] fp32, zero padded to pitch
+    const float* inv_norm; // [n] fp32 1/‖row‖ (0 for zero rows)
+    const uint64_t* ids;   // [n] or nullptr when id == id_base + pos
+    const ArenaStats* stats;
+    uint64_t id_base;
+    uint64_t pos_base;
+    uint32_t n;
+    uint32_t dim;
+    uint32_t pitch;        // floats, multiple of 4
+};
+
+struct ScanWork {          // per workspace slot
+    uint64_t* cand;        // [nq][grid_x][Kp]
+    uint32_t* cand_count;  // [nq][grid_x]
+    QueryCtl* ctl;         // [nq]
+    int grid_x;
+    int Kp;
+};
+
+struct SearchOut {         // device outputs, [nq][k]
+    uint64_t* ids;
+    double* scores;
+    uint64_t* pos;         // may be nullptr
+    uint32_t* counts;      // [nq]
+    uint32_t* flags;       // [nq]
+};
+
+// single-query-per-CTA-column fp32 streaming scan (grid = grid_x × nq)
+cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t nq, int metric,
+                             const ScanWork& w, cudaStream_t s);
+// merge per-CTA candidates, fp64 rescore in reference order, rank, certify (grid = nq)
+cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k,
+                                 int metric, const ScanWork& w, const SearchOut& out, float eps_scale,
+                                 cudaStream_t s);
+size_t flat_scan_smem_bytes(uint32_t pitch);
+int flat_scan_max_grid_x(int device, uint32_t pitch);
+
+// exact path: every row scored in f64 in reference order
+cudaError_t launch_exact_scores(const FlatView& v, const float* d_query, int metric, double* d_scores,
+                                uint32_t* d_flags, cudaStream_t s);
+// stable select of the top-k of d_scores[n] → out (single query q_index of the out arrays)
+struct ExactScratch {
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    uint64_t* keys_in = nullptr;
+    uint64_t* keys_out = nullptr;
+    uint32_t* vals_in = nullptr;
+    uint32_t* vals_out = nullptr;
+    size_t cap = 0;
+};
+cudaError_t exact_select(const FlatView& v, const double* d_scores, uint32_t k, ExactScratch& sc,
+                         const SearchOut& out, uint32_t q_index, cudaStream_t s);
+void exact_scratch_free(ExactScratch& sc);
+
+// insert-time kernels
+cudaError_t launch_row_norms(float* rows, uint64_t first, uint64_t n, uint32_t dim, uint32_t pitch,
+                             float* inv_norm, ArenaStats* stats, cudaStream_t s);
+cudaError_t launch_synth_fill(float* rows, uint64_t first_pos, uint64_t n, uint32_t dim, uint32_t pitch,
+                              uint64_t seed, uint64_t first_row, uint32_t clusters, cudaStream_t s);
+cudaError_t launch_merge_topk(uint32_t G, uint32_t nq, uint32_t k, const uint64_t* ids,
+                              const double* scores, const uint64_t* pos, const uint32_t* counts,
+                              uint64_t* out_ids, double* out_scores, uint64_t* out_pos,
+                              uint32_t* out_counts, cudaStream_t s);
+
+}  // namespace vl

@@ -1,0 +1,132 @@
+"""Row-sharded flat index: one process per GPU, contiguous row ranges, per-shard top-k exchanged
+with ONE all-gather over NCCL (NVLink/NVSwitch) and merged by a device kernel.
+
+The reference has no multi-device path; this is the shard-aware routing the north
+star adds.  Rows are independent and top-k is a decomposable reduction, so the only exchange is
+nq·k·(8+8+8) bytes per rank.  Global storage position = shard base + local position keeps the
+reference's stable-sort tie-break (flat.rs:116) exact across shards.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import FlatIndex, SimilarityMetric, VectorLiteError, lib, _err, VL_OK
+
+
+def shard_range(n_total: int, world: int, rank: int):
+    """Contiguous row range [lo, hi) owned by `rank` (same rule on every rank)."""
+    per, rem = divmod(n_total, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+class ShardedFlatIndex:
+    def __init__(self, dim: int, rank: Optional[int] = None, world: Optional[int] = None,
+                 device: Optional[int] = None, group=None):
+        self.group = group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.device = torch.cuda.current_device() if device is None else device
+        self.dim = dim
+        self.local = FlatIndex(dim, device=self.device)
+        self.base = 0
+        self._bufs = {}
+
+    def fill_synthetic(self, seed: int, n_total: int, clusters: int = 0):
+        lo, hi = shard_range(n_total, self.world, self.rank)
+        self.base = lo
+        self.local.fill_synthetic(seed, hi - lo, first_row=lo, clusters=clusters, first_id=lo)
+        self.local.set_pos_base(lo)
+
+    def add_shard(self, ids, rows, base: int):
+        self.base = base
+        self.local.add_batch(ids, rows)
+        self.local.set_pos_base(base)
+
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            dev = torch.device("cuda", self.device)
+            G = self.world
+            self._bufs[key] = dict(
+                ids=torch.zeros((G, nq, k), dtype=torch.int64, device=dev),
+                sc=torch.zeros((G, nq, k), dtype=torch.float64, device=dev),
+                pos=torch.zeros((G, nq, k), dtype=torch.int64, device=dev),
+                cnt=torch.zeros((G, nq), dtype=torch.int32, device=dev),
+                flg=torch.zeros((G, nq), dtype=torch.int32, device=dev),
+                o_ids=torch.zeros((nq, k), dtype=torch.int64, device=dev),
+                o_sc=torch.zeros((nq, k), dtype=torch.float64, device=dev),
+                o_pos=torch.zeros((nq, k), dtype=torch.int64, device=dev),
+                o_cnt=torch.zeros((nq,), dtype=torch.int32, device=dev),
+            )
+        return self._bufs[key]
+
+    def search_device(self, d_queries: torch.Tensor, k: int, metric: SimilarityMetric):
+        """d_queries: [nq, dim] fp32 CUDA tensor (replicated on every rank).  The shard kernel writes
+        its top-k straight into this rank's slot of the all-gather buffer; returns device tensors
+        (ids, scores, counts, flags) valid on every rank.  No host synchronisation."""
+        nq = d_queries.shape[0]
+        b = self._buffers(nq, k)
+        r = self.rank
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world == 1:  # single shard: the local result is already the global one
+            self.local.search_device(d_queries.data_ptr(), nq, k, metric, b["o_ids"].data_ptr(),
+                                     b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
+                                     b["flg"][0].data_ptr(), stream)
+            return b["o_ids"], b["o_sc"], b["o_cnt"], b["flg"]
+        self.local.search_device(d_queries.data_ptr(), nq, k, metric, b["ids"][r].data_ptr(),
+                                 b["sc"][r].data_ptr(), b["pos"][r].data_ptr(), b["cnt"][r].data_ptr(),
+                                 b["flg"][r].data_ptr(), stream)
+        if self.world > 1:
+            for name in ("ids", "sc", "pos", "cnt", "flg"):
+                t = b[name]
+                dist.all_gather_into_tensor(t.view(-1), t[r].reshape(-1).clone(), group=self.group)
+        st = lib().vl_merge_topk_device(self.device, self.world, nq, k, b["ids"].data_ptr(), b["sc"].data_ptr(),
+                                        b["pos"].data_ptr(), b["cnt"].data_ptr(), b["o_ids"].data_ptr(),
+                                        b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
+                                        C.c_void_p(stream))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        return b["o_ids"], b["o_sc"], b["o_cnt"], b["flg"]
+
+    def search(self, queries: np.ndarray, k: int, metric: SimilarityMetric):
+        """Host in / host out (the e2e path): H2D of the queries, sharded search, D2H of the merged
+        top-k.  A shard whose certificate fails re-runs its queries through the exact path."""
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).pin_memory()
+        d_q = q.to(torch.device("cuda", self.device), non_blocking=True)
+        ids, sc, cnt, flg = self.search_device(d_q, k, metric)
+        h_ids, h_sc, h_cnt, h_flg = ids.cpu(), sc.cpu(), cnt.cpu(), flg.cpu()
+        if int(h_flg.max()) != 0:
+            return self._search_exact(queries, k, metric)
+        return h_ids.numpy().view(np.uint64), h_sc.numpy(), h_cnt.numpy().view(np.uint32)
+
+    def _search_exact(self, queries, k, metric):
+        # every rank saw the same gathered flags → all ranks take this branch together
+        gi, gs, gc = self.local.search_batch(queries, k, metric)  # host API handles the fallback
+        nq = queries.shape[0]
+        b = self._buffers(nq, k)
+        r = self.rank
+        dev = torch.device("cuda", self.device)
+        b["ids"][r].copy_(torch.from_numpy(gi.view(np.int64)).to(dev))
+        b["sc"][r].copy_(torch.from_numpy(gs).to(dev))
+        pos = gi.astype(np.int64)  # sharded stores use id == global position
+        b["pos"][r].copy_(torch.from_numpy(pos).to(dev))
+        b["cnt"][r].copy_(torch.from_numpy(gc.view(np.int32)).to(dev))
+        if self.world > 1:
+            for name in ("ids", "sc", "pos", "cnt"):
+                t = b[name]
+                dist.all_gather_into_tensor(t.view(-1), t[r].reshape(-1).clone(), group=self.group)
+        stream = torch.cuda.current_stream().cuda_stream
+        st = lib().vl_merge_topk_device(self.device, self.world, nq, k, b["ids"].data_ptr(), b["sc"].data_ptr(),
+                                        b["pos"].data_ptr(), b["cnt"].data_ptr(), b["o_ids"].data_ptr(),
+                                        b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
+                                        C.c_void_p(stream))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        return (b["o_ids"].cpu().numpy().view(np.uint64), b["o_sc"].cpu().numpy(),
+                b["o_cnt"].cpu().numpy().view(np.uint32))
