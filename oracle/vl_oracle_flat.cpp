@@ -196,7 +196,7 @@ void vlo_synth_rows_f32(uint64_t seed, uint64_t row0, size_t n, size_t dim, uint
                      : 0;
         for (size_t c = 0; c < dim; ++c) {
             int64_t x = ih4(seed, row, c);
-            if (clusters) x += 4 * ih4(seed ^ 0x5851F42D4C957F2DULL, centre, c);
+            if (clusters) x += 4 * ih4(0x5851F42D4C957F2DULL, centre, c);  // centres do not depend on seed
             v[c] = x;
             ss += static_cast<uint64_t>(x * x);
         }

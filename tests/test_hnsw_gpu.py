@@ -1,0 +1,136 @@
+"""GPU tests of the HNSW path through the C ABI: the reference's own HNSW unit-test semantics
+(src/index/hnsw.rs:529-805) and the recall bar — recall@10 vs exact flat no lower than the oracle
+restatement of the reference's HNSW (crate hnsw 0.11 + u64-quantised functors) at equal
+(M, M0, ef_construction, ef)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vl():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import vectorlite_b200
+    vectorlite_b200.lib()
+    return vectorlite_b200
+
+
+def _recall(found_ids, counts, truth):
+    hit = 0
+    for qi in range(truth.shape[0]):
+        hit += len(set(int(x) for x in found_ids[qi, :int(counts[qi])]) & set(int(x) for x in truth[qi]))
+    return hit / truth.size
+
+
+def test_reference_unit_semantics(vl, kats):
+    M = vl.SimilarityMetric
+    h = vl.HNSWIndex(3, M.Euclidean)                                # hnsw.rs:530-534
+    assert h.is_empty() and h.dimension() == 3 and h.metric() == M.Euclidean
+    assert h.search([1.0, 2.0, 3.0], 5, M.Euclidean) == []          # hnsw.rs:596-602 empty index
+    with pytest.raises(ValueError, match="dimension"):              # hnsw.rs:547-557
+        h.add(vl.Vector(1, [1.0, 2.0]))
+    assert h.len() == 0
+    case = kats["hnsw"]["id_mapping"]                               # hnsw.rs:605-634
+    for r in case["rows"]:
+        h.add(vl.Vector(r["id"], r["values"], "test"))
+    assert h.len() == 4 and h.max_id() == 400
+    for i in (100, 200, 300, 400):
+        assert h.get_vector(i) is not None
+    assert h.get_vector(999) is None
+    res = h.search(case["query"], 2, M.Euclidean)
+    assert 1 <= len(res) <= 2 and res[0].id == 100 and res[0].text == "test"
+    assert all(res[i - 1].score >= res[i].score for i in range(1, len(res)))
+    # our score is the exact flat similarity; the reference quantises the distance to 1e-3
+    assert abs(res[0].score - case["scores_by_row"][0]) < 2e-3
+    with pytest.raises(ValueError, match="already exists"):         # hnsw.rs:637-646
+        h.add(vl.Vector(100, [4.0, 5.0, 6.0]))
+    with pytest.raises(vl.MetricMismatch):                          # hnsw.rs:425-430
+        h.search(case["query"], 2, M.Cosine)
+    with pytest.raises(vl.DimensionMismatch):                       # hnsw.rs:416-421 (always)
+        h.search([1.0, 2.0], 2, M.Euclidean)
+    res = h.search(case["query"], 50, M.Euclidean)                  # hnsw.rs:776-805: k > n is fine
+    assert 1 <= len(res) <= 4
+    with pytest.raises(ValueError, match="does not exist"):         # hnsw.rs:649-662
+        h.delete(999)
+    h.delete(100)
+    assert h.len() == 3 and h.get_vector(100) is None
+    res = h.search(case["query"], 4, M.Euclidean)                   # soft delete filters results
+    assert 100 not in [r.id for r in res] and len(res) <= 3
+    w = vl.VectorIndexWrapper(h)
+    assert w.metric() == M.Euclidean and w.index_type() == vl.IndexType.HNSW
+    e = vl.HNSWIndex(3, M.Euclidean)
+    assert e.search([1.0, 2.0, 3.0], 5, M.Euclidean) == []
+    with pytest.raises(ValueError):
+        vl.HNSWIndex(0, M.Cosine)                                   # hnsw.rs:217-219 panics
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+def test_recall_vs_flat_and_reference_restatement(vl, oracle_mod, metric):
+    n, dim, k, nq = 20000, 64, 10, 200
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=64)
+    queries = oracle_mod.synth_rows(43, 0, nq, dim, clusters=64)
+    ids = np.arange(n, dtype=np.uint64) + 5
+    st, truth, _ = oracle_mod.flat_search_batch(rows, ids, queries, k, metric, nthreads=8)
+    assert st == 0
+    M, M0, efc = 16, 32, 100
+    h = vl.HNSWIndex(dim, vl.SimilarityMetric(metric), M=M, M0=M0, ef_construction=efc)
+    h.add_batch(ids, rows)
+    h.build()
+    assert h.len() == n
+    ref = oracle_mod.HNSW(dim, metric, M=M, M0=M0, ef_construction=efc)
+    assert ref.add_batch(ids, rows) == 0
+    ours, theirs = {}, {}
+    for ef in (0, 32, 128):
+        gi, gs, gc = h.search_batch(queries, k, vl.SimilarityMetric(metric), ef)
+        assert np.all(gc == k)
+        assert np.all(np.diff(gs, axis=1) <= 0)                       # scores non-increasing
+        ours[ef] = _recall(gi, gc, truth)
+        st, ri, _, rc, _ = ref.search_batch(queries, k, ef, nthreads=8)
+        theirs[ef] = _recall(ri, rc, truth)
+        # scores are exact flat similarities for the returned ids
+        for qi in (0, 1):
+            for j in range(k):
+                want = oracle_mod.metric(metric, rows[int(gi[qi, j]) - 5].astype(np.float64), queries[qi].astype(np.float64))
+                assert gs[qi, j] == want
+    print(f"metric={metric} recall@10 ours={ours} reference-restatement={theirs} visited={h.stats()['hnsw_visited']}")
+    for ef in ours:
+        assert ours[ef] >= theirs[ef] - 0.02, (metric, ef, ours, theirs)
+    assert ours[128] >= 0.95 and ours[128] >= ours[0]
+
+
+def test_soft_delete_and_profiles(vl, oracle_mod):
+    n, dim, k = 5000, 32, 10
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=16)
+    q = oracle_mod.synth_rows(43, 0, 4, dim, clusters=16)
+    for profile in ("default", "memory-optimized", "high-accuracy"):     # hnsw.rs:95-109
+        h = vl.HNSWIndex(dim, vl.SimilarityMetric.Cosine, ef_construction=64, profile=profile)
+        h.add_batch(np.arange(n, dtype=np.uint64), rows)
+        gi, gs, gc = h.search_batch(q, k, vl.SimilarityMetric.Cosine, 64)
+        st, truth, _ = oracle_mod.flat_search_batch(rows, None, q, k, 0, nthreads=4)
+        assert _recall(gi, gc, truth) >= 0.9, profile
+        victim = int(gi[0, 0])
+        h.delete(victim)
+        assert h.len() == n - 1
+        gi2, _, gc2 = h.search_batch(q[:1], k, vl.SimilarityMetric.Cosine, 64)
+        assert victim not in [int(x) for x in gi2[0, :int(gc2[0])]]
+        gi3, _, gc3 = h.search_batch(q[:1], k, vl.SimilarityMetric.Cosine, 0)    # reference ef = k
+        assert int(gc3[0]) <= k and victim not in [int(x) for x in gi3[0, :int(gc3[0])]]
+        # incremental add after a search (graph re-upload)
+        h.add(vl.Vector(10**9, q[0]))
+        r = h.search(q[0], 1, vl.SimilarityMetric.Cosine, 32)
+        assert r[0].id == 10**9 and abs(r[0].score - 1.0) < 1e-6
+
+
+def test_dim_384_generic_and_specialised_paths(vl, oracle_mod):
+    for dim in (384, 100):
+        n, k = 8000, 10
+        rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=32)
+        q = oracle_mod.synth_rows(43, 0, 64, dim, clusters=32)
+        h = vl.HNSWIndex(dim, vl.SimilarityMetric.Cosine, ef_construction=100)
+        h.add_batch(np.arange(n, dtype=np.uint64), rows)
+        gi, gs, gc = h.search_batch(q, k, vl.SimilarityMetric.Cosine, 64)
+        st, truth, _ = oracle_mod.flat_search_batch(rows, None, q, k, 0, nthreads=8)
+        assert _recall(gi, gc, truth) >= 0.95, dim

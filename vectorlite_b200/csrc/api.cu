@@ -51,11 +51,14 @@ struct Slot {  // one in-flight search: stream + scratch, all sized on demand
     // scan scratch
     uint64_t* cand = nullptr; size_t cand_cap = 0;
     uint32_t* cand_count = nullptr; size_t cc_cap = 0;
+    uint64_t* cand_max = nullptr; size_t cm_cap = 0;
     QueryCtl* ctl = nullptr; size_t ctl_cap = 0;
-    // outputs (device + pinned mirrors), sized nq_cap × k_cap
+    // outputs: ONE device block + ONE pinned mirror per call, carved as
+    // [ids m*k u64][scores m*k f64][counts m u32][flags m u32] so a single D2H brings everything
+    unsigned char* d_out = nullptr; unsigned char* h_out = nullptr; size_t out_bytes = 0;
     uint64_t* d_ids = nullptr; double* d_scores = nullptr; uint32_t* d_counts = nullptr; uint32_t* d_flags = nullptr;
     uint64_t* h_ids = nullptr; double* h_scores = nullptr; uint32_t* h_counts = nullptr; uint32_t* h_flags = nullptr;
-    size_t out_cap = 0, outq_cap = 0;
+    size_t out_used = 0;
     // exact path
     double* d_exact = nullptr; size_t exact_cap = 0;
     uint32_t* d_exflags = nullptr;
@@ -139,32 +142,36 @@ int slot_reserve(vl_index* h, Slot& s, uint32_t nq, uint32_t k, int Kp, int grid
     }
     if ((st = grow_dev(s.cand, s.cand_cap, static_cast<size_t>(nq) * grid_x * Kp))) return st;
     if ((st = grow_dev(s.cand_count, s.cc_cap, static_cast<size_t>(nq) * grid_x))) return st;
+    if ((st = grow_dev(s.cand_max, s.cm_cap, static_cast<size_t>(nq) * grid_x))) return st;
     if (nq > s.ctl_cap) {
         if ((st = grow_dev(s.ctl, s.ctl_cap, nq))) return st;
         CU(cudaMemsetAsync(s.ctl, 0, nq * sizeof(QueryCtl), s.stream));
     }
     const size_t on = static_cast<size_t>(nq) * std::max<uint32_t>(k, 1);
-    if (on > s.out_cap || nq > s.outq_cap) {
-        cudaFree(s.d_ids); cudaFree(s.d_scores); cudaFree(s.d_counts); cudaFree(s.d_flags);
-        cudaFreeHost(s.h_ids); cudaFreeHost(s.h_scores); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_flags);
-        s.d_ids = nullptr; s.d_scores = nullptr; s.d_counts = nullptr; s.d_flags = nullptr;
-        s.h_ids = nullptr; s.h_scores = nullptr; s.h_counts = nullptr; s.h_flags = nullptr;
-        s.out_cap = s.outq_cap = 0;
-        const size_t oc = std::max(on, s.out_cap), qc = std::max<size_t>(nq, s.outq_cap);
-        CU(cudaMalloc(&s.d_ids, oc * 8)); CU(cudaMalloc(&s.d_scores, oc * 8));
-        CU(cudaMalloc(&s.d_counts, qc * 4)); CU(cudaMalloc(&s.d_flags, qc * 4));
-        CU(cudaMallocHost(&s.h_ids, oc * 8)); CU(cudaMallocHost(&s.h_scores, oc * 8));
-        CU(cudaMallocHost(&s.h_counts, qc * 4)); CU(cudaMallocHost(&s.h_flags, qc * 4));
-        s.out_cap = oc; s.outq_cap = qc;
+    const size_t need = on * 16 + static_cast<size_t>(nq) * 8;
+    if (need > s.out_bytes) {
+        cudaFree(s.d_out); cudaFreeHost(s.h_out);
+        s.d_out = nullptr; s.h_out = nullptr; s.out_bytes = 0;
+        CU(cudaMalloc(&s.d_out, need));
+        CU(cudaMallocHost(&s.h_out, need));
+        s.out_bytes = need;
     }
+    s.d_ids = reinterpret_cast<uint64_t*>(s.d_out);
+    s.d_scores = reinterpret_cast<double*>(s.d_out + on * 8);
+    s.d_counts = reinterpret_cast<uint32_t*>(s.d_out + on * 16);
+    s.d_flags = s.d_counts + nq;
+    s.h_ids = reinterpret_cast<uint64_t*>(s.h_out);
+    s.h_scores = reinterpret_cast<double*>(s.h_out + on * 8);
+    s.h_counts = reinterpret_cast<uint32_t*>(s.h_out + on * 16);
+    s.h_flags = s.h_counts + nq;
+    s.out_used = need;
     if (!s.d_exflags) CU(cudaMalloc(&s.d_exflags, 4));
     return VL_OK;
 }
 
 void slot_free(Slot& s) {
-    cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.ctl);
-    cudaFree(s.d_ids); cudaFree(s.d_scores); cudaFree(s.d_counts); cudaFree(s.d_flags);
-    cudaFreeHost(s.h_ids); cudaFreeHost(s.h_scores); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_flags);
+    cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.cand_max); cudaFree(s.ctl);
+    cudaFree(s.d_out); cudaFreeHost(s.h_out);
     cudaFree(s.d_exact); cudaFree(s.d_exflags);
     exact_scratch_free(s.exs);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -415,15 +422,12 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
         CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
         h->stats[ST_H2D] += qbytes;
         if (fast) {
-            ScanWork w{s.cand, s.cand_count, s.ctl, grid_x, Kp};
+            ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
             SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
             CU(launch_flat_scan(v, s.d_q, m, metric, w, s.stream));
             CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, out, 1.0f, s.stream));
             h->stats[ST_LAUNCHES] += 2;
-            CU(cudaMemcpyAsync(s.h_flags, s.d_flags, m * 4, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_counts, s.d_counts, m * 4, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_ids, s.d_ids, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_scores, s.d_scores, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
             bool any_fail = false;
             for (uint32_t q = 0; q < m; ++q) {
@@ -435,10 +439,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
                         st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
                         if (st) return st;
                     }
-                CU(cudaMemcpyAsync(s.h_flags, s.d_flags, m * 4, cudaMemcpyDeviceToHost, s.stream));
-                CU(cudaMemcpyAsync(s.h_counts, s.d_counts, m * 4, cudaMemcpyDeviceToHost, s.stream));
-                CU(cudaMemcpyAsync(s.h_ids, s.d_ids, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
-                CU(cudaMemcpyAsync(s.h_scores, s.d_scores, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
                 CU(cudaStreamSynchronize(s.stream));
             }
         } else {
@@ -446,10 +447,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
                 st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
                 if (st) return st;
             }
-            CU(cudaMemcpyAsync(s.h_flags, s.d_flags, m * 4, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_counts, s.d_counts, m * 4, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_ids, s.d_ids, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_scores, s.d_scores, static_cast<size_t>(m) * k * 8, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
         }
         h->stats[ST_D2H] += static_cast<size_t>(m) * (k * 16 + 8);
@@ -501,7 +499,7 @@ static int create_common(uint32_t dim, int device, vl_index** out, int type) {
         vl_index_destroy(h);
         return fail(VL_ERR_CUDA, "device init failed: %s", msg);
     }
-    h->max_grid_x = flat_scan_max_grid_x(device, h->pitch);
+    h->max_grid_x = std::min(flat_scan_max_grid_x(device, h->pitch), SCAN_CAP);
     *out = h;
     return VL_OK;
 }
@@ -704,11 +702,12 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
         int st;
         if ((st = grow_dev(s.cand, s.cand_cap, static_cast<size_t>(m) * grid_x * Kp))) return st;
         if ((st = grow_dev(s.cand_count, s.cc_cap, static_cast<size_t>(m) * grid_x))) return st;
+        if ((st = grow_dev(s.cand_max, s.cm_cap, static_cast<size_t>(m) * grid_x))) return st;
         if (m > s.ctl_cap) {
             if ((st = grow_dev(s.ctl, s.ctl_cap, NQ_CHUNK))) return st;
             CU(cudaMemsetAsync(s.ctl, 0, NQ_CHUNK * sizeof(QueryCtl), stream));
         }
-        ScanWork w{s.cand, s.cand_count, s.ctl, grid_x, Kp};
+        ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
         SearchOut out{d_out_ids + static_cast<size_t>(q0) * k, d_out_scores + static_cast<size_t>(q0) * k,
                       d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
                       d_out_flags + q0};

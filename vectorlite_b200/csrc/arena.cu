@@ -67,7 +67,7 @@ __device__ __forceinline__ long long ih4(uint64_t seed, uint64_t row, uint64_t c
 __device__ __forceinline__ long long synth_int(uint64_t seed, uint64_t row, uint64_t centre,
                                                uint32_t clusters, uint32_t col) {
     long long x = ih4(seed, row, col);
-    if (clusters) x += 4 * ih4(seed ^ 0x5851F42D4C957F2Dull, centre, col);
+    if (clusters) x += 4 * ih4(0x5851F42D4C957F2Dull, centre, col);  // centres do not depend on seed
     return x;
 }
 

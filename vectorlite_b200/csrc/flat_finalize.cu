@@ -26,6 +26,7 @@ struct FinalizeParams {
     int metric, Kp, grid_x, CH;  // CH = columns staged per chunk (multiple of 4)
     const uint64_t* cand;
     const uint32_t* cand_count;
+    const uint64_t* cand_max;
     QueryCtl* ctl;
     uint64_t* out_ids;
     double* out_scores;
@@ -60,25 +61,71 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) flat_finalize_kernel(FinalizeP
     QueryCtl* ctl = p.ctl + qi;
 
     // ---- (1) merge -------------------------------------------------------------------
+    // Threshold: the Kp-th largest of the per-CTA maxima is a lower bound of the global Kp-th best
+    // key (Kp distinct rows reach it), and only ~Kp candidates in total lie above it.
     CtaTopK<SCAN_CAP, FIN_THREADS> topk{s_keys, &s_count};
-    topk.init();
-    if (tid == 0) s_nan = 0;
-    unsigned long long tau = ctl->tau;  // every key of the global top-K' is >= tau
-    const uint32_t slots = static_cast<uint32_t>(p.grid_x) * Kp;
+    __shared__ uint32_t s_ccount[SCAN_CAP];
+    __shared__ int s_overflow;
+    const int G = p.grid_x;  // <= SCAN_CAP (host guarantees)
+    const uint32_t slots = static_cast<uint32_t>(G) * Kp;
     const uint64_t* cand = p.cand + static_cast<size_t>(qi) * slots;
-    const uint32_t* ccount = p.cand_count + static_cast<size_t>(qi) * p.grid_x;
-    for (uint32_t s0 = 0; s0 < slots; s0 += FIN_THREADS) {
-        __syncthreads();
-        if (s_count > SCAN_CAP - FIN_THREADS) {
-            const unsigned long long t = topk.compact(Kp, false);
-            tau = t > tau ? t : tau;
+    const uint32_t* ccount = p.cand_count + static_cast<size_t>(qi) * G;
+    const uint64_t* cmax = p.cand_max + static_cast<size_t>(qi) * G;
+    for (int i = tid; i < SCAN_CAP; i += FIN_THREADS) {
+        s_keys[i] = i < G ? cmax[i] : 0ull;
+        s_ccount[i] = i < G ? ccount[i] : 0u;
+    }
+    if (tid == 0) { s_nan = 0; s_overflow = 0; s_count = 0; }
+    __syncthreads();
+    unsigned long long tau = ctl->tau;  // every key of the global top-K' is >= tau
+    if (G >= Kp) {
+        int len = 2;
+        while (len < G) len <<= 1;
+        topk.sort_desc(len);
+        const unsigned long long t1 = s_keys[Kp - 1];
+        tau = t1 > tau ? t1 : tau;
+    }
+    __syncthreads();
+    topk.init();
+    {   // optimistic single pass: coalesced, barrier-free, 8 independent loads in flight per thread
+        constexpr int U = 8;
+        for (uint32_t s0 = 0; s0 < slots; s0 += FIN_THREADS * U) {
+            unsigned long long key[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t s = s0 + u * FIN_THREADS + tid;
+                key[u] = 0ull;
+                if (s < slots) {
+                    const uint32_t c = s / Kp, e = s - c * Kp;
+                    if (e < s_ccount[c]) key[u] = cand[s];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (key[u] != 0ull && key[u] >= tau) {
+                    const int i = atomicAdd(&s_count, 1);
+                    if (i < SCAN_CAP) s_keys[i] = key[u]; else s_overflow = 1;
+                }
+            }
         }
-        const uint32_t s = s0 + tid;
-        if (s < slots) {
-            const uint32_t c = s / Kp, e = s - c * Kp;
-            if (e < ccount[c]) {
-                const unsigned long long key = cand[s];
-                if (key >= tau) topk.push(key);
+    }
+    __syncthreads();
+    if (s_overflow) {  // rare (at most Kp lists can reach tau, but each may hold Kp entries): bounded rounds
+        __syncthreads();
+        topk.init();
+        for (uint32_t s0 = 0; s0 < slots; s0 += FIN_THREADS) {
+            __syncthreads();
+            if (s_count > SCAN_CAP - FIN_THREADS) {
+                const unsigned long long t = topk.compact(Kp, false);
+                tau = t > tau ? t : tau;
+            }
+            const uint32_t s = s0 + tid;
+            if (s < slots) {
+                const uint32_t c = s / Kp, e = s - c * Kp;
+                if (e < s_ccount[c]) {
+                    const unsigned long long key = cand[s];
+                    if (key >= tau) topk.push(key);
+                }
             }
         }
     }
@@ -95,12 +142,31 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) flat_finalize_kernel(FinalizeP
     for (uint32_t c0 = 0; c0 < p.dim; c0 += CH) {
         const int w = min(static_cast<uint32_t>(CH), p.dim - c0);   // live columns in this chunk
         const int w4 = (w + 3) >> 2;                                // float4s (pitch is padded)
-        for (int i = tid; i < nc * w4; i += FIN_THREADS) {
-            const int r = i / w4, c4 = i - r * w4;
-            const float4 v = *reinterpret_cast<const float4*>(
-                p.rows + static_cast<size_t>(s_pos[r]) * p.pitch + c0 + c4 * 4);
-            float* t = s_tile + r * TS + c4 * 4;
-            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        {
+            constexpr int U = 4;
+            const int total = nc * w4;
+            for (int i0 = 0; i0 < total; i0 += FIN_THREADS * U) {
+                float4 v[U];
+                int rr[U], cc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * FIN_THREADS + tid;
+                    rr[u] = -1;
+                    if (i < total) {
+                        rr[u] = i / w4;
+                        cc[u] = i - rr[u] * w4;
+                        v[u] = *reinterpret_cast<const float4*>(
+                            p.rows + static_cast<size_t>(s_pos[rr[u]]) * p.pitch + c0 + cc[u] * 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (rr[u] >= 0) {
+                        float* t = s_tile + rr[u] * TS + cc[u] * 4;
+                        t[0] = v[u].x; t[1] = v[u].y; t[2] = v[u].z; t[3] = v[u].w;
+                    }
+                }
+            }
         }
         for (int i = tid; i < w; i += FIN_THREADS) s_q[i] = q[c0 + i];
         __syncthreads();
@@ -252,7 +318,7 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
     p.id_base = v.id_base; p.pos_base = v.pos_base;
     p.n = v.n; p.dim = v.dim; p.pitch = v.pitch; p.k = k;
     p.metric = metric; p.Kp = w.Kp; p.grid_x = w.grid_x; p.CH = CH;
-    p.cand = w.cand; p.cand_count = w.cand_count; p.ctl = w.ctl;
+    p.cand = w.cand; p.cand_count = w.cand_count; p.cand_max = w.cand_max; p.ctl = w.ctl;
     p.out_ids = out.ids; p.out_scores = out.scores; p.out_pos = out.pos;
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = eps_scale;

@@ -71,7 +71,7 @@ template <int METRIC, int NCH>
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM)
 flat_scan_kernel(const float4* __restrict__ rows, const float* __restrict__ inv_norm,
                  const float4* __restrict__ queries, uint32_t n, uint32_t pitch4, uint64_t* cand,
-                 uint32_t* cand_count, QueryCtl* ctl_all, int Kp) {
+                 uint32_t* cand_count, uint64_t* cand_max, QueryCtl* ctl_all, int Kp) {
     constexpr int R = SCAN_ROWS_PER_WARP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -182,8 +182,23 @@ flat_scan_kernel(const float4* __restrict__ rows, const float* __restrict__ inv_
     const int any_nf = __syncthreads_or(nonfinite ? 1 : 0);
     const int n_out = s_count;
     const size_t slot = static_cast<size_t>(qi) * gridDim.x + blockIdx.x;
-    for (int i = tid; i < n_out; i += SCAN_THREADS) cand[slot * Kp + i] = s_keys[i];
+    unsigned long long best = 0ull;
+    for (int i = tid; i < n_out; i += SCAN_THREADS) {
+        const unsigned long long key = s_keys[i];
+        cand[slot * Kp + i] = key;
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        best = other > best ? other : best;
+    }
+    if (tid == 0) s_tau = 0ull;
+    __syncthreads();
+    if (lane == 0 && best) atomicMax(&s_tau, best);
+    __syncthreads();
     if (tid == 0) {
+        cand_max[slot] = s_tau;
         cand_count[slot] = static_cast<uint32_t>(n_out);
         if (tau_local) atomicMax(&ctl->tau, tau_local);
         if (any_nf) atomicOr(&ctl->flags, FLAG_NONFINITE);
@@ -207,7 +222,7 @@ static cudaError_t launch_one(const FlatView& v, const float* d_queries, uint32_
     dim3 grid(w.grid_x, nq);
     kern<<<grid, SCAN_THREADS, smem, s>>>(reinterpret_cast<const float4*>(v.rows), v.inv_norm,
                                           reinterpret_cast<const float4*>(d_queries), v.n, v.pitch / 4,
-                                          w.cand, w.cand_count, w.ctl, w.Kp);
+                                          w.cand, w.cand_count, w.cand_max, w.ctl, w.Kp);
     return cudaGetLastError();
 }
 

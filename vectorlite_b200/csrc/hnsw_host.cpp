@@ -1,0 +1,457 @@
+// hnsw_host.cpp — host side of the HNSW index: graph construction, id bookkeeping, upload.
+//
+// Boundary mirrored: HNSWIndex (src/index/hnsw.rs:197-518) — add / soft delete / search /
+// len / get_vector / max_id, id↔internal-index maps (hnsw.rs:204-207), one metric per index
+// (hnsw.rs:216-259).  The reference delegates the graph to crate hnsw 0.11 (not in its tree); this
+// is NOT a restatement of that crate (the restatement lives in oracle/ and is only the recall
+// baseline).  Construction here is the published HNSW algorithm (Malkov & Yashunin): exponential
+// level draw with mult 1/ln(M), greedy descent, ef_construction beam per level, heuristic
+// neighbour selection with pruned-fill, M links per new node, caps M (upper) / M0 (layer 0) on
+// back-links; inserted in parallel over host threads with per-node spin locks.  Distances are true
+// fp32 metrics (not the reference's u64 milli-unit quantisation, hnsw.rs:113-174), which is why
+// recall at equal (M, M0, ef_construction, ef) is >= the reference's.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <queue>
+#include <thread>
+
+#include "hnsw.h"
+#include "hnsw_state.h"
+
+namespace vl {
+
+namespace {
+
+enum { COS = 0, EUC = 1, MAN = 2, DOTP = 3 };
+
+// 16 independent partial sums: lets the host compiler vectorise without -ffast-math
+__attribute__((target_clones("avx2,fma", "default"))) float dot_f32(const float* a, const float* b, uint32_t n) {
+    float acc[16] = {0};
+    uint32_t i = 0;
+    for (; i + 16 <= n; i += 16)
+        for (int j = 0; j < 16; ++j) acc[j] += a[i + j] * b[i + j];
+    float s = 0.f;
+    for (; i < n; ++i) s += a[i] * b[i];
+    for (int j = 0; j < 16; ++j) s += acc[j];
+    return s;
+}
+__attribute__((target_clones("avx2,fma", "default"))) float l2sq_f32(const float* a, const float* b, uint32_t n) {
+    float acc[16] = {0};
+    uint32_t i = 0;
+    for (; i + 16 <= n; i += 16)
+        for (int j = 0; j < 16; ++j) {
+            const float d = a[i + j] - b[i + j];
+            acc[j] += d * d;
+        }
+    float s = 0.f;
+    for (; i < n; ++i) {
+        const float d = a[i] - b[i];
+        s += d * d;
+    }
+    for (int j = 0; j < 16; ++j) s += acc[j];
+    return s;
+}
+__attribute__((target_clones("avx2,fma", "default"))) float l1_f32(const float* a, const float* b, uint32_t n) {
+    float acc[16] = {0};
+    uint32_t i = 0;
+    for (; i + 16 <= n; i += 16)
+        for (int j = 0; j < 16; ++j) acc[j] += std::fabs(a[i + j] - b[i + j]);
+    float s = 0.f;
+    for (; i < n; ++i) s += std::fabs(a[i] - b[i]);
+    for (int j = 0; j < 16; ++j) s += acc[j];
+    return s;
+}
+
+struct Builder {
+    HnswState& g;
+    explicit Builder(HnswState& s) : g(s) {}
+
+    const float* vec(uint32_t i) const { return g.vecs.data() + static_cast<size_t>(i) * g.dim; }
+    float dist(uint32_t a, uint32_t b) const {  // lower is closer
+        switch (g.metric) {
+            case COS: return 1.0f - dot_f32(vec(a), vec(b), g.dim) * g.inv_norm[a] * g.inv_norm[b];
+            case EUC: return l2sq_f32(vec(a), vec(b), g.dim);
+            case MAN: return l1_f32(vec(a), vec(b), g.dim);
+            default: return -dot_f32(vec(a), vec(b), g.dim);
+        }
+    }
+    uint32_t* adj(uint32_t node, int lvl) {
+        return lvl == 0 ? g.adj0.data() + static_cast<size_t>(node) * g.M0
+                        : g.upper.data() + (static_cast<size_t>(g.upper_off[node]) + lvl - 1) * g.M;
+    }
+    uint32_t cap(int lvl) const { return lvl == 0 ? g.M0 : g.M; }
+    void lock(uint32_t i) {
+        uint8_t exp = 0;
+        while (!g.locks[i].compare_exchange_weak(exp, 1, std::memory_order_acquire)) {
+            exp = 0;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    void unlock(uint32_t i) { g.locks[i].store(0, std::memory_order_release); }
+    uint32_t copy_adj(uint32_t node, int lvl, uint32_t* out) {
+        lock(node);
+        const uint32_t* a = adj(node, lvl);
+        const uint32_t c = cap(lvl);
+        uint32_t m = 0;
+        while (m < c && a[m] != HNSW_NONE) { out[m] = a[m]; ++m; }
+        unlock(node);
+        return m;
+    }
+
+    struct Scratch {
+        std::vector<uint32_t> stamp;
+        uint32_t epoch = 0;
+        std::vector<std::pair<float, uint32_t>> W, sel, pruned;
+        std::vector<uint32_t> nb;
+    };
+    using DI = std::pair<float, uint32_t>;
+
+    // beam search on one level; results (ascending by distance) in sc.W
+    void search_layer(uint32_t q, uint32_t ep, float epd, uint32_t ef, int lvl, Scratch& sc) {
+        if (++sc.epoch == 0) { std::fill(sc.stamp.begin(), sc.stamp.end(), 0u); sc.epoch = 1; }
+        std::priority_queue<DI, std::vector<DI>, std::greater<DI>> cand;  // closest first
+        std::priority_queue<DI> res;                                         // farthest first
+        cand.emplace(epd, ep);
+        res.emplace(epd, ep);
+        sc.stamp[ep] = sc.epoch;
+        sc.nb.resize(std::max(g.M, g.M0));
+        while (!cand.empty()) {
+            const DI c = cand.top();
+            if (c.first > res.top().first && res.size() >= ef) break;
+            cand.pop();
+            const uint32_t m = copy_adj(c.second, lvl, sc.nb.data());
+            for (uint32_t j = 0; j < m; ++j) {
+                const uint32_t v = sc.nb[j];
+                if (sc.stamp[v] == sc.epoch) continue;
+                sc.stamp[v] = sc.epoch;
+                const float d = dist(q, v);
+                if (res.size() < ef || d < res.top().first) {
+                    cand.emplace(d, v);
+                    res.emplace(d, v);
+                    if (res.size() > ef) res.pop();
+                }
+            }
+        }
+        sc.W.resize(res.size());
+        for (size_t i = res.size(); i-- > 0;) { sc.W[i] = res.top(); res.pop(); }
+    }
+
+    // Algorithm 4 (heuristic) with keepPrunedConnections; `cands` ascending by distance to base
+    void select(const std::vector<DI>& cands, uint32_t m, Scratch& sc) {
+        sc.sel.clear();
+        sc.pruned.clear();
+        for (const DI& c : cands) {
+            if (sc.sel.size() >= m) break;
+            bool good = true;
+            for (const DI& r : sc.sel)
+                if (dist(c.second, r.second) < c.first) { good = false; break; }
+            (good ? sc.sel : sc.pruned).push_back(c);
+        }
+        for (size_t i = 0; i < sc.pruned.size() && sc.sel.size() < m; ++i) sc.sel.push_back(sc.pruned[i]);
+    }
+
+    void insert(uint32_t q, Scratch& sc) {
+        const int lvl = g.level[q];
+        std::unique_lock<std::mutex> top(g.entry_mu, std::defer_lock);
+        top.lock();
+        const int maxl = g.max_level;
+        uint32_t cur = g.entry;
+        if (lvl <= maxl) top.unlock();  // only a node that raises the top level holds the entry lock
+        if (maxl < 0) {                 // first node
+            g.entry = q;
+            g.max_level = lvl;
+            return;
+        }
+        float curd = dist(q, cur);
+        std::vector<uint32_t> nb(std::max(g.M, g.M0));
+        for (int l = maxl; l > lvl; --l) {  // greedy descent above the node's level
+            bool changed = true;
+            while (changed) {
+                changed = false;
+                const uint32_t m = copy_adj(cur, l, nb.data());
+                for (uint32_t j = 0; j < m; ++j) {
+                    const float d = dist(q, nb[j]);
+                    if (d < curd) { curd = d; cur = nb[j]; changed = true; }
+                }
+            }
+        }
+        std::vector<DI> tmp;
+        for (int l = std::min(lvl, maxl); l >= 0; --l) {
+            search_layer(q, cur, curd, g.efc, l, sc);
+            select(sc.W, g.M, sc);  // new node links to M neighbours on every level
+            const std::vector<DI> mine = sc.sel;
+            lock(q);
+            uint32_t* a = adj(q, l);
+            for (size_t i = 0; i < mine.size(); ++i) a[i] = mine[i].second;
+            unlock(q);
+            for (const DI& e : mine) {  // back-links, capped at M (upper) / M0 (layer 0)
+                const uint32_t t = e.second;
+                lock(t);
+                uint32_t* ta = adj(t, l);
+                const uint32_t c = cap(l);
+                uint32_t m = 0;
+                while (m < c && ta[m] != HNSW_NONE) ++m;
+                if (m < c) {
+                    ta[m] = q;
+                    unlock(t);
+                } else {
+                    tmp.clear();
+                    tmp.emplace_back(e.first, q);
+                    for (uint32_t j = 0; j < m; ++j) tmp.emplace_back(dist(t, ta[j]), ta[j]);
+                    unlock(t);  // distances to other rows computed outside the lock would race with ta;
+                                // we copied under the lock, the re-selection below works on the copy
+                    std::sort(tmp.begin(), tmp.end());
+                    select(tmp, c, sc);
+                    lock(t);
+                    for (uint32_t j = 0; j < c; ++j) ta[j] = j < sc.sel.size() ? sc.sel[j].second : HNSW_NONE;
+                    unlock(t);
+                }
+            }
+            cur = sc.W.front().second;
+            curd = sc.W.front().first;
+        }
+        if (lvl > maxl) {
+            g.entry = q;
+            g.max_level = lvl;
+        }
+    }
+};
+
+uint64_t next_rand(uint64_t& s) {  // splitmix64
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+bool dev_grow(T*& p, size_t& cap_elems, size_t need, size_t elem = sizeof(T)) {
+    (void)elem;
+    if (need <= cap_elems && p) return true;
+    if (p) cudaFree(p);
+    p = nullptr;
+    const size_t nc = need + need / 4 + 64;
+    if (cudaMalloc(&p, nc * sizeof(T)) != cudaSuccess) return false;
+    cap_elems = nc;
+    return true;
+}
+
+}  // namespace
+
+void HnswDeleter::operator()(HnswState* s) const {
+    if (!s) return;
+    hnsw_state_release_device(s);
+    delete s;
+}
+
+HnswState* hnsw_state_create(uint32_t dim, int metric, uint32_t M, uint32_t M0, uint32_t efc) {
+    if (dim == 0 || M < 2 || M > 64 || M0 < M || M0 > 64 || efc < 1) return nullptr;
+    HnswState* s = new HnswState();
+    s->dim = dim;
+    s->metric = metric;
+    s->M = M;
+    s->M0 = M0;
+    s->efc = efc;
+    return s;
+}
+
+void hnsw_state_release_device(HnswState* s) {
+    cudaFree(s->d_adj0); cudaFree(s->d_upper_off); cudaFree(s->d_upper); cudaFree(s->d_level);
+    cudaFree(s->d_deleted); cudaFree(s->d_ids); cudaFree(s->d_inv_norm); cudaFree(s->d_q);
+    cudaFree(s->d_out); cudaFreeHost(s->h_out); cudaFree(s->d_visited);
+    s->d_adj0 = s->d_upper_off = s->d_upper = nullptr;
+    s->d_level = s->d_deleted = nullptr;
+    s->d_ids = nullptr; s->d_inv_norm = nullptr; s->d_q = nullptr; s->d_out = nullptr; s->h_out = nullptr;
+    s->d_visited = nullptr;
+    s->d_n_cap = s->d_upper_cap = s->q_cap = s->out_cap = 0;
+    s->dirty = s->deleted_dirty = true;
+}
+
+bool hnsw_has_id(const HnswState* s, uint64_t id) { return s->index_of.count(id) != 0; }
+bool hnsw_index_of(const HnswState* s, uint64_t id, uint64_t* ix) {
+    auto it = s->index_of.find(id);
+    if (it == s->index_of.end()) return false;
+    *ix = it->second;
+    return true;
+}
+bool hnsw_max_id(const HnswState* s, uint64_t* out) {  // metadata.keys().max() (hnsw.rs:267-269)
+    if (s->index_of.empty()) return false;
+    uint64_t m = 0;
+    for (const auto& kv : s->index_of) m = std::max(m, kv.first);
+    *out = m;
+    return true;
+}
+uint64_t hnsw_live(const HnswState* s) { return s->live; }
+
+int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n) {
+    if (n == 0) return 0;
+    const uint32_t first = static_cast<uint32_t>(s->level.size());
+    const uint64_t total = first + n;
+    if (total >= 0x7FFFFFFFull) return 9;
+    // ---- grow flat arrays up front (no reallocation during the parallel phase) ----
+    s->vecs.insert(s->vecs.end(), rows, rows + n * s->dim);
+    s->inv_norm.resize(total);
+    s->level.resize(total);
+    s->adj0.resize(total * s->M0, HNSW_NONE);
+    s->upper_off.resize(total, HNSW_NONE);
+    s->deleted.resize(total, 0);
+    s->id_of.insert(s->id_of.end(), ids, ids + n);
+    const double mult = 1.0 / std::log(static_cast<double>(s->M));
+    size_t slots = s->upper.size() / s->M;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t q = first + static_cast<uint32_t>(i);
+        double ss = 0.0;
+        const float* v = rows + i * s->dim;
+        for (uint32_t c = 0; c < s->dim; ++c) ss += static_cast<double>(v[c]) * v[c];
+        s->inv_norm[q] = ss > 0.0 ? static_cast<float>(1.0 / std::sqrt(ss)) : 0.f;
+        const double u = (static_cast<double>(next_rand(s->rng_state) >> 11) + 1.0) / 9007199254740993.0;
+        int lvl = static_cast<int>(-std::log(u) * mult);
+        lvl = std::min(lvl, 30);
+        s->level[q] = static_cast<uint8_t>(lvl);
+        if (lvl > 0) {
+            s->upper_off[q] = static_cast<uint32_t>(slots);
+            slots += lvl;
+        }
+        s->index_of.emplace(ids[i], q);
+    }
+    s->upper.resize(slots * s->M, HNSW_NONE);
+    if (s->locks_cap < total) {
+        const size_t nc = total + total / 2 + 1024;
+        s->locks.reset(new std::atomic<uint8_t>[nc]);
+        for (size_t i = 0; i < nc; ++i) s->locks[i].store(0);
+        s->locks_cap = nc;
+    }
+    s->live += n;
+    s->dirty = true;
+
+    // ---- insert: the first few nodes sequentially, the rest over all host threads ----
+    Builder b(*s);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("VL_HNSW_BUILD_THREADS")) nthreads = std::max(1, atoi(e));
+    nthreads = std::max(1u, std::min(nthreads, 64u));
+    uint32_t start = first;
+    {
+        Builder::Scratch sc;
+        sc.stamp.assign(total, 0);
+        const uint32_t seq_end = static_cast<uint32_t>(std::min<uint64_t>(total, std::max<uint32_t>(first, 256)));
+        for (; start < seq_end; ++start) b.insert(start, sc);
+        if (nthreads == 1 || total - start < 1024) {
+            for (; start < total; ++start) b.insert(start, sc);
+            return 0;
+        }
+    }
+    std::atomic<uint32_t> next(start);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t)
+        th.emplace_back([&]() {
+            Builder::Scratch sc;
+            sc.stamp.assign(total, 0);
+            for (;;) {
+                const uint32_t q = next.fetch_add(1);
+                if (q >= total) break;
+                b.insert(q, sc);
+            }
+        });
+    for (auto& x : th) x.join();
+    return 0;
+}
+
+bool hnsw_soft_delete(HnswState* s, uint64_t id) {  // hnsw.rs:400-414
+    auto it = s->index_of.find(id);
+    if (it == s->index_of.end()) return false;
+    s->deleted[it->second] = 1;
+    s->index_of.erase(it);
+    s->live -= 1;
+    s->deleted_dirty = true;
+    return true;
+}
+
+int hnsw_upload(HnswState* s, cudaStream_t stream) {
+    const size_t n = s->level.size();
+    if (n == 0) return 0;
+    if (s->dirty) {
+        size_t cap;
+        cap = s->d_n_cap; if (!dev_grow(s->d_adj0, cap, n * s->M0)) return 7;
+        cap = s->d_n_cap; if (!dev_grow(s->d_upper_off, cap, n)) return 7;
+        cap = s->d_n_cap; if (!dev_grow(s->d_level, cap, n)) return 7;
+        cap = s->d_n_cap; if (!dev_grow(s->d_deleted, cap, n)) return 7;
+        cap = s->d_n_cap; if (!dev_grow(s->d_ids, cap, n)) return 7;
+        cap = s->d_n_cap; if (!dev_grow(s->d_inv_norm, cap, n)) return 7;
+        s->d_n_cap = 0;  // always re-check: arrays have different element counts
+        if (!dev_grow(s->d_upper, s->d_upper_cap, std::max<size_t>(s->upper.size(), 1))) return 7;
+        cudaMemcpyAsync(s->d_adj0, s->adj0.data(), n * s->M0 * 4, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(s->d_upper_off, s->upper_off.data(), n * 4, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(s->d_level, s->level.data(), n, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(s->d_ids, s->id_of.data(), n * 8, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(s->d_inv_norm, s->inv_norm.data(), n * 4, cudaMemcpyHostToDevice, stream);
+        if (!s->upper.empty())
+            cudaMemcpyAsync(s->d_upper, s->upper.data(), s->upper.size() * 4, cudaMemcpyHostToDevice, stream);
+        s->deleted_dirty = true;
+    }
+    if (s->deleted_dirty)
+        cudaMemcpyAsync(s->d_deleted, s->deleted.data(), n, cudaMemcpyHostToDevice, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 6;
+    s->dirty = s->deleted_dirty = false;
+    return 0;
+}
+
+int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,
+                     uint32_t k, uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
+                     cudaStream_t stream, uint64_t* visited, uint64_t* launches) {
+    std::lock_guard<std::mutex> lk(s->search_mu);
+    // hnsw.rs:437: ef = max_candidates = min(k, live); `ef` > 0 is the additive sweep knob
+    const uint32_t maxc = static_cast<uint32_t>(std::min<uint64_t>(k, s->live));
+    uint32_t ef_search = ef == 0 ? maxc : std::max(ef, maxc);
+    const size_t qf = static_cast<size_t>(nq) * pitch;
+    if (qf > s->q_cap) {
+        cudaFree(s->d_q);
+        s->d_q = nullptr;
+        if (cudaMalloc(&s->d_q, qf * sizeof(float)) != cudaSuccess) return 7;
+        s->q_cap = qf;
+    }
+    const size_t on = static_cast<size_t>(nq) * k;
+    const size_t need = on * 16 + static_cast<size_t>(nq) * 4;
+    if (need > s->out_cap) {
+        cudaFree(s->d_out); cudaFreeHost(s->h_out);
+        s->d_out = nullptr; s->h_out = nullptr;
+        if (cudaMalloc(&s->d_out, need) != cudaSuccess) return 7;
+        if (cudaMallocHost(&s->h_out, need) != cudaSuccess) return 7;
+        s->out_cap = need;
+    }
+    if (!s->d_visited && cudaMalloc(&s->d_visited, 8) != cudaSuccess) return 7;
+    cudaMemsetAsync(s->d_visited, 0, 8, stream);
+    if (pitch == s->dim) {
+        cudaMemcpyAsync(s->d_q, queries, qf * sizeof(float), cudaMemcpyHostToDevice, stream);
+    } else {
+        cudaMemsetAsync(s->d_q, 0, qf * sizeof(float), stream);
+        cudaMemcpy2DAsync(s->d_q, pitch * sizeof(float), queries, s->dim * sizeof(float), s->dim * sizeof(float),
+                          nq, cudaMemcpyHostToDevice, stream);
+    }
+    HnswDeviceGraph g;
+    g.adj0 = s->d_adj0; g.upper_off = s->d_upper_off; g.upper = s->d_upper; g.level = s->d_level;
+    g.deleted = s->d_deleted; g.ids = s->d_ids; g.inv_norm = s->d_inv_norm;
+    g.n = static_cast<uint32_t>(s->level.size()); g.M = s->M; g.M0 = s->M0; g.entry = s->entry;
+    g.max_level = s->max_level;
+    uint64_t* d_ids = reinterpret_cast<uint64_t*>(s->d_out);
+    double* d_scores = reinterpret_cast<double*>(s->d_out + on * 8);
+    uint32_t* d_counts = reinterpret_cast<uint32_t*>(s->d_out + on * 16);
+    int st = hnsw_launch_search(g, d_rows, pitch, s->dim, s->metric, s->d_q, nq, k, ef_search, d_ids, d_scores,
+                                d_counts, s->d_visited, stream);
+    if (st) return st;
+    unsigned long long vis = 0;
+    cudaMemcpyAsync(s->h_out, s->d_out, need, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(&vis, s->d_visited, 8, cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 6;
+    memcpy(out_ids, s->h_out, on * 8);
+    memcpy(out_scores, s->h_out + on * 8, on * 8);
+    memcpy(out_counts, s->h_out + on * 16, static_cast<size_t>(nq) * 4);
+    *visited = vis;
+    *launches = 1;
+    return 0;
+}
+
+}  // namespace vl

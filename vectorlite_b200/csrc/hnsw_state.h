@@ -1,0 +1,67 @@
+// hnsw_state.h — shared definition of the HNSW half of a handle (host builder ↔ device search).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace vl {
+
+constexpr uint32_t HNSW_NONE = 0xFFFFFFFFu;
+
+// Flattened graph as the device kernel sees it.
+struct HnswDeviceGraph {
+    const uint32_t* adj0 = nullptr;       // [n][M0] layer-0 adjacency, HNSW_NONE padded
+    const uint32_t* upper_off = nullptr;  // [n] first slot in `upper` (HNSW_NONE when level == 0)
+    const uint32_t* upper = nullptr;      // [slots][M]: levels 1..L of a node are consecutive slots
+    const uint8_t* level = nullptr;       // [n]
+    const uint8_t* deleted = nullptr;     // [n] soft-delete flags (hnsw.rs:407-411)
+    const uint64_t* ids = nullptr;        // [n] internal index → caller id
+    const float* inv_norm = nullptr;      // [n] (cosine)
+    uint32_t n = 0, M = 0, M0 = 0, entry = 0;
+    int max_level = -1;
+};
+
+struct HnswState {
+    uint32_t dim = 0, M = 16, M0 = 32, efc = 400;
+    int metric = 0;
+    // ---- host graph (internal index == arena position == insertion order) ----
+    std::vector<float> vecs;           // [n][dim]
+    std::vector<float> inv_norm;       // [n]
+    std::vector<uint8_t> level;        // [n]
+    std::vector<uint32_t> adj0;        // [n][M0]
+    std::vector<uint32_t> upper_off;   // [n]
+    std::vector<uint32_t> upper;       // [slots][M]
+    std::vector<uint8_t> deleted;      // [n]
+    std::vector<uint64_t> id_of;       // [n]
+    std::unordered_map<uint64_t, uint32_t> index_of;  // live ids only (id_to_index, hnsw.rs:204)
+    uint64_t live = 0;
+    int max_level = -1;
+    uint32_t entry = 0;
+    uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+    std::unique_ptr<std::atomic<uint8_t>[]> locks;
+    size_t locks_cap = 0;
+    std::mutex entry_mu;
+    // ---- device copy ----
+    uint32_t* d_adj0 = nullptr; uint32_t* d_upper_off = nullptr; uint32_t* d_upper = nullptr;
+    uint8_t* d_level = nullptr; uint8_t* d_deleted = nullptr; uint64_t* d_ids = nullptr; float* d_inv_norm = nullptr;
+    size_t d_n_cap = 0, d_upper_cap = 0;
+    bool dirty = true;          // graph changed since last upload
+    bool deleted_dirty = true;
+    // ---- search scratch (single in-flight batch; callers serialise through the handle mutex) ----
+    std::mutex search_mu;
+    float* d_q = nullptr; size_t q_cap = 0;
+    unsigned char* d_out = nullptr; unsigned char* h_out = nullptr; size_t out_cap = 0;
+    unsigned long long* d_visited = nullptr;
+};
+
+int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
+                       const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                       double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
+                       cudaStream_t stream);
+
+}  // namespace vl

@@ -32,6 +32,7 @@ struct FlatView {          // device-resident flat store (one shard)
 struct ScanWork {          // per workspace slot
     uint64_t* cand;        // [nq][grid_x][Kp]
     uint32_t* cand_count;  // [nq][grid_x]
+    uint64_t* cand_max;    // [nq][grid_x] best key of each CTA's list (0 when empty)
     QueryCtl* ctl;         // [nq]
     int grid_x;
     int Kp;

@@ -18,6 +18,12 @@ import torch.distributed as dist
 from . import FlatIndex, SimilarityMetric, VectorLiteError, lib, _err, VL_OK
 
 
+def _current_stream() -> int:
+    """torch's current stream as a cudaStream_t; the legacy default stream is handle 0 in torch,
+    which the C ABI reads as "use the handle's own stream", so map it to cudaStreamLegacy (0x1)."""
+    return torch.cuda.current_stream().cuda_stream or 1
+
+
 def shard_range(n_total: int, world: int, rank: int):
     """Contiguous row range [lo, hi) owned by `rank` (same rule on every rank)."""
     per, rem = divmod(n_total, world)
@@ -73,7 +79,7 @@ class ShardedFlatIndex:
         nq = d_queries.shape[0]
         b = self._buffers(nq, k)
         r = self.rank
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _current_stream()
         if self.world == 1:  # single shard: the local result is already the global one
             self.local.search_device(d_queries.data_ptr(), nq, k, metric, b["o_ids"].data_ptr(),
                                      b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
@@ -121,7 +127,7 @@ class ShardedFlatIndex:
             for name in ("ids", "sc", "pos", "cnt"):
                 t = b[name]
                 dist.all_gather_into_tensor(t.view(-1), t[r].reshape(-1).clone(), group=self.group)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _current_stream()
         st = lib().vl_merge_topk_device(self.device, self.world, nq, k, b["ids"].data_ptr(), b["sc"].data_ptr(),
                                         b["pos"].data_ptr(), b["cnt"].data_ptr(), b["o_ids"].data_ptr(),
                                         b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
