@@ -209,6 +209,7 @@ def main():
     idx = ShardedFlatIndex(DIM, rank=rank, world=world, device=local_rank)
     idx.fill_synthetic(42, n_total)
     assert idx.local.len() == n_shard
+    idx.local.set_pipelined(True)   # PDL: scan of query i+1 overlaps the rescore/certify kernel of query i
 
     import oracle  # checker + cpu_baseline leg only (never on the measured GPU path)
     oracle.build()
@@ -336,7 +337,8 @@ def main():
             "config": {"workload": f"flat {n_shard}x{DIM} f32 per GPU shard, {args.metric}, k={k}, B=1 "
                                    f"({QUERIES_PER_STEP} single-query searches per step)",
                        "rows_total": n_total, "parallelism": f"row-sharded x{world}, NCCL all-gather + merge kernel",
-                       "l2": "inputs larger than L2 (1.536 GB store vs 126 MB)", "exactness":
+                       "l2": "inputs larger than L2 (1.536 GB store vs 126 MB)",
+                       "pipelining": "programmatic dependent launch between consecutive searches", "exactness":
                        "ids == oracle, f64 scores bit-identical (fp32 scan + fp64 rescore + certificate)"},
             "global_qps": qps_global,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

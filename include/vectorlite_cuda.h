@@ -148,6 +148,13 @@ int vl_index_set_pos_base(vl_index* h, uint64_t base);
 /* Counters since creation: [0] kernels launched, [1] searches served by the certified fast path,
  * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited. */
 int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n);
+/* Pipelined device searches (flat, vl_index_search_device only).  When enabled, consecutive searches
+ * enqueued on one stream overlap through programmatic dependent launch: the scan of search i+1
+ * starts while the small rescore/certify kernel of search i is still running (results of each
+ * search still become visible in stream order).  Contract: the queries of a search must not be
+ * produced by the kernel enqueued immediately before it on that stream (resident query batches,
+ * H2D copies and earlier kernels are fine).  Off by default. */
+int vl_index_set_pipelined(vl_index* h, int enabled);
 /* Kernel timing for roofline reports: while enabled, vl_index_search_device brackets every launch
  * of the dominant scan kernel with CUDA events on the launching stream (ring of 1024 pairs).
  * vl_index_profile_read synchronises, returns the summed duration (ms) and number of the bracketed

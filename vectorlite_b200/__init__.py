@@ -141,6 +141,7 @@ def lib():
         "vl_index_set_mode": (i32, [vp, i32]),
         "vl_index_set_pos_base": (i32, [vp, u64]),
         "vl_index_stats": (i32, [vp, u64p, u32]),
+        "vl_index_set_pipelined": (i32, [vp, i32]),
         "vl_index_set_profiling": (i32, [vp, i32]),
         "vl_index_profile_read": (i32, [vp, dp, u64p]),
         "vl_index_device_rows": (i32, [vp, C.POINTER(vp), u32p]),
@@ -291,6 +292,9 @@ class _CudaIndex:
         st = self._L.vl_index_set_mode(self._h, int(mode))
         if st != VL_OK:
             raise VectorLiteError(st, _err())
+
+    def set_pipelined(self, on: bool) -> None:
+        self._L.vl_index_set_pipelined(self._h, 1 if on else 0)
 
     def set_profiling(self, on: bool) -> None:
         self._L.vl_index_set_profiling(self._h, 1 if on else 0)

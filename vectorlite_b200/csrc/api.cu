@@ -96,6 +96,8 @@ struct vl_index {
     int max_grid_x = 148 * 4;
     std::atomic<uint64_t> stats[ST_N];
     // ---- profiling (roofline reports) ----
+    bool pipelined = false;      // vl_index_set_pipelined: PDL overlap between consecutive device searches
+    uint32_t dev_parity = 0;     // ping-pong of the dev_slot control blocks
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // pairs
     size_t prof_n = 0;                  // pairs recorded since last read
@@ -424,7 +426,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
         if (fast) {
             ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
             SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
-            CU(launch_flat_scan(v, s.d_q, m, metric, w, s.stream));
+            CU(launch_flat_scan(v, s.d_q, m, metric, w, false, s.stream));
             CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, out, 1.0f, s.stream));
             h->stats[ST_LAUNCHES] += 2;
             CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
@@ -703,18 +705,22 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
         if ((st = grow_dev(s.cand, s.cand_cap, static_cast<size_t>(m) * grid_x * Kp))) return st;
         if ((st = grow_dev(s.cand_count, s.cc_cap, static_cast<size_t>(m) * grid_x))) return st;
         if ((st = grow_dev(s.cand_max, s.cm_cap, static_cast<size_t>(m) * grid_x))) return st;
-        if (m > s.ctl_cap) {
-            if ((st = grow_dev(s.ctl, s.ctl_cap, NQ_CHUNK))) return st;
-            CU(cudaMemsetAsync(s.ctl, 0, NQ_CHUNK * sizeof(QueryCtl), stream));
+        if (s.ctl_cap < 2 * NQ_CHUNK) {
+            if ((st = grow_dev(s.ctl, s.ctl_cap, 2 * NQ_CHUNK))) return st;
+            CU(cudaMemsetAsync(s.ctl, 0, 2 * NQ_CHUNK * sizeof(QueryCtl), stream));
         }
-        ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
+        // two control-block sets, alternated per launch: in pipelined mode the next scan starts
+        // while the previous finalize (which re-arms its own set at the end) may still be running
+        QueryCtl* ctl = s.ctl + (h->dev_parity & 1) * NQ_CHUNK;
+        h->dev_parity ^= 1;
+        ScanWork w{s.cand, s.cand_count, s.cand_max, ctl, grid_x, Kp};
         SearchOut out{d_out_ids + static_cast<size_t>(q0) * k, d_out_scores + static_cast<size_t>(q0) * k,
                       d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
                       d_out_flags + q0};
         const float* dq = d_queries + static_cast<size_t>(q0) * h->pitch;
         const bool prof = h->profiling && h->prof_n < h->prof_ev.size() / 2;
         if (prof) CU(cudaEventRecord(h->prof_ev[2 * h->prof_n], stream));
-        CU(launch_flat_scan(v, dq, m, metric, w, stream));
+        CU(launch_flat_scan(v, dq, m, metric, w, h->pipelined, stream));
         if (prof) {
             CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
             h->prof_n += 1;
@@ -801,6 +807,11 @@ int vl_index_set_pos_base(vl_index* h, uint64_t base) {
 int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n) {
     if (!h || !out) return fail(VL_ERR_INVALID, "null argument");
     for (uint32_t i = 0; i < n; ++i) out[i] = i < ST_N ? h->stats[i].load() : 0;
+    return VL_OK;
+}
+int vl_index_set_pipelined(vl_index* h, int enabled) {
+    if (!h) return fail(VL_ERR_INVALID, "null handle");
+    h->pipelined = enabled != 0;
     return VL_OK;
 }
 int vl_index_set_profiling(vl_index* h, int enabled) {

@@ -83,4 +83,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return v;
 }
 
+// Programmatic dependent launch (sm_90+): `pdl_wait` blocks until the previous kernel in the stream
+// has completed and its writes are visible (no-op unless THIS kernel was launched with the
+// programmatic-stream-serialization attribute); `pdl_launch_dependents` lets the next kernel in
+// the stream start early (it only matters if THAT kernel carries the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace vl

@@ -59,45 +59,62 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) flat_finalize_kernel(FinalizeP
     const uint32_t qi = blockIdx.x;
     const int Kp = p.Kp;
     QueryCtl* ctl = p.ctl + qi;
+    pdl_launch_dependents();  // the next query's scan may start now (it never reads our outputs)
+    pdl_wait();               // the scan that produced our candidates is complete and visible
 
     // ---- (1) merge -------------------------------------------------------------------
-    // Threshold: the Kp-th largest of the per-CTA maxima is a lower bound of the global Kp-th best
-    // key (Kp distinct rows reach it), and only ~Kp candidates in total lie above it.
+    // The Kp-th largest of the per-CTA maxima (tau1) is a lower bound of the global Kp-th best key
+    // (Kp distinct rows reach it); exactly Kp lists have a maximum >= tau1, so only those Kp·Kp
+    // slots can hold a member of the global top-Kp, and only ~Kp entries actually pass tau1.
     CtaTopK<SCAN_CAP, FIN_THREADS> topk{s_keys, &s_count};
+    __shared__ unsigned long long s_max[SCAN_CAP];
     __shared__ uint32_t s_ccount[SCAN_CAP];
-    __shared__ int s_overflow;
+    __shared__ uint16_t s_qual[KP_MAX];
+    __shared__ unsigned long long s_tau1;
+    __shared__ int s_overflow, s_nz;
     const int G = p.grid_x;  // <= SCAN_CAP (host guarantees)
     const uint32_t slots = static_cast<uint32_t>(G) * Kp;
     const uint64_t* cand = p.cand + static_cast<size_t>(qi) * slots;
     const uint32_t* ccount = p.cand_count + static_cast<size_t>(qi) * G;
     const uint64_t* cmax = p.cand_max + static_cast<size_t>(qi) * G;
-    for (int i = tid; i < SCAN_CAP; i += FIN_THREADS) {
-        s_keys[i] = i < G ? cmax[i] : 0ull;
-        s_ccount[i] = i < G ? ccount[i] : 0u;
+    if (tid == 0) { s_nan = 0; s_overflow = 0; s_count = 0; s_tau1 = 0ull; s_nz = 0; }
+    __syncthreads();
+    {
+        int nz = 0;
+        for (int i = tid; i < G; i += FIN_THREADS) {
+            const unsigned long long m = cmax[i];
+            s_max[i] = m;
+            s_ccount[i] = ccount[i];
+            nz += m != 0ull;
+        }
+        if (nz) atomicAdd(&s_nz, nz);
     }
-    if (tid == 0) { s_nan = 0; s_overflow = 0; s_count = 0; }
+    __syncthreads();
+    const int nqual = min(Kp, s_nz);
+    for (int i = tid; i < G; i += FIN_THREADS) {  // rank by counting: no barriers, broadcast reads
+        const unsigned long long me = s_max[i];
+        if (me == 0ull) continue;
+        int r = 0;
+        for (int j = 0; j < G; ++j) r += s_max[j] > me;
+        if (r < Kp) s_qual[r] = static_cast<uint16_t>(i);
+        if (r == Kp - 1) s_tau1 = me;
+    }
     __syncthreads();
     unsigned long long tau = ctl->tau;  // every key of the global top-K' is >= tau
-    if (G >= Kp) {
-        int len = 2;
-        while (len < G) len <<= 1;
-        topk.sort_desc(len);
-        const unsigned long long t1 = s_keys[Kp - 1];
-        tau = t1 > tau ? t1 : tau;
-    }
-    __syncthreads();
-    topk.init();
-    {   // optimistic single pass: coalesced, barrier-free, 8 independent loads in flight per thread
+    tau = s_tau1 > tau ? s_tau1 : tau;
+    {   // one pass over the qualifying lists: coalesced, barrier-free, 8 independent loads in flight
         constexpr int U = 8;
-        for (uint32_t s0 = 0; s0 < slots; s0 += FIN_THREADS * U) {
+        const uint32_t qslots = static_cast<uint32_t>(nqual) * Kp;
+        for (uint32_t s0 = 0; s0 < qslots; s0 += FIN_THREADS * U) {
             unsigned long long key[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t s = s0 + u * FIN_THREADS + tid;
                 key[u] = 0ull;
-                if (s < slots) {
-                    const uint32_t c = s / Kp, e = s - c * Kp;
-                    if (e < s_ccount[c]) key[u] = cand[s];
+                if (s < qslots) {
+                    const uint32_t l = s / Kp, e = s - l * Kp;
+                    const uint32_t c = s_qual[l];
+                    if (e < s_ccount[c]) key[u] = cand[static_cast<size_t>(c) * Kp + e];
                 }
             }
 #pragma unroll
@@ -110,7 +127,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) flat_finalize_kernel(FinalizeP
         }
     }
     __syncthreads();
-    if (s_overflow) {  // rare (at most Kp lists can reach tau, but each may hold Kp entries): bounded rounds
+    if (s_overflow) {  // rare: more than SCAN_CAP entries above tau1 → bounded rounds with compaction
         __syncthreads();
         topk.init();
         for (uint32_t s0 = 0; s0 < slots; s0 += FIN_THREADS) {
@@ -128,8 +145,30 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) flat_finalize_kernel(FinalizeP
                 }
             }
         }
+        topk.compact(Kp, true);  // sorted descending, count <= Kp
+    } else {
+        // rank-sort the survivors (typically ~Kp..2Kp of them) by counting: no barrier-laden network
+        const int n = s_count;
+        unsigned long long mine[2];
+        int rk[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = tid + u * FIN_THREADS;
+            rk[u] = -1;
+            if (i < n) {
+                mine[u] = s_keys[i];
+                int r = 0;
+                for (int j = 0; j < n; ++j) r += s_keys[j] > mine[u];
+                rk[u] = r;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (rk[u] >= 0 && rk[u] < Kp) s_keys[rk[u]] = mine[u];
+        if (tid == 0) s_count = min(n, Kp);
+        __syncthreads();
     }
-    topk.compact(Kp, true);  // sorted descending, count <= Kp
     const int nc = s_count;
     if (tid < nc) s_pos[tid] = key_pos(s_keys[tid]);
     __syncthreads();
@@ -322,8 +361,17 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
     p.out_ids = out.ids; p.out_scores = out.scores; p.out_pos = out.pos;
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = eps_scale;
-    flat_finalize_kernel<<<nq, FIN_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nq);
+    cfg.blockDim = dim3(FIN_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;  // always: launch latency overlaps the scan's tail; pdl_wait() orders the data
+    return cudaLaunchKernelEx(&cfg, flat_finalize_kernel, p);
 }
 
 }  // namespace vl

@@ -177,6 +177,7 @@ flat_scan_kernel(const float4* __restrict__ rows, const float* __restrict__ inv_
     }
 
     // epilogue: keep this CTA's best Kp, publish its threshold and its candidates
+    pdl_wait();  // pipelined mode: the previous query's finalize must be done with cand[] first
     const unsigned long long t = topk.compact(Kp, false);
     tau_local = t > tau_local ? t : tau_local;
     const int any_nf = __syncthreads_or(nonfinite ? 1 : 0);
@@ -211,7 +212,7 @@ size_t flat_scan_smem_bytes(uint32_t pitch) {
 
 template <int METRIC, int NCH>
 static cudaError_t launch_one(const FlatView& v, const float* d_queries, uint32_t nq, const ScanWork& w,
-                              cudaStream_t s) {
+                              bool pipelined, cudaStream_t s) {
     const size_t smem = flat_scan_smem_bytes(v.pitch);
     auto kern = flat_scan_kernel<METRIC, NCH>;
     if (smem > 48 * 1024) {
@@ -219,30 +220,38 @@ static cudaError_t launch_one(const FlatView& v, const float* d_queries, uint32_
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(w.grid_x, nq);
-    kern<<<grid, SCAN_THREADS, smem, s>>>(reinterpret_cast<const float4*>(v.rows), v.inv_norm,
-                                          reinterpret_cast<const float4*>(d_queries), v.n, v.pitch / 4,
-                                          w.cand, w.cand_count, w.cand_max, w.ctl, w.Kp);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(w.grid_x, nq);
+    cfg.blockDim = dim3(SCAN_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pipelined ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const float4*>(v.rows), v.inv_norm,
+                              reinterpret_cast<const float4*>(d_queries), v.n, v.pitch / 4, w.cand,
+                              w.cand_count, w.cand_max, w.ctl, w.Kp);
 }
 
 template <int METRIC>
 static cudaError_t launch_metric(const FlatView& v, const float* q, uint32_t nq, const ScanWork& w,
-                                 cudaStream_t s) {
+                                 bool pipelined, cudaStream_t s) {
     switch (v.pitch) {
-        case 384: return launch_one<METRIC, 3>(v, q, nq, w, s);
-        case 768: return launch_one<METRIC, 6>(v, q, nq, w, s);
-        default: return launch_one<METRIC, 0>(v, q, nq, w, s);
+        case 384: return launch_one<METRIC, 3>(v, q, nq, w, pipelined, s);
+        case 768: return launch_one<METRIC, 6>(v, q, nq, w, pipelined, s);
+        default: return launch_one<METRIC, 0>(v, q, nq, w, pipelined, s);
     }
 }
 
 cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t nq, int metric,
-                             const ScanWork& w, cudaStream_t s) {
+                             const ScanWork& w, bool pipelined, cudaStream_t s) {
     switch (metric) {
-        case COSINE: return launch_metric<COSINE>(v, d_queries, nq, w, s);
-        case EUCLIDEAN: return launch_metric<EUCLIDEAN>(v, d_queries, nq, w, s);
-        case MANHATTAN: return launch_metric<MANHATTAN>(v, d_queries, nq, w, s);
-        case DOT: return launch_metric<DOT>(v, d_queries, nq, w, s);
+        case COSINE: return launch_metric<COSINE>(v, d_queries, nq, w, pipelined, s);
+        case EUCLIDEAN: return launch_metric<EUCLIDEAN>(v, d_queries, nq, w, pipelined, s);
+        case MANHATTAN: return launch_metric<MANHATTAN>(v, d_queries, nq, w, pipelined, s);
+        case DOT: return launch_metric<DOT>(v, d_queries, nq, w, pipelined, s);
         default: return cudaErrorInvalidValue;
     }
 }

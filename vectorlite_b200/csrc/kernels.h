@@ -47,8 +47,11 @@ struct SearchOut {         // device outputs, [nq][k]
 };
 
 // single-query-per-CTA-column fp32 streaming scan (grid = grid_x × nq)
+// pipelined: launch with the PDL attribute so the scan may start while the PREVIOUS kernel in the
+// stream (the previous query's finalize) is still running; the scan only waits for it right before
+// publishing its candidates.  The caller guarantees the queries were not produced by that kernel.
 cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t nq, int metric,
-                             const ScanWork& w, cudaStream_t s);
+                             const ScanWork& w, bool pipelined, cudaStream_t s);
 // merge per-CTA candidates, fp64 rescore in reference order, rank, certify (grid = nq)
 cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k,
                                  int metric, const ScanWork& w, const SearchOut& out, float eps_scale,
