@@ -292,3 +292,40 @@ def test_full_size_1m_properties_and_sampled_oracle(vl, oracle_mod):
     for metric in vl.SimilarityMetric:
         _check(vl, oracle_mod, idx, rows, None, q, k, metric)
     assert idx.stats()["exact_queries"] == 0, "certificate should hold on i.i.d. data"
+
+
+@pytest.mark.parametrize("n,dim", [(5, 8), (3000, 96), (20000, 384), (70000, 100)])
+def test_batched_pipeline_parity(vl, oracle_mod, n, dim):
+    """nq >= 8 goes through the staged-threshold tile pipeline (CUDA-core kernel): ids exact, f64
+    scores bit-identical to the oracle, all four metrics, stage boundaries (4096, 65536) crossed."""
+    rng = np.random.default_rng(n + dim)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    if n > 100:
+        rows[50] = rows[7]            # duplicate across tile boundaries → positional tie-break
+        rows[n - 1] = rows[7]
+        rows[9] = 0.0
+    queries = rng.standard_normal((40, dim)).astype(np.float32)
+    queries[3] = rows[min(7, n - 1)]
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    st, _, _ = oracle_mod.flat_search_batch(rows, None, queries[:1], 1, 0)
+    for metric in vl.SimilarityMetric:
+        for k in (10, 100):
+            gi, gs, gc = idx.search_batch(queries, k, metric)
+            st, oi, os_ = oracle_mod.flat_search_batch(rows, None, queries, k, int(metric), nthreads=8)
+            assert st == 0
+            kk = min(k, n)
+            assert np.all(gc == kk)
+            assert np.array_equal(gi[:, :kk], oi[:, :kk]), (metric, k)
+            assert np.array_equal(gs[:, :kk].view(np.uint64), os_[:, :kk].view(np.uint64)), (metric, k)
+
+
+def test_batched_pipeline_ties_fall_back(vl, oracle_mod):
+    n, dim = 6000, 64
+    rows = np.tile(np.linspace(0.1, 1.0, dim, dtype=np.float32), (n, 1))
+    queries = np.tile(rows[:1], (16, 1))
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    gi, gs, gc = idx.search_batch(queries, 10, vl.SimilarityMetric.Cosine)
+    assert np.all(gi == np.arange(10, dtype=np.uint64)[None, :])
+    assert idx.stats()["exact_queries"] >= 16

@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "batch.h"
 #include "hnsw.h"
 #include "kernels.h"
 
@@ -43,6 +44,9 @@ enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HN
 namespace {
 
 constexpr uint32_t NQ_CHUNK = 32;  // queries per launch of the per-query scan
+constexpr uint32_t BATCH_MIN = 8;        // nq >= BATCH_MIN → batched tile pipeline
+constexpr uint32_t BATCH_CHUNK = 1024;   // queries per batched pass
+constexpr uint32_t BATCH_CAPQ = 4096;    // candidate slots per query
 
 struct Slot {  // one in-flight search: stream + scratch, all sized on demand
     cudaStream_t stream = nullptr;
@@ -59,6 +63,11 @@ struct Slot {  // one in-flight search: stream + scratch, all sized on demand
     uint64_t* d_ids = nullptr; double* d_scores = nullptr; uint32_t* d_counts = nullptr; uint32_t* d_flags = nullptr;
     uint64_t* h_ids = nullptr; double* h_scores = nullptr; uint32_t* h_counts = nullptr; uint32_t* h_flags = nullptr;
     size_t out_used = 0;
+    // batched pipeline scratch
+    uint64_t* b_cand = nullptr; size_t b_cand_cap = 0;
+    uint32_t* b_count = nullptr; size_t b_count_cap = 0;
+    float* b_tau = nullptr; size_t b_tau_cap = 0;
+    uint32_t* b_qflags = nullptr; size_t b_qflags_cap = 0;
     // exact path
     double* d_exact = nullptr; size_t exact_cap = 0;
     uint32_t* d_exflags = nullptr;
@@ -171,9 +180,20 @@ int slot_reserve(vl_index* h, Slot& s, uint32_t nq, uint32_t k, int Kp, int grid
     return VL_OK;
 }
 
+int slot_reserve_batch(Slot& s, uint32_t nq, BatchWork* w) {
+    int st;
+    if ((st = grow_dev(s.b_cand, s.b_cand_cap, static_cast<size_t>(nq) * BATCH_CAPQ))) return st;
+    if ((st = grow_dev(s.b_count, s.b_count_cap, nq))) return st;
+    if ((st = grow_dev(s.b_tau, s.b_tau_cap, nq))) return st;
+    if ((st = grow_dev(s.b_qflags, s.b_qflags_cap, nq))) return st;
+    w->cand = s.b_cand; w->count = s.b_count; w->tau = s.b_tau; w->qflags = s.b_qflags; w->capq = BATCH_CAPQ;
+    return VL_OK;
+}
+
 void slot_free(Slot& s) {
     cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.cand_max); cudaFree(s.ctl);
     cudaFree(s.d_out); cudaFreeHost(s.h_out);
+    cudaFree(s.b_cand); cudaFree(s.b_count); cudaFree(s.b_tau); cudaFree(s.b_qflags);
     cudaFree(s.d_exact); cudaFree(s.d_exflags);
     exact_scratch_free(s.exs);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -411,9 +431,11 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
     int rc = VL_OK;
-    for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += NQ_CHUNK) {
-        const uint32_t m = std::min(NQ_CHUNK, nq - q0);
-        int st = slot_reserve(h, s, m, k, Kp, grid_x);
+    const bool batched = fast && nq >= BATCH_MIN && h->mode != VL_MODE_FP32;
+    const uint32_t chunk = batched ? BATCH_CHUNK : NQ_CHUNK;
+    for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += chunk) {
+        const uint32_t m = std::min(chunk, nq - q0);
+        int st = slot_reserve(h, s, m, k, Kp, batched ? 1 : grid_x);
         if (st) return st;
         for (uint32_t q = 0; q < m; ++q) {
             float* d = s.h_q + static_cast<size_t>(q) * h->pitch;
@@ -424,11 +446,19 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
         CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
         h->stats[ST_H2D] += qbytes;
         if (fast) {
-            ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
             SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
-            CU(launch_flat_scan(v, s.d_q, m, metric, w, false, s.stream));
-            CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, out, 1.0f, s.stream));
-            h->stats[ST_LAUNCHES] += 2;
+            if (batched) {
+                BatchWork bw;
+                if ((st = slot_reserve_batch(s, m, &bw))) return st;
+                uint64_t nl = 0;
+                CU(launch_batch_flat(v, s.d_q, m, k, metric, Kp, bw, out, nullptr, &nl, s.stream));
+                h->stats[ST_LAUNCHES] += nl;
+            } else {
+                ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
+                CU(launch_flat_scan(v, s.d_q, m, metric, w, false, s.stream));
+                CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, out, 1.0f, s.stream));
+                h->stats[ST_LAUNCHES] += 2;
+            }
             CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
             bool any_fail = false;
@@ -698,6 +728,22 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
     const int Kp = pick_kp(k);
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
+    if (nq >= BATCH_MIN && h->mode != VL_MODE_FP32) {
+        for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
+            const uint32_t m = std::min(BATCH_CHUNK, nq - q0);
+            BatchWork bw;
+            int st = slot_reserve_batch(s, m, &bw);
+            if (st) return st;
+            SearchOut out{d_out_ids + static_cast<size_t>(q0) * k, d_out_scores + static_cast<size_t>(q0) * k,
+                          d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
+                          d_out_flags + q0};
+            uint64_t nl = 0;
+            CU(launch_batch_flat(v, d_queries + static_cast<size_t>(q0) * h->pitch, m, k, metric, Kp, bw, out,
+                                 nullptr, &nl, stream));
+            h->stats[ST_LAUNCHES] += nl;
+        }
+        return VL_OK;
+    }
     for (uint32_t q0 = 0; q0 < nq; q0 += NQ_CHUNK) {
         const uint32_t m = std::min(NQ_CHUNK, nq - q0);
         // scratch only (no query / output staging): reserve with k = 0 sized outputs

@@ -1,0 +1,33 @@
+// batch.h — internal interface of the batched flat scan (batch_scan.cu, batch_tc.cu).
+#pragma once
+#include "kernels.h"
+
+namespace vl {
+
+struct BatchWork {        // per workspace slot, sized for nq queries
+    uint64_t* cand;       // [nq][capq] candidate keys
+    uint32_t* count;      // [nq]
+    float* tau;           // [nq] running threshold in scan units (score of the K'-th best so far)
+    uint32_t* qflags;     // [nq] FLAG_* bits raised by the scan kernels
+    uint32_t capq;
+};
+
+struct BatchTensor {      // bf16 mirror of the arena for the tcgen05 path (batch_tc.cu)
+    bool usable = false;
+    const void* rows_bf16 = nullptr;   // [n][pitch] bf16 (cosine: rows pre-scaled by 1/‖row‖)
+    const void* rows_bf16_raw = nullptr;  // [n][pitch] bf16, unscaled (dot, L2)
+    const float* sq_norm = nullptr;    // [n] ‖row‖² fp32 (L2 via ‖x‖²+‖q‖²−2x·q)
+    double eps_scale = 1.0;
+    void* scratch = nullptr;           // kernel-private (tensor maps, bf16 queries)
+};
+
+cudaError_t batch_scan_cuda_cores(const FlatView& v, const float* d_q, uint32_t nq, int metric, uint32_t lo,
+                                  uint32_t hi, const BatchWork& w, cudaStream_t s);
+cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& tc, const float* d_q, uint32_t nq, int metric,
+                              uint32_t lo, uint32_t hi, const BatchWork& w, cudaStream_t s);
+// full pipeline: init → 3 staged scans with per-query selects → rescore/certify.  tc may be null.
+cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k, int metric,
+                              int Kp, const BatchWork& w, const SearchOut& out, const BatchTensor* tc,
+                              uint64_t* launches, cudaStream_t s);
+
+}  // namespace vl

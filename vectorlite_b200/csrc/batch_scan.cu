@@ -1,0 +1,306 @@
+// batch_scan.cu — batched flat scan (B queries at once), CUDA-core tile kernel + the staged
+// threshold pipeline shared with the tensor-core kernel (batch_tc.cu).
+//
+// The reference has no batched search; this is the additive path the north star
+// asks for.  Arithmetic per (row, query) pair is that of src/lib.rs:425-572 in fp32; the B×N score
+// matrix (4 GB at B=1024, N=1M) is never materialised:
+//
+//   stage 0: rows [0, S0)      scored, everything kept     → per-query K'-th best  τ0
+//   stage 1: rows [S0, S1)     only scores >= τ0 are kept  → τ1 (K'-th best of the first S1 rows)
+//   stage 2: rows [S1, N)      only scores >= τ1 are kept  (≈ K'·N/S1 survivors per query)
+//   then    : per query sort the survivors, keep K', fp64 re-score in reference order, rank, certify
+//
+// Survivors go to per-query candidate buffers with one global atomicAdd each (≈0.1 % of the pairs
+// after stage 0).  Manhattan has no tensor-core form and always runs here (bound: FP32 issue rate,
+// 2 instructions per element); cosine / L2 / dot run here when the tensor path is not applicable.
+//
+// Tile kernel: CTA = 256 threads, 128 rows × 128 queries, 8×8 micro-tile per thread with rows and
+// queries interleaved by 16 (conflict-free shared-memory reads, query reads are warp broadcasts),
+// K chunks of 32 columns staged through registers into transposed, odd-pitch shared tiles.
+#include "batch.h"
+#include "rescore.cuh"
+#include "topk.cuh"
+
+namespace vl {
+
+constexpr int BT_THREADS = 256;
+constexpr int BT_ROWS = 128, BT_QS = 128, BT_K = 32, BT_LD = 129;
+
+__global__ void batch_init_kernel(uint32_t nq, uint32_t* count, float* tau, uint32_t* qflags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) {
+        count[i] = 0u;
+        tau[i] = -INFINITY;
+        qflags[i] = 0u;
+    }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(BT_THREADS, 2)
+batch_scan_cc_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm,
+                     const float* __restrict__ queries, uint32_t row_lo, uint32_t row_hi, uint32_t pitch,
+                     uint32_t nq, const float* __restrict__ tau, uint64_t* cand, uint32_t* count,
+                     uint32_t capq, uint32_t* qflags) {
+    extern __shared__ float smem[];
+    float* s_x = smem;                          // [2][BT_K][BT_LD]
+    float* s_q = smem + 2 * BT_K * BT_LD;       // [2][BT_K][BT_LD]
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;     // rows tx + 16 i, queries ty + 16 j
+    const uint32_t row0 = row_lo + blockIdx.x * BT_ROWS;
+    const uint32_t q0 = blockIdx.y * BT_QS;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // global → register staging: 4 float4 of the X tile and 4 of the Q tile per thread
+    const int lr = tid >> 3, lc4 = tid & 7;     // 32 tile-rows per pass, 8 float4 per tile-row
+    float4 gx[4], gq[4];
+    auto gload = [&](uint32_t k0) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t r = row0 + p * 32 + lr, c = k0 + lc4 * 4;
+            gx[p] = (r < row_hi && c < pitch) ? __ldg(reinterpret_cast<const float4*>(rows + static_cast<size_t>(r) * pitch + c))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t qq = q0 + p * 32 + lr;
+            gq[p] = (qq < nq && c < pitch) ? __ldg(reinterpret_cast<const float4*>(queries + static_cast<size_t>(qq) * pitch + c))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto sstore = [&](int buf) {
+        float* x = s_x + buf * BT_K * BT_LD;
+        float* q = s_q + buf * BT_K * BT_LD;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int r = p * 32 + lr, c = lc4 * 4;
+            x[(c + 0) * BT_LD + r] = gx[p].x; x[(c + 1) * BT_LD + r] = gx[p].y;
+            x[(c + 2) * BT_LD + r] = gx[p].z; x[(c + 3) * BT_LD + r] = gx[p].w;
+            q[(c + 0) * BT_LD + r] = gq[p].x; q[(c + 1) * BT_LD + r] = gq[p].y;
+            q[(c + 2) * BT_LD + r] = gq[p].z; q[(c + 3) * BT_LD + r] = gq[p].w;
+        }
+    };
+
+    const uint32_t nchunks = (pitch + BT_K - 1) / BT_K;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) gload((ch + 1) * BT_K);
+        const float* x = s_x + buf * BT_K * BT_LD + tx;
+        const float* q = s_q + buf * BT_K * BT_LD + ty;
+#pragma unroll 8
+        for (int k = 0; k < BT_K; ++k) {
+            float xv[8], qv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = x[k * BT_LD + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) qv[j] = q[k * BT_LD + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (METRIC == COSINE || METRIC == DOT) {
+                        acc[i][j] = fmaf(xv[i], qv[j], acc[i][j]);
+                    } else if (METRIC == EUCLIDEAN) {
+                        const float d = xv[i] - qv[j];
+                        acc[i][j] = fmaf(d, d, acc[i][j]);
+                    } else {
+                        acc[i][j] += fabsf(xv[i] - qv[j]);
+                    }
+                }
+        }
+        if (ch + 1 < nchunks) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // epilogue: threshold filter, survivors to the per-query candidate buffers
+    float tq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t qq = q0 + ty + 16 * j;
+        tq[j] = qq < nq ? __ldg(tau + qq) : INFINITY;
+    }
+    bool nonfinite = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t r = row0 + tx + 16 * i;
+        if (r >= row_hi) continue;
+        const float invn = METRIC == COSINE ? __ldg(inv_norm + r) : 1.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = acc[i][j];
+            if (METRIC == COSINE) s *= invn;
+            if (METRIC == EUCLIDEAN || METRIC == MANHATTAN) s = -s;
+            const uint32_t qq = q0 + ty + 16 * j;
+            if (qq >= nq) continue;
+            if (!isfinite(s)) nonfinite = true;
+            if (s >= tq[j] || !(s == s)) {
+                const uint32_t idx = atomicAdd(count + qq, 1u);
+                if (idx < capq) cand[static_cast<size_t>(qq) * capq + idx] = make_key(s, r);
+                else atomicOr(qflags + qq, FLAG_OVERFLOW);
+            }
+        }
+    }
+    if (nonfinite) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t qq = q0 + ty + 16 * j;
+            if (qq < nq) atomicOr(qflags + qq, FLAG_NONFINITE);  // conservative: whole query tile
+        }
+    }
+}
+
+// per query: sort the candidate buffer (descending), keep the best Kp, publish the new threshold
+__global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint32_t* count, float* tau,
+                                                           uint32_t capq, int Kp) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(sm);  // [capq rounded to pow2]
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = static_cast<int>(min(count[q], capq));
+    if (n <= Kp) {
+        if (tid == 0) count[q] = n;  // clamp (overflow already flagged)
+        return;
+    }
+    int len = 2;
+    while (len < n) len <<= 1;
+    uint64_t* mine = cand + static_cast<size_t>(q) * capq;
+    for (int i = tid; i < len; i += 256) s_keys[i] = i < n ? mine[i] : 0ull;
+    __syncthreads();
+    for (int k = 2; k <= len; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (len >> 1); t += 256) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int pp = i | j;
+                const bool desc = (i & k) == 0;
+                const uint64_t a = s_keys[i], b = s_keys[pp];
+                if ((a < b) == desc) { s_keys[i] = b; s_keys[pp] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < Kp; i += 256) mine[i] = s_keys[i];
+    if (tid == 0) {
+        count[q] = Kp;
+        tau[q] = key_score(s_keys[Kp - 1]);
+    }
+}
+
+// per query: load the (sorted, <= Kp) survivors and run the shared rescore / rank / certify phases
+__global__ void __launch_bounds__(FIN_THREADS, 1) batch_rescore_kernel(FinalizeParams p, const uint32_t* count,
+                                                                       const uint32_t* qflags, uint32_t capq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
+    double* s_exact = reinterpret_cast<double*>(s_keys + SCAN_CAP);
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_exact + KP_MAX);
+    float* s_q = reinterpret_cast<float*>(s_pos + KP_MAX);
+    float* s_tile = s_q + p.CH;
+    const uint32_t qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = static_cast<int>(min(count[qi], static_cast<uint32_t>(p.Kp)));
+    // count <= Kp here: either select truncated it, or fewer than Kp survivors exist → sort by counting
+    const uint64_t* mine = p.cand + static_cast<size_t>(qi) * capq;
+    uint64_t* s_tmp = reinterpret_cast<uint64_t*>(s_tile);  // staging tile is free until the rescore
+    uint64_t key = 0;
+    if (tid < n) {
+        key = mine[tid];
+        s_tmp[tid] = key;
+    }
+    __syncthreads();
+    if (tid < n) {
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += s_tmp[j] > key;
+        s_keys[r] = key;
+    }
+    __syncthreads();
+    rescore_rank_certify(p, qi, n, s_keys, s_exact, s_pos, s_q, s_tile, qflags[qi]);
+}
+
+static size_t rescore_smem(int Kp, int CH) {
+    return SCAN_CAP * sizeof(uint64_t) + KP_MAX * sizeof(double) + KP_MAX * sizeof(uint32_t) +
+           static_cast<size_t>(CH) * sizeof(float) + static_cast<size_t>(Kp) * (CH + 1) * sizeof(float);
+}
+
+template <int METRIC>
+static cudaError_t launch_cc(const FlatView& v, const float* d_q, uint32_t nq, uint32_t lo, uint32_t hi,
+                             const BatchWork& w, cudaStream_t s) {
+    const size_t smem = 4 * BT_K * BT_LD * sizeof(float);
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(batch_scan_cc_kernel<METRIC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        attr[dev & 63] = true;
+    }
+    dim3 grid((hi - lo + BT_ROWS - 1) / BT_ROWS, (nq + BT_QS - 1) / BT_QS);
+    batch_scan_cc_kernel<METRIC><<<grid, BT_THREADS, smem, s>>>(v.rows, v.inv_norm, d_q, lo, hi, v.pitch, nq, w.tau,
+                                                                w.cand, w.count, w.capq, w.qflags);
+    return cudaGetLastError();
+}
+
+cudaError_t batch_scan_cuda_cores(const FlatView& v, const float* d_q, uint32_t nq, int metric, uint32_t lo,
+                                  uint32_t hi, const BatchWork& w, cudaStream_t s) {
+    switch (metric) {
+        case COSINE: return launch_cc<COSINE>(v, d_q, nq, lo, hi, w, s);
+        case EUCLIDEAN: return launch_cc<EUCLIDEAN>(v, d_q, nq, lo, hi, w, s);
+        case MANHATTAN: return launch_cc<MANHATTAN>(v, d_q, nq, lo, hi, w, s);
+        case DOT: return launch_cc<DOT>(v, d_q, nq, lo, hi, w, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k, int metric,
+                              int Kp, const BatchWork& w, const SearchOut& out, const BatchTensor* tc,
+                              uint64_t* launches, cudaStream_t s) {
+    cudaError_t e;
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 63]) {
+        if ((e = cudaFuncSetAttribute(batch_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(batch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
+        attr[dev & 63] = true;
+    }
+    batch_init_kernel<<<(nq + 255) / 256, 256, 0, s>>>(nq, w.count, w.tau, w.qflags);
+    uint64_t nl = 1;
+    const uint32_t S0 = min(v.n, min(w.capq, 4096u));
+    const uint32_t S1 = min(v.n, 65536u);
+    const uint32_t bounds[4] = {0u, S0, S1, v.n};
+    uint32_t sel_len = 2;
+    while (sel_len < w.capq) sel_len <<= 1;
+    const bool use_tc = tc && tc->usable && metric != MANHATTAN;
+    for (int st = 0; st < 3; ++st) {
+        const uint32_t lo = bounds[st], hi = bounds[st + 1];
+        if (hi <= lo) continue;
+        if (use_tc) e = batch_scan_tensor(v, *tc, d_queries, nq, metric, lo, hi, w, s);
+        else e = batch_scan_cuda_cores(v, d_queries, nq, metric, lo, hi, w, s);
+        if (e != cudaSuccess) return e;
+        batch_select_kernel<<<nq, 256, sel_len * sizeof(uint64_t), s>>>(w.cand, w.count, w.tau, w.capq, Kp);
+        nl += 2;
+    }
+    // rescore + certify
+    const size_t budget = 180 * 1024;
+    int CH = static_cast<int>((v.dim + 3) / 4 * 4);
+    while (CH > 4 && rescore_smem(Kp, CH) > budget) CH = (CH / 2 + 3) / 4 * 4;
+    FinalizeParams p;
+    p.rows = v.rows; p.ids = v.ids; p.stats = v.stats; p.queries = d_queries;
+    p.id_base = v.id_base; p.pos_base = v.pos_base;
+    p.n = v.n; p.dim = v.dim; p.pitch = v.pitch; p.k = k;
+    p.metric = metric; p.Kp = Kp; p.grid_x = 0; p.CH = CH;
+    p.cand = w.cand; p.cand_count = nullptr; p.cand_max = nullptr; p.ctl = nullptr;
+    p.out_ids = out.ids; p.out_scores = out.scores; p.out_pos = out.pos;
+    p.out_counts = out.counts; p.out_flags = out.flags;
+    p.eps_scale = use_tc ? tc->eps_scale : 1.0;
+    batch_rescore_kernel<<<nq, FIN_THREADS, rescore_smem(Kp, CH), s>>>(p, w.count, w.qflags, w.capq);
+    nl += 1;
+    if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+
+}  // namespace vl

@@ -1,0 +1,210 @@
+// rescore.cuh — phases (2)-(4) shared by the single-query finalize and the batched pipeline:
+// exact f64 re-score in reference summation order, final (score desc, position asc) order,
+// optimality certificate.  See flat_finalize.cu for the argument.
+#pragma once
+#include "kernels.h"
+
+namespace vl {
+
+struct FinalizeParams {
+    const float* rows;
+    const uint64_t* ids;
+    const ArenaStats* stats;
+    const float* queries;
+    uint64_t id_base, pos_base;
+    uint32_t n, dim, pitch, k;
+    int metric, Kp, grid_x, CH;  // CH = columns staged per chunk (multiple of 4)
+    const uint64_t* cand;
+    const uint32_t* cand_count;
+    const uint64_t* cand_max;
+    QueryCtl* ctl;
+    uint64_t* out_ids;
+    double* out_scores;
+    uint64_t* out_pos;
+    uint32_t* out_counts;
+    uint32_t* out_flags;
+    double eps_scale;  // multiplies the per-term rounding unit (1 = fp32 scan, larger for bf16)
+};
+
+__device__ __forceinline__ double sim_from_l2(double ss) {  // lib.rs:485-488
+    return __ddiv_rn(1.0, __dadd_rn(1.0, __dsqrt_rn(ss)));
+}
+__device__ __forceinline__ double sim_from_l1(double s) {   // lib.rs:528-531
+    return __ddiv_rn(1.0, __dadd_rn(1.0, s));
+}
+
+
+// Shared-memory carve-up expected by rescore_rank_certify (dynamic smem of the calling kernel):
+//   keys[SCAN_CAP] u64 | exact[KP_MAX] f64 | pos[KP_MAX] u32 | q[CH] f32 | tile[Kp][CH+1] f32
+// s_keys[0..nc) must hold the candidates sorted by key, descending.  All FIN_THREADS threads call.
+__device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, uint32_t qi, int nc,
+                                                     uint64_t* s_keys, double* s_exact, uint32_t* s_pos,
+                                                     float* s_q, float* s_tile, uint32_t extra_flags) {
+    __shared__ double s_kth, s_qnorm;
+    __shared__ int s_nan;
+    const int tid = threadIdx.x;
+    QueryCtl* ctl = p.ctl ? p.ctl + qi : nullptr;
+    if (tid == 0) s_nan = 0;
+    if (tid < nc) s_pos[tid] = key_pos(s_keys[tid]);
+    __syncthreads();
+
+    // ---- (2) exact f64 rescore, reference summation order --------------------------------
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;  // cosine: dot, Σx², Σy²; others: a0 only
+    double qn2 = 0.0;                     // ‖q‖² for the dot-product bound (last thread)
+    const float* q = p.queries + static_cast<size_t>(qi) * p.pitch;
+    const int CH = p.CH, TS = CH + 1;
+    for (uint32_t c0 = 0; c0 < p.dim; c0 += CH) {
+        const int w = min(static_cast<uint32_t>(CH), p.dim - c0);   // live columns in this chunk
+        const int w4 = (w + 3) >> 2;                                // float4s (pitch is padded)
+        {
+            constexpr int U = 4;
+            const int total = nc * w4;
+            for (int i0 = 0; i0 < total; i0 += FIN_THREADS * U) {
+                float4 v[U];
+                int rr[U], cc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * FIN_THREADS + tid;
+                    rr[u] = -1;
+                    if (i < total) {
+                        rr[u] = i / w4;
+                        cc[u] = i - rr[u] * w4;
+                        v[u] = *reinterpret_cast<const float4*>(
+                            p.rows + static_cast<size_t>(s_pos[rr[u]]) * p.pitch + c0 + cc[u] * 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (rr[u] >= 0) {
+                        float* t = s_tile + rr[u] * TS + cc[u] * 4;
+                        t[0] = v[u].x; t[1] = v[u].y; t[2] = v[u].z; t[3] = v[u].w;
+                    }
+                }
+            }
+        }
+        for (int i = tid; i < w; i += FIN_THREADS) s_q[i] = q[c0 + i];
+        __syncthreads();
+        if (tid < nc) {
+            const float* t = s_tile + tid * TS;
+            if (p.metric == COSINE) {
+                for (int j = 0; j < w; ++j) {
+                    const double x = static_cast<double>(t[j]), y = static_cast<double>(s_q[j]);
+                    a0 = __dadd_rn(a0, __dmul_rn(x, y));
+                    a1 = __dadd_rn(a1, __dmul_rn(x, x));
+                    a2 = __dadd_rn(a2, __dmul_rn(y, y));
+                }
+            } else if (p.metric == EUCLIDEAN) {
+                for (int j = 0; j < w; ++j) {
+                    const double d = __dsub_rn(static_cast<double>(t[j]), static_cast<double>(s_q[j]));
+                    a0 = __dadd_rn(a0, __dmul_rn(d, d));
+                }
+            } else if (p.metric == MANHATTAN) {
+                for (int j = 0; j < w; ++j) {
+                    const double d = __dsub_rn(static_cast<double>(t[j]), static_cast<double>(s_q[j]));
+                    a0 = __dadd_rn(a0, fabs(d));
+                }
+            } else {
+                for (int j = 0; j < w; ++j)
+                    a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(t[j]), static_cast<double>(s_q[j])));
+            }
+        }
+        if (p.metric == DOT && tid == FIN_THREADS - 1) {
+            for (int j = 0; j < w; ++j) {
+                const double y = static_cast<double>(s_q[j]);
+                qn2 = __dadd_rn(qn2, __dmul_rn(y, y));
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < nc) {
+        double sc;
+        if (p.metric == COSINE) {
+            const double na = __dsqrt_rn(a1), nb = __dsqrt_rn(a2);
+            sc = (na == 0.0 || nb == 0.0) ? 0.0 : __ddiv_rn(a0, __dmul_rn(na, nb));
+            if (tid == 0) s_qnorm = nb;
+        } else if (p.metric == EUCLIDEAN) {
+            sc = sim_from_l2(a0);
+        } else if (p.metric == MANHATTAN) {
+            sc = sim_from_l1(a0);
+        } else {
+            sc = a0;
+        }
+        s_exact[tid] = sc;
+        if (sc != sc) s_nan = 1;
+    }
+    if (p.metric == DOT && tid == FIN_THREADS - 1) s_qnorm = __dsqrt_rn(qn2);
+    __syncthreads();
+
+    // ---- (3) final order: score desc, position asc (stable sort of flat.rs:116) -------------
+    const int cnt = min(static_cast<int>(p.k), nc);
+    if (tid < nc) {
+        const double me = s_exact[tid];
+        const uint32_t mp = s_pos[tid];
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) {
+            const double o = s_exact[j];
+            rank += (o > me) || (o == me && s_pos[j] < mp);
+        }
+        if (rank < cnt) {
+            const size_t o = static_cast<size_t>(qi) * p.k + rank;
+            p.out_ids[o] = p.ids ? p.ids[mp] : p.id_base + mp;
+            p.out_scores[o] = me;
+            if (p.out_pos) p.out_pos[o] = p.pos_base + mp;
+            if (rank == cnt - 1) s_kth = me;
+        }
+    }
+    for (int i = cnt + tid; i < static_cast<int>(p.k); i += FIN_THREADS) {
+        const size_t o = static_cast<size_t>(qi) * p.k + i;
+        p.out_ids[o] = ~0ull;
+        p.out_scores[o] = 0.0;
+        if (p.out_pos) p.out_pos[o] = ~0ull;
+    }
+    __syncthreads();
+
+    // ---- (4) certificate ---------------------------------------------------------------
+    if (tid == 0) {
+        uint32_t flags = (ctl ? ctl->flags : 0u) | extra_flags;
+        if (s_nan) flags |= FLAG_NAN;
+        const bool excluded_exist = p.n > static_cast<uint32_t>(nc);
+        if (excluded_exist && cnt > 0) {
+            // every excluded row has approximate score <= worst (in scan units)
+            const double worst = static_cast<double>(key_score(s_keys[nc - 1]));
+            const double u = 5.9604644775390625e-08 * p.eps_scale;  // 2^-24 × scale
+            const double nn = static_cast<double>(p.pitch);
+            const double kth = s_kth;
+            bool ok;
+            if (p.metric == COSINE) {
+                // |fl32(dot)·fl32(1/‖a‖) − dot/‖a‖| <= ((nn+8)·u)·‖q‖ ; cosine = that / ‖q‖
+                const double qn = s_qnorm;
+                const double min_nz = __longlong_as_double(p.stats->min_nz_norm_sq_bits);
+                const bool scale_ok = qn >= 1e-15 && !(min_nz < 1e-30);
+                const double bound = worst / qn + (nn + 8.0) * u * 1.01 + 1e-30;
+                ok = scale_ok && kth > bound;
+            } else if (p.metric == DOT) {
+                const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
+                const double bound = worst + (nn + 2.0) * u * 1.01 * maxn * s_qnorm + 1e-30;
+                ok = kth > bound;
+            } else if (p.metric == EUCLIDEAN) {
+                // Σ(a−q)² has only non-negative terms → RELATIVE error <= (nn+4)·u
+                double L = (-worst) * (1.0 - (nn + 4.0) * u * 1.01) - 1e-36;
+                L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                ok = kth > sim_from_l2(L);
+            } else {
+                double L = (-worst) * (1.0 - (nn + 2.0) * u * 1.01) - 1e-36;
+                L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                ok = kth > sim_from_l1(L);
+            }
+            if (!ok) flags |= FLAG_CERT_FAIL;
+        }
+        if (flags & (FLAG_NONFINITE | FLAG_OVERFLOW)) flags |= FLAG_CERT_FAIL;
+        p.out_counts[qi] = static_cast<uint32_t>(cnt);
+        p.out_flags[qi] = flags;
+        if (ctl) {  // re-arm the control block for the next search on this slot
+            ctl->tau = 0ull;
+            ctl->flags = 0u;
+            ctl->done = 0u;
+        }
+    }
+}
+
+}  // namespace vl
