@@ -19,6 +19,7 @@
 #include "batch.h"
 #include "hnsw.h"
 #include "kernels.h"
+#include "tc_state.h"
 
 using namespace vl;
 
@@ -110,6 +111,9 @@ struct vl_index {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // pairs
     size_t prof_n = 0;                  // pairs recorded since last read
+    // ---- tensor-core batched path ----
+    TcState tc;
+    std::mutex tc_mu;
     // ---- hnsw ----
     HnswPtr hnsw;
     int hnsw_metric = -1;
@@ -383,6 +387,7 @@ int flat_remove_pos(vl_index* h, uint32_t pos) {
         cudaFree(tmp);
         CU(e);
     }
+    h->tc.built_norm = h->tc.built_raw = 0;  // bf16 mirrors are positional: rebuild lazily
     const uint64_t id = h->ids_host[pos];
     h->id_to_pos.erase(id);
     h->ids_host.erase(h->ids_host.begin() + pos);
@@ -431,7 +436,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
     int rc = VL_OK;
-    const bool batched = fast && nq >= BATCH_MIN && h->mode != VL_MODE_FP32;
+    const bool batched = fast && nq >= BATCH_MIN;
     const uint32_t chunk = batched ? BATCH_CHUNK : NQ_CHUNK;
     for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += chunk) {
         const uint32_t m = std::min(chunk, nq - q0);
@@ -451,7 +456,18 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
                 BatchWork bw;
                 if ((st = slot_reserve_batch(s, m, &bw))) return st;
                 uint64_t nl = 0;
-                CU(launch_batch_flat(v, s.d_q, m, k, metric, Kp, bw, out, nullptr, &nl, s.stream));
+                const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
+                if (want_tc) {
+                    std::lock_guard<std::mutex> lk(h->tc_mu);  // shared bf16 query staging + maps
+                    CU(tc_prepare(&h->tc, v, h->cap, metric, m, s.stream));
+                    BatchTensor bt;
+                    bt.usable = h->tc.usable;
+                    bt.scratch = &h->tc;
+                    CU(launch_batch_flat(v, s.d_q, m, k, metric, Kp, bw, out, &bt, &nl, s.stream));
+                    CU(cudaStreamSynchronize(s.stream));
+                } else {
+                    CU(launch_batch_flat(v, s.d_q, m, k, metric, Kp, bw, out, nullptr, &nl, s.stream));
+                }
                 h->stats[ST_LAUNCHES] += nl;
             } else {
                 ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
@@ -564,6 +580,7 @@ void vl_index_destroy(vl_index* h) {
     slot_free(h->dev_slot);
     cudaFree(h->d_rows); cudaFree(h->d_inv_norm); cudaFree(h->d_ids); cudaFree(h->d_stats);
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
+    tc_state_free(&h->tc);
     if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
     delete h;
 }
@@ -728,7 +745,8 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
     const int Kp = pick_kp(k);
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
-    if (nq >= BATCH_MIN && h->mode != VL_MODE_FP32) {
+    if (nq >= BATCH_MIN) {
+        const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
         for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
             const uint32_t m = std::min(BATCH_CHUNK, nq - q0);
             BatchWork bw;
@@ -738,8 +756,14 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
                           d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
                           d_out_flags + q0};
             uint64_t nl = 0;
+            BatchTensor bt;
+            if (want_tc) {  // device API: calls on one handle are caller-ordered, no lock needed
+                CU(tc_prepare(&h->tc, v, h->cap, metric, m, stream));
+                bt.usable = h->tc.usable;
+                bt.scratch = &h->tc;
+            }
             CU(launch_batch_flat(v, d_queries + static_cast<size_t>(q0) * h->pitch, m, k, metric, Kp, bw, out,
-                                 nullptr, &nl, stream));
+                                 want_tc ? &bt : nullptr, &nl, stream));
             h->stats[ST_LAUNCHES] += nl;
         }
         return VL_OK;

@@ -17,8 +17,8 @@ struct BatchTensor {      // bf16 mirror of the arena for the tcgen05 path (batc
     const void* rows_bf16 = nullptr;   // [n][pitch] bf16 (cosine: rows pre-scaled by 1/‖row‖)
     const void* rows_bf16_raw = nullptr;  // [n][pitch] bf16, unscaled (dot, L2)
     const float* sq_norm = nullptr;    // [n] ‖row‖² fp32 (L2 via ‖x‖²+‖q‖²−2x·q)
-    double eps_scale = 1.0;
-    void* scratch = nullptr;           // kernel-private (tensor maps, bf16 queries)
+    double tc_abs = 0.0040;            // certificate: |approx − exact| <= tc_abs·‖x‖·‖q‖
+    void* scratch = nullptr;           // TcState*
 };
 
 cudaError_t batch_scan_cuda_cores(const FlatView& v, const float* d_q, uint32_t nq, int metric, uint32_t lo,

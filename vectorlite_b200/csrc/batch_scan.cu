@@ -296,7 +296,8 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     p.cand = w.cand; p.cand_count = nullptr; p.cand_max = nullptr; p.ctl = nullptr;
     p.out_ids = out.ids; p.out_scores = out.scores; p.out_pos = out.pos;
     p.out_counts = out.counts; p.out_flags = out.flags;
-    p.eps_scale = use_tc ? tc->eps_scale : 1.0;
+    p.eps_scale = 1.0;
+    p.tc_abs = use_tc ? tc->tc_abs : 0.0;
     batch_rescore_kernel<<<nq, FIN_THREADS, rescore_smem(Kp, CH), s>>>(p, w.count, w.qflags, w.capq);
     nl += 1;
     if (launches) *launches += nl;

@@ -1,12 +1,475 @@
-// batch_tc.cu — tensor-core (tcgen05 / TMEM / TMA) batched scan.  Placeholder until the kernel lands:
-// reports "not usable" so launch_batch_flat stays on the CUDA-core tile kernel.
+// batch_tc.cu — batched cosine / L2 / dot scan on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// S = Q · Xᵀ as a tile contraction: the query block is the A operand (M = 128 queries, K-major,
+// resident in shared memory for the CTA's whole life), database row tiles are the B operand
+// (N = 256 rows per tile, K-major, streamed by TMA through a 3-stage ring, optionally multicast
+// across a cluster of CTAs that work on different query blocks of the same row tiles), and the
+// 128×256 fp32 accumulator lives in TMEM, double buffered (2 × 256 of the 512 columns) so the
+// epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// TMEM lane == query: every epilogue thread owns one query, keeps that query's running threshold
+// in a register, reads its 256 scores with tcgen05.ld (32x32b.x32) and pushes the rare survivors
+// (score >= τ) to the per-query candidate buffer — the B×N score matrix never reaches memory.
+// Inputs are a bf16 mirror of the arena (rows pre-scaled by 1/‖row‖ for cosine); the selected
+// candidates are re-scored in f64 from the fp32 arena by the shared rescore/certify kernel, whose
+// certificate uses the bf16 error bound (FinalizeParams::eps_scale / tc_abs).
+//
+// Roofline: tensor pipe.  flops per pass = 2·B·N·K; one 128×256×16 MMA = 128 cycles (4096 MAC/clk/SM).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "batch.h"
+#include "tc_state.h"
 
 namespace vl {
 
-cudaError_t batch_scan_tensor(const FlatView&, const BatchTensor&, const float*, uint32_t, int, uint32_t,
-                              uint32_t, const BatchWork&, cudaStream_t) {
-    return cudaErrorNotSupported;
+namespace tc {
+constexpr int BM = 128, BN = 256, BK = 64, NSTAGE = 3, THREADS = 192, KCH_MAX = 6;
+constexpr uint32_t A_CHUNK_BYTES = BM * BK * 2;   // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr uint32_t SMEM_A = KCH_MAX * A_CHUNK_BYTES;          // 96 KB
+constexpr uint32_t SMEM_B = NSTAGE * B_STAGE_BYTES;           // 96 KB
+constexpr uint32_t SMEM_XN = 2 * BN * 4;                      // 2 KB
+constexpr uint32_t SMEM_BAR = 256;
+constexpr uint32_t SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_XN + SMEM_BAR + 1024;  // + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (static_cast<uint64_t>((saddr >> 4) & 0x3FFF)) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = 256
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+struct Params {
+    const float* sq_norm;   // [n] (L2)
+    const float* qn2;       // [nq_pad] ‖q‖² (L2)
+    const float* tau;
+    uint64_t* cand;
+    uint32_t* count;
+    uint32_t* qflags;
+    uint32_t capq, nq, row_lo, row_hi, kch, qblocks, tiles;
+};
+
+template <int METRIC, int CS>
+__global__ void __launch_bounds__(THREADS, 1)
+batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q, Params p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* s_a = base;
+    unsigned char* s_b = base + SMEM_A;
+    float* s_xn = reinterpret_cast<float*>(base + SMEM_A + SMEM_B);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + SMEM_A + SMEM_B + SMEM_XN);
+    // bars: [0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, then a_full, tmem_full[2], tmem_empty[2]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE), bar_a = smem_u32(bars + 2 * NSTAGE);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE + 1), bar_tempty = smem_u32(bars + 2 * NSTAGE + 3);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CS > 1 ? cluster_rank() : 0;
+    // work: cluster (or CTA) `cid` serves query group `qg` and row tiles t0, t0+tstride, ...
+    const uint32_t cid = blockIdx.x / CS, nclusters = gridDim.x / CS;
+    const uint32_t qgroups = (p.qblocks + CS - 1) / CS;
+    const uint32_t qg = cid % qgroups, t0 = cid / qgroups, tstride = nclusters / qgroups;
+    const uint32_t qblock = qg * CS + rank;   // may be >= qblocks (padding CTA of the last group): scores ignored
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, CS);   // one tcgen05.commit arrival from every CTA of the cluster
+        }
+        mbar_init(bar_a, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const bool active = t0 < p.tiles && tstride > 0;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0 && active) {
+            mbar_expect_tx(bar_a, p.kch * A_CHUNK_BYTES);
+            for (uint32_t kc = 0; kc < p.kch; ++kc)
+                tma_load_2d(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, bar_a, kc * BK, qblock * BM);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t0; t < p.tiles; t += tstride) {
+                const int row = static_cast<int>(p.row_lo + t * BN);
+                for (uint32_t kc = 0; kc < p.kch; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, B_STAGE_BYTES);
+                    if (CS == 1) {
+                        tma_load_2d(smem_u32(s_b + stage * B_STAGE_BYTES), &map_x, bar_full + 8 * stage, kc * BK, row);
+                    } else {
+                        constexpr uint32_t SLICE = BN / CS;  // rows loaded by this CTA, multicast to all
+                        tma_load_2d_mc(smem_u32(s_b + stage * B_STAGE_BYTES + rank * SLICE * 128), &map_x,
+                                       bar_full + 8 * stage, kc * BK, row + rank * SLICE,
+                                       static_cast<uint16_t>((1u << CS) - 1));
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0 && active) {
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
+            for (uint32_t t = t0; t < p.tiles; t += tstride) {
+                mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * BN;
+                for (uint32_t kc = 0; kc < p.kch; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(s_a + kc * A_CHUNK_BYTES), b0 = smem_u32(s_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j)
+                        umma_bf16(d, make_desc(a0 + j * 32), make_desc(b0 + j * 32), IDESC, (kc | j) != 0 ? 1u : 0u);
+                    if (CS == 1) umma_commit(bar_empty + 8 * stage);
+                    else umma_commit_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << CS) - 1));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * buf);
+                buf ^= 1;
+                if (buf == 0) tphase ^= 1;
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM lane == query =================
+        const int quarter = warp & 3;                       // TMEM lanes [32q, 32q+32) belong to this warp
+        const int etid = (warp - 2) * 32 + lane;            // 0..127 among the epilogue threads
+        const uint32_t q = qblock * BM + quarter * 32 + lane;
+        const bool qvalid = qblock < p.qblocks && q < p.nq;
+        float tau = qvalid ? __ldg(p.tau + q) : INFINITY;
+        float qn = 0.f;
+        if (METRIC == EUCLIDEAN) {
+            qn = qvalid ? __ldg(p.qn2 + q) : 0.f;
+            tau += qn;                                      // compare 2·acc − ‖x‖² against τ + ‖q‖²
+        }
+        bool nonfinite = false;
+        if (active) {
+            uint32_t buf = 0, tphase = 0;
+            for (uint32_t t = t0; t < p.tiles; t += tstride) {
+                const uint32_t row0 = p.row_lo + t * BN;
+                if (METRIC == EUCLIDEAN) {
+                    // stage ‖x‖² of the tile's rows (all epilogue warps read all 256 of them)
+                    for (int i = etid; i < BN; i += 128) {
+                        const uint32_t r = row0 + i;
+                        s_xn[buf * BN + i] = r < p.row_hi ? __ldg(p.sq_norm + r) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait(bar_tfull + 8 * buf, tphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + buf * BN + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float s = __uint_as_float(v[i]);
+                        if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -s_xn[buf * BN + c0 + i]);
+                        if (s >= tau || !(s == s)) {
+                            const uint32_t r = row0 + c0 + i;
+                            if (qvalid && r < p.row_hi) {
+                                if (METRIC == EUCLIDEAN) s -= qn;   // back to −‖x−q‖²
+                                if (!isfinite(s)) nonfinite = true;
+                                const uint32_t idx = atomicAdd(p.count + q, 1u);
+                                if (idx < p.capq) p.cand[static_cast<size_t>(q) * p.capq + idx] = make_key(s, r);
+                                else atomicOr(p.qflags + q, FLAG_OVERFLOW);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                buf ^= 1;
+                if (buf == 0) tphase ^= 1;
+            }
+        }
+        if (nonfinite && qvalid) atomicOr(p.qflags + q, FLAG_NONFINITE);
+    }
+
+    tc_fence_before();
+    if (CS > 1) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// fp32 arena rows → bf16 mirror [n][KP] (cosine: scaled by 1/‖row‖), zero padded to KP
+__global__ void to_bf16_rows_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm, uint64_t first,
+                                    uint64_t n, uint32_t dim, uint32_t pitch, uint32_t KP, int normalise,
+                                    __nv_bfloat16* out, float* sq_norm) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const float* src = rows + (first + r) * pitch;
+        const float sc = normalise ? inv_norm[first + r] : 1.f;
+        double ss = 0.0;
+        for (uint32_t c = lane; c < KP; c += 32) {
+            const float x = c < dim ? src[c] : 0.f;
+            ss += static_cast<double>(x) * x;
+            out[(first + r) * KP + c] = __float2bfloat16_rn(x * sc);
+        }
+        if (sq_norm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+            if (lane == 0) sq_norm[first + r] = static_cast<float>(ss);
+        }
+    }
+}
+
+// fp32 queries [nq][pitch] → bf16 [nq_pad][KP] (+ ‖q‖² for L2); rows >= nq are zero
+__global__ void to_bf16_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t nq_pad, uint32_t dim,
+                                       uint32_t pitch, uint32_t KP, __nv_bfloat16* out, float* qn2) {
+    const uint32_t r = blockIdx.x;
+    double ss = 0.0;
+    for (uint32_t c = threadIdx.x; c < KP; c += blockDim.x) {
+        const float x = (r < nq && c < dim) ? q[static_cast<size_t>(r) * pitch + c] : 0.f;
+        ss += static_cast<double>(x) * x;
+        out[static_cast<size_t>(r) * KP + c] = __float2bfloat16_rn(x);
+    }
+    __shared__ double s_red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (uint32_t i = 0; i < (blockDim.x + 31) / 32; ++i) t += s_red[i];
+        qn2[r] = static_cast<float>(t);
+    }
+    (void)nq_pad;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t KP, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {KP, rows};
+    const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(KP) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(tc::BK), box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int tc_cluster_size() {
+    static int cs = -1;
+    if (cs < 0) {
+        cs = 1;
+        if (const char* e = std::getenv("VL_TC_CLUSTER")) cs = atoi(e);
+        if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+    }
+    return cs;
+}
+
+void tc_state_free(TcState* t) {
+    if (!t) return;
+    cudaFree(t->rows_norm); cudaFree(t->rows_raw); cudaFree(t->sq_norm); cudaFree(t->q_bf16); cudaFree(t->qn2);
+    *t = TcState();
+}
+
+// bring the bf16 mirror(s) needed by `metric` up to date with the arena (rows [0, n))
+cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int metric, uint32_t nq, cudaStream_t s) {
+    if (v.dim > tc::KCH_MAX * tc::BK || !encode_fn()) { t->usable = false; return cudaSuccess; }
+    const uint32_t KP = (v.dim + tc::BK - 1) / tc::BK * tc::BK;
+    cudaError_t e;
+    if (t->cap < arena_cap || t->KP != KP) {  // (re)allocate lazily per mirror below
+        cudaFree(t->rows_norm); cudaFree(t->rows_raw); cudaFree(t->sq_norm);
+        t->rows_norm = t->rows_raw = nullptr; t->sq_norm = nullptr;
+        t->built_norm = t->built_raw = 0;
+        t->cap = arena_cap;
+        t->KP = KP;
+    }
+    const bool cosine = metric == COSINE;
+    __nv_bfloat16** mirror = reinterpret_cast<__nv_bfloat16**>(cosine ? &t->rows_norm : &t->rows_raw);
+    uint64_t* built = cosine ? &t->built_norm : &t->built_raw;
+    if (!*mirror) {
+        if ((e = cudaMalloc(mirror, t->cap * KP * 2)) != cudaSuccess) { t->usable = false; cudaGetLastError(); return cudaSuccess; }
+        *built = 0;
+    }
+    if (!cosine && !t->sq_norm) {
+        if ((e = cudaMalloc(&t->sq_norm, t->cap * 4)) != cudaSuccess) { t->usable = false; cudaGetLastError(); return cudaSuccess; }
+    }
+    if (*built < v.n) {
+        const uint64_t m = v.n - *built;
+        uint64_t blocks = std::min<uint64_t>((m + 7) / 8, 148 * 16);
+        tc::to_bf16_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+            v.rows, v.inv_norm, *built, m, v.dim, v.pitch, KP, cosine ? 1 : 0, *mirror, cosine ? nullptr : t->sq_norm);
+        *built = v.n;
+        t->maps_n = 0;  // force re-encode
+    }
+    const uint32_t nq_pad = (nq + tc::BM - 1) / tc::BM * tc::BM;
+    if (t->q_cap < nq_pad) {
+        cudaFree(t->q_bf16); cudaFree(t->qn2);
+        t->q_bf16 = nullptr; t->qn2 = nullptr;
+        if ((e = cudaMalloc(&t->q_bf16, static_cast<size_t>(nq_pad) * KP * 2)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&t->qn2, static_cast<size_t>(nq_pad) * 4)) != cudaSuccess) return e;
+        t->q_cap = nq_pad;
+    }
+    t->usable = true;
+    return cudaGetLastError();
+}
+
+template <int METRIC, int CS>
+static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mq, const tc::Params& p, int grid, cudaStream_t s) {
+    auto kern = tc::batch_scan_tc_kernel<METRIC, CS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CS > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, mx, mq, p);
+}
+
+cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const float* d_q, uint32_t nq, int metric,
+                              uint32_t lo, uint32_t hi, const BatchWork& w, cudaStream_t s) {
+    TcState* t = static_cast<TcState*>(bt.scratch);
+    if (!t || !t->usable) return cudaErrorNotSupported;
+    const uint32_t KP = t->KP;
+    const uint32_t nq_pad = (nq + tc::BM - 1) / tc::BM * tc::BM;
+    const int CS = tc_cluster_size();
+    if (lo == 0) {  // first stage of a batch: convert the queries, (re)encode the maps
+        tc::to_bf16_queries_kernel<<<nq_pad, 128, 0, s>>>(d_q, nq, nq_pad, v.dim, v.pitch, KP,
+                                                        static_cast<__nv_bfloat16*>(t->q_bf16), t->qn2);
+        const void* mirror = metric == COSINE ? t->rows_norm : t->rows_raw;
+        if (t->maps_n != v.n || t->maps_base != mirror || t->maps_cs != CS) {
+            if (!make_map(&t->map_x, mirror, v.n, KP, tc::BN / CS)) return cudaErrorUnknown;
+            t->maps_n = v.n; t->maps_base = mirror; t->maps_cs = CS;
+        }
+        if (t->mapq_rows != nq_pad || t->mapq_base != t->q_bf16) {
+            if (!make_map(&t->map_q, t->q_bf16, nq_pad, KP, tc::BM)) return cudaErrorUnknown;
+            t->mapq_rows = nq_pad; t->mapq_base = t->q_bf16;
+        }
+    }
+    tc::Params p;
+    p.sq_norm = t->sq_norm; p.qn2 = t->qn2; p.tau = w.tau; p.cand = w.cand; p.count = w.count; p.qflags = w.qflags;
+    p.capq = w.capq; p.nq = nq; p.row_lo = lo; p.row_hi = hi; p.kch = KP / tc::BK;
+    p.qblocks = nq_pad / tc::BM;
+    p.tiles = (hi - lo + tc::BN - 1) / tc::BN;
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t qgroups = (p.qblocks + CS - 1) / CS;
+    // clusters per query group: as many as fit (cluster placement may strand a few SMs for CS = 4)
+    uint32_t max_clusters = static_cast<uint32_t>(sms) / CS;
+    if (CS == 4) max_clusters = std::min<uint32_t>(max_clusters, 33);
+    uint32_t per_group = std::max<uint32_t>(1, max_clusters / qgroups);
+    per_group = std::min<uint32_t>(per_group, p.tiles);
+    const int grid = static_cast<int>(per_group * qgroups * CS);
+#define VL_TC_LAUNCH(M)                                                          \
+    (CS == 1 ? launch_tc<M, 1>(t->map_x, t->map_q, p, grid, s)                  \
+             : CS == 2 ? launch_tc<M, 2>(t->map_x, t->map_q, p, grid, s) : launch_tc<M, 4>(t->map_x, t->map_q, p, grid, s))
+    switch (metric) {
+        case COSINE: return VL_TC_LAUNCH(COSINE);
+        case EUCLIDEAN: return VL_TC_LAUNCH(EUCLIDEAN);
+        case DOT: return VL_TC_LAUNCH(DOT);
+        default: return cudaErrorNotSupported;
+    }
+#undef VL_TC_LAUNCH
 }
 
 }  // namespace vl

@@ -23,7 +23,8 @@ struct FinalizeParams {
     uint64_t* out_pos;
     uint32_t* out_counts;
     uint32_t* out_flags;
-    double eps_scale;  // multiplies the per-term rounding unit (1 = fp32 scan, larger for bf16)
+    double eps_scale;  // multiplies the per-term rounding unit (1 = fp32 scan)
+    double tc_abs;     // > 0: bf16 tensor-core scan, |approx − exact| <= tc_abs·‖x‖·‖q‖ (absolute)
 };
 
 __device__ __forceinline__ double sim_from_l2(double ss) {  // lib.rs:485-488
@@ -108,7 +109,7 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
                     a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(t[j]), static_cast<double>(s_q[j])));
             }
         }
-        if (p.metric == DOT && tid == FIN_THREADS - 1) {
+        if (p.metric != COSINE && p.metric != MANHATTAN && tid == FIN_THREADS - 1) {
             for (int j = 0; j < w; ++j) {
                 const double y = static_cast<double>(s_q[j]);
                 qn2 = __dadd_rn(qn2, __dmul_rn(y, y));
@@ -132,7 +133,7 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
         s_exact[tid] = sc;
         if (sc != sc) s_nan = 1;
     }
-    if (p.metric == DOT && tid == FIN_THREADS - 1) s_qnorm = __dsqrt_rn(qn2);
+    if (p.metric != COSINE && p.metric != MANHATTAN && tid == FIN_THREADS - 1) s_qnorm = __dsqrt_rn(qn2);
     __syncthreads();
 
     // ---- (3) final order: score desc, position asc (stable sort of flat.rs:116) -------------
@@ -173,7 +174,21 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
             const double nn = static_cast<double>(p.pitch);
             const double kth = s_kth;
             bool ok;
-            if (p.metric == COSINE) {
+            if (p.tc_abs > 0.0) {
+                // bf16 inputs: x̃ = x(1+δ), |δ| <= 2^-9 each side → |Σx̃q̃ − Σxq| <= (2^-8+2^-18)·‖x‖‖q‖,
+                // plus fp32 accumulation in the tensor core; tc_abs covers both with margin.
+                const double qn = s_qnorm;
+                const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
+                if (p.metric == COSINE) {       // rows pre-normalised: scan units are cos·‖q‖
+                    ok = qn >= 1e-15 && kth > worst / qn + p.tc_abs;
+                } else if (p.metric == DOT) {
+                    ok = kth > worst + p.tc_abs * maxn * qn + 1e-30;
+                } else {                        // −‖x−q‖² from ‖x‖² + ‖q‖² − 2x·q
+                    double L = (-worst) - 2.0 * p.tc_abs * maxn * qn - 2e-6 * (maxn * maxn + qn * qn) - 1e-36;
+                    L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                    ok = kth > sim_from_l2(L);
+                }
+            } else if (p.metric == COSINE) {
                 // |fl32(dot)·fl32(1/‖a‖) − dot/‖a‖| <= ((nn+8)·u)·‖q‖ ; cosine = that / ‖q‖
                 const double qn = s_qnorm;
                 const double min_nz = __longlong_as_double(p.stats->min_nz_norm_sq_bits);
