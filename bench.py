@@ -300,7 +300,7 @@ def main():
         e2e_dt = float(t.item())
     e2e_qps = e2e_steps * QUERIES_PER_STEP / e2e_dt * world
 
-    # ---- extras: other metrics -------------------------------------------------------------------
+    # ---- extras: other metrics, batched (B=1024) tensor-core / CUDA-core pipelines ---------------------
     extras = {}
     if args.extras:
         for name, mid in METRIC_NAMES.items():
@@ -312,6 +312,33 @@ def main():
             f()
             t_ms = timed(f, 5)
             extras[f"flat_b1_{name}_qps"] = 5 * QUERIES_PER_STEP / (t_ms * 1e-3)
+        B = 1024
+        bq = oracle.synth_rows(43, 1000, B, DIM)
+        d_bq = torch.from_numpy(bq).to(dev)
+        tc_peak = None
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            tc_peak = json.load(open(pk)).get("bf16_tflops_sustained")
+        for name, mid in METRIC_NAMES.items():
+            m2 = vl.SimilarityMetric(mid)
+            reps = 2 if name == "manhattan" else 5
+
+            def g():
+                idx.search_device(d_bq, k, m2)
+            g()
+            torch.cuda.synchronize()
+            flg = idx._buffers(B, k)["flg"]
+            failed = int((flg[0] & 1).sum().item())
+            t_ms = timed(g, reps) / reps
+            qps = B / (t_ms * 1e-3) * world
+            rec = {"qps": qps, "ms_per_batch": t_ms, "cert_failed_of_1024": failed}
+            if name != "manhattan":
+                tf = 2.0 * B * n_shard * DIM / (t_ms * 1e-3) / 1e12
+                rec.update({"tflops_whole_pipeline": tf, "frac_of_measured_bf16_sustained": tf / tc_peak if tc_peak else None})
+            else:
+                rec.update({"lane_ops_per_s": 2.0 * B * n_shard * DIM / (t_ms * 1e-3)})
+            extras[f"flat_b1024_{name}"] = rec
+        extras["tc_cluster"] = int(os.environ.get("VL_TC_CLUSTER", "1"))
 
     # ---- CPU baseline + sampled oracle check (rank 0, N = 1 only) ----------------------------------
     cpu = None

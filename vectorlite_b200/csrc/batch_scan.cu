@@ -155,43 +155,71 @@ batch_scan_cc_kernel(const float* __restrict__ rows, const float* __restrict__ i
     }
 }
 
-// per query: sort the candidate buffer (descending), keep the best Kp, publish the new threshold
+// per query: keep the best Kp candidates and publish the new threshold.  8-pass MSB radix select
+// over the 64-bit keys (unique: they embed the row position) finds the exact Kp-th largest key T in
+// shared memory; the Kp keys >= T are written back unordered (the rescore kernel ranks them).
 __global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint32_t* count, float* tau,
-                                                           uint32_t capq, int Kp) {
+                                                           uint32_t capq, int Kp, uint32_t n_override) {
     extern __shared__ __align__(16) unsigned char sm[];
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(sm);  // [capq rounded to pow2]
+    uint64_t* s_k = reinterpret_cast<uint64_t*>(sm);  // [capq]
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_bin, s_need, s_out;
     const uint32_t q = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int n = static_cast<int>(min(count[q], capq));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = static_cast<int>(n_override ? n_override : min(count[q], capq));
     if (n <= Kp) {
-        if (tid == 0) count[q] = n;  // clamp (overflow already flagged)
+        if (tid == 0) count[q] = n;  // clamp (overflow already flagged); threshold unchanged
         return;
     }
-    int len = 2;
-    while (len < n) len <<= 1;
     uint64_t* mine = cand + static_cast<size_t>(q) * capq;
-    for (int i = tid; i < len; i += 256) s_keys[i] = i < n ? mine[i] : 0ull;
-    __syncthreads();
-    for (int k = 2; k <= len; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (len >> 1); t += 256) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int pp = i | j;
-                const bool desc = (i & k) == 0;
-                const uint64_t a = s_keys[i], b = s_keys[pp];
-                if ((a < b) == desc) { s_keys[i] = b; s_keys[pp] = a; }
-            }
-            __syncthreads();
+    for (int i = tid; i < n; i += 256) s_k[i] = mine[i];
+    if (tid == 0) { s_need = static_cast<uint32_t>(Kp); s_out = 0; }
+    uint64_t prefix = 0;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        s_hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) {
+            const uint64_t key = s_k[i];
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                atomicAdd(&s_hist[(key >> shift) & 255], 1u);
         }
-    for (int i = tid; i < Kp; i += 256) mine[i] = s_keys[i];
+        __syncthreads();
+        const uint32_t need = s_need;  // read before anybody may update it (barrier below)
+        // suffix sums from the top bin down: thread t owns bin 255 − t
+        const uint32_t mycount = s_hist[255 - tid];
+        uint32_t incl = mycount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t offset = 0;
+        for (int w2 = 0; w2 < warp; ++w2) offset += s_wsum[w2];
+        incl += offset;
+        if (incl >= need && incl - mycount < need) {  // exactly one thread: the bin holding the need-th key
+            s_bin = 255 - tid;
+            s_need = need - (incl - mycount);
+        }
+        __syncthreads();
+        prefix |= static_cast<uint64_t>(s_bin) << shift;
+    }
+    // prefix is now the exact Kp-th largest key
+    for (int i = tid; i < n; i += 256) {
+        const uint64_t key = s_k[i];
+        if (key >= prefix) mine[atomicAdd(&s_out, 1u)] = key;
+    }
     if (tid == 0) {
         count[q] = Kp;
-        tau[q] = key_score(s_keys[Kp - 1]);
+        tau[q] = key_score(prefix);
     }
 }
 
 // per query: load the (sorted, <= Kp) survivors and run the shared rescore / rank / certify phases
-__global__ void __launch_bounds__(FIN_THREADS, 1) batch_rescore_kernel(FinalizeParams p, const uint32_t* count,
+__global__ void __launch_bounds__(FIN_THREADS) batch_rescore_kernel(FinalizeParams p, const uint32_t* count,
                                                                        const uint32_t* qflags, uint32_t capq) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -281,13 +309,15 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
         if (use_tc) e = batch_scan_tensor(v, *tc, d_queries, nq, metric, lo, hi, w, s);
         else e = batch_scan_cuda_cores(v, d_queries, nq, metric, lo, hi, w, s);
         if (e != cudaSuccess) return e;
-        batch_select_kernel<<<nq, 256, sel_len * sizeof(uint64_t), s>>>(w.cand, w.count, w.tau, w.capq, Kp);
+        const uint32_t n_override = (use_tc && lo == 0 && hi <= w.capq) ? hi - lo : 0u;  // stage 0 of the tensor path is atomics-free
+        batch_select_kernel<<<nq, 256, sel_len * sizeof(uint64_t), s>>>(w.cand, w.count, w.tau, w.capq, Kp, n_override);
         nl += 2;
     }
     // rescore + certify
     const size_t budget = 180 * 1024;
     int CH = static_cast<int>((v.dim + 3) / 4 * 4);
     while (CH > 4 && rescore_smem(Kp, CH) > budget) CH = (CH / 2 + 3) / 4 * 4;
+    if (nq >= 64 && CH > 128) CH = 128;  // many queries: smaller staging tile → 4 CTAs per SM instead of 1
     FinalizeParams p;
     p.rows = v.rows; p.ids = v.ids; p.stats = v.stats; p.queries = d_queries;
     p.id_base = v.id_base; p.pos_base = v.pos_base;

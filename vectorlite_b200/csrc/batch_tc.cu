@@ -31,7 +31,9 @@ constexpr uint32_t SMEM_A = KCH_MAX * A_CHUNK_BYTES;          // 96 KB
 constexpr uint32_t SMEM_B = NSTAGE * B_STAGE_BYTES;           // 96 KB
 constexpr uint32_t SMEM_XN = 2 * BN * 4;                      // 2 KB
 constexpr uint32_t SMEM_BAR = 256;
-constexpr uint32_t SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_XN + SMEM_BAR + 1024;  // + alignment slack
+constexpr int QCAP = 16;                                      // survivor queue entries per epilogue thread
+constexpr uint32_t SMEM_PQ = QCAP * 128 * 8;                  // 16 KB, interleaved [QCAP][128]
+constexpr uint32_t SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_XN + SMEM_BAR + SMEM_PQ + 1024;  // + alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -78,7 +80,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// v[i] for a runtime i without spilling v to local memory (31 selects; survivors are rare)
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int i) {
+    uint32_t r = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) r = (j == i) ? v[j] : r;
+    return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -107,6 +116,7 @@ struct Params {
     uint32_t* count;
     uint32_t* qflags;
     uint32_t capq, nq, row_lo, row_hi, kch, qblocks, tiles;
+    uint32_t direct;        // stage 0: every score is kept, slot = row − row_lo, no atomics
 };
 
 template <int METRIC, int CS>
@@ -122,6 +132,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE), bar_a = smem_u32(bars + 2 * NSTAGE);
     const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE + 1), bar_tempty = smem_u32(bars + 2 * NSTAGE + 3);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+    unsigned long long* s_pq = reinterpret_cast<unsigned long long*>(base + SMEM_A + SMEM_B + SMEM_XN + SMEM_BAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CS > 1 ? cluster_rank() : 0;
@@ -216,6 +227,20 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             tau += qn;                                      // compare 2·acc − ‖x‖² against τ + ‖q‖²
         }
         bool nonfinite = false;
+        // Survivors are queued in shared memory ([QCAP][128], conflict-free) and flushed with ONE
+        // slot-reserving atomicAdd per QCAP entries: the scan loop never waits on an L2 round trip.
+        int nloc = 0;
+        unsigned long long* my_q = s_pq + etid;
+        auto flush = [&]() {
+            if (nloc) {
+                const uint32_t idx0 = atomicAdd(p.count + q, static_cast<uint32_t>(nloc));
+                for (int i = 0; i < nloc; ++i) {
+                    if (idx0 + i < p.capq) p.cand[static_cast<size_t>(q) * p.capq + idx0 + i] = my_q[i * 128];
+                    else atomicOr(p.qflags + q, FLAG_OVERFLOW);
+                }
+                nloc = 0;
+            }
+        };
         if (active) {
             uint32_t buf = 0, tphase = 0;
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
@@ -230,25 +255,55 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 }
                 mbar_wait(bar_tfull + 8 * buf, tphase);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + buf * BN + c0 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+                const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+                const float* xn = s_xn + buf * BN;
+                // one 32-column chunk: branch-free survivor mask (2 instructions per score), then a
+                // compact loop over the (rare) set bits — keeps the hot loop inside the instruction cache
+                auto process = [&](const uint32_t (&v)[32], int c0) {
+                    if (p.direct) {
+                        if (qvalid) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const uint32_t r = row0 + c0 + i;
+                                float s = __uint_as_float(v[i]);
+                                if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]) - qn;
+                                if (!isfinite(s)) nonfinite = true;
+                                if (r < p.row_hi) p.cand[static_cast<size_t>(q) * p.capq + (r - p.row_lo)] = make_key(s, r);
+                            }
+                        }
+                        return;
+                    }
+                    uint32_t mask = 0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         float s = __uint_as_float(v[i]);
-                        if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -s_xn[buf * BN + c0 + i]);
-                        if (s >= tau || !(s == s)) {
-                            const uint32_t r = row0 + c0 + i;
-                            if (qvalid && r < p.row_hi) {
-                                if (METRIC == EUCLIDEAN) s -= qn;   // back to −‖x−q‖²
-                                if (!isfinite(s)) nonfinite = true;
-                                const uint32_t idx = atomicAdd(p.count + q, 1u);
-                                if (idx < p.capq) p.cand[static_cast<size_t>(q) * p.capq + idx] = make_key(s, r);
-                                else atomicOr(p.qflags + q, FLAG_OVERFLOW);
-                            }
+                        if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]);
+                        mask |= !(s < tau) ? (1u << i) : 0u;   // s >= tau, or NaN
+                    }
+                    while (mask) {
+                        const int i = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t r = row0 + c0 + i;
+                        if (qvalid && r < p.row_hi) {
+                            float s = __uint_as_float(select32(v, i));
+                            if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]) - qn;   // −‖x−q‖²
+                            if (!isfinite(s)) nonfinite = true;
+                            my_q[nloc * 128] = make_key(s, r);
+                            if (++nloc == QCAP) flush();
                         }
                     }
+                };
+                uint32_t va[32], vb[32];
+                tmem_ld32(tbase, va);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 64) {   // two chunks per iteration, loads double buffered
+                    tmem_ld32(tbase + c0 + 32, vb);
+                    process(va, c0);
+                    tmem_ld_wait();
+                    if (c0 + 64 < BN) tmem_ld32(tbase + c0 + 64, va);
+                    process(vb, c0 + 32);
+                    tmem_ld_wait();
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -257,6 +312,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (buf == 0) tphase ^= 1;
             }
         }
+        flush();
         if (nonfinite && qvalid) atomicOr(p.qflags + q, FLAG_NONFINITE);
     }
 
@@ -449,6 +505,7 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     p.capq = w.capq; p.nq = nq; p.row_lo = lo; p.row_hi = hi; p.kch = KP / tc::BK;
     p.qblocks = nq_pad / tc::BM;
     p.tiles = (hi - lo + tc::BN - 1) / tc::BN;
+    p.direct = (lo == 0 && hi <= w.capq) ? 1u : 0u;
     int sms = 148;
     int dev = 0;
     cudaGetDevice(&dev);
