@@ -134,3 +134,29 @@ def test_dim_384_generic_and_specialised_paths(vl, oracle_mod):
         gi, gs, gc = h.search_batch(q, k, vl.SimilarityMetric.Cosine, 64)
         st, truth, _ = oracle_mod.flat_search_batch(rows, None, q, k, 0, nthreads=8)
         assert _recall(gi, gc, truth) >= 0.95, dim
+
+
+@pytest.mark.parametrize("clusters", [0, 1024])
+def test_recall_vs_committed_reference_numbers_384d(vl, oracle_mod, clusters):
+    """Equal (M, M0, ef_construction = 400 [crate default], ef) on the bench's 384-d synthetic data:
+    recall@10 vs exact flat must be no lower than the reference restatement's, whose numbers were
+    generated once by tests/golden/make_hnsw_reference_recall.py (CPU, ~10 min single-threaded) and
+    committed."""
+    import json, os
+    path = os.path.join(os.path.dirname(__file__), "golden", f"hnsw_reference_recall_n20000_c{clusters}_M16.json")
+    ref = json.load(open(path))
+    n, dim, k, nq = ref["n"], ref["dim"], ref["k"], ref["nq"]
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters)
+    queries = oracle_mod.synth_rows(43, 0, nq, dim, clusters)
+    flat = vl.FlatIndex(dim)
+    flat.add_batch(np.arange(n, dtype=np.uint64), rows)
+    truth, _, _ = flat.search_batch(queries, k, vl.SimilarityMetric.Cosine)     # exact (certified) flat
+    h = vl.HNSWIndex(dim, vl.SimilarityMetric.Cosine, M=ref["M"], M0=ref["M0"], ef_construction=ref["ef_construction"])
+    h.add_batch(np.arange(n, dtype=np.uint64), rows)
+    report = {}
+    for ef_s, r in ref["sweep"].items():
+        gi, gs, gc = h.search_batch(queries, k, vl.SimilarityMetric.Cosine, int(ef_s))
+        ours = _recall(gi, gc, truth)
+        report[ef_s] = (round(ours, 3), round(r["recall_at_10"], 3), h.stats()["hnsw_visited"] // nq, int(r["visited_per_query"]))
+        assert ours >= r["recall_at_10"] - 0.01, (clusters, ef_s, ours, r["recall_at_10"])
+    print(f"clusters={clusters} ef: (ours, reference, our visited/q, reference visited/q) = {report}")
