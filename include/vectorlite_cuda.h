@@ -126,6 +126,15 @@ int vl_merge_topk_device(int device, uint32_t G, uint32_t nq, uint32_t k, const 
                          uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
                          uint32_t* d_out_counts, void* cuda_stream);
 
+/* Packed variant for a single-collective exchange.  Each shard's result block is
+ *   [ids nq*k u64][scores nq*k f64][positions nq*k u64][counts nq u32][flags nq u32]
+ * (vl_packed_result_bytes(nq,k) bytes; point vl_index_search_device's outputs at the five sections of
+ * this rank's block), the G blocks are laid out back to back as ONE all-gather leaves them. */
+uint64_t vl_packed_result_bytes(uint32_t nq, uint32_t k);
+int vl_merge_topk_packed_device(int device, uint32_t G, uint32_t nq, uint32_t k, const void* d_packed,
+                                uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                                uint32_t* d_out_counts, void* cuda_stream);
+
 /* ---- accessors ------------------------------------------------------------------------ */
 uint64_t vl_index_len(const vl_index* h);          /* VectorIndex::len */
 uint32_t vl_index_dim(const vl_index* h);          /* VectorIndex::dimension */

@@ -1,0 +1,30 @@
+"""torchrun -n G scripts/sharded_check.py — row-sharded flat search on G real GPUs vs the unsharded
+oracle (ids + f64 scores bit-exact, all metrics, B=1 and batched), through ShardedFlatIndex."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import oracle, vectorlite_b200 as vl
+from vectorlite_b200.sharded import ShardedFlatIndex
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+n, dim, k = 200_000, 384, 10
+idx = ShardedFlatIndex(dim, rank=rank, world=world, device=lr)
+idx.fill_synthetic(42, n)
+rows = oracle.synth_rows(42, 0, n, dim) if rank == 0 else None
+queries = oracle.synth_rows(43, 0, 40, dim)
+ok = True
+for metric in vl.SimilarityMetric:
+    for qs in (queries[:1], queries[:5], queries):          # B=1, small, batched (tensor / CUDA-core tiles)
+        gi, gs, gc = idx.search(qs, k, metric)
+        if rank == 0:
+            st, oi, os_ = oracle.flat_search_batch(rows, None, qs, k, int(metric), nthreads=8)
+            good = np.array_equal(gi, oi) and np.array_equal(gs.view(np.uint64), os_.view(np.uint64))
+            ok = ok and good
+            print(f"metric={metric.name} nq={qs.shape[0]} {'OK' if good else 'MISMATCH'}", flush=True)
+if rank == 0:
+    print("SHARDED_CHECK", "PASS" if ok else "FAIL", "world", world)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

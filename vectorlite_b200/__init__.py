@@ -130,6 +130,8 @@ def lib():
         "vl_index_search_f64": (i32, [vp, dp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
         "vl_index_search_device": (i32, [vp, vp, u32, u32, i32, u32, vp, vp, vp, vp, vp, vp]),
         "vl_merge_topk_device": (i32, [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "vl_packed_result_bytes": (u64, [u32, u32]),
+        "vl_merge_topk_packed_device": (i32, [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]),
         "vl_index_len": (u64, [vp]),
         "vl_index_dim": (u32, [vp]),
         "vl_index_type_of": (i32, [vp]),

@@ -808,9 +808,28 @@ int vl_merge_topk_device(int device, uint32_t G, uint32_t nq, uint32_t k, const 
     if (!d_ids || !d_scores || !d_pos || !d_counts || !d_out_ids || !d_out_scores || !d_out_counts)
         return fail(VL_ERR_INVALID, "null argument");
     DeviceGuard dg(device);
-    CU(launch_merge_topk(G, nq, k, d_ids, d_scores, d_pos, d_counts, d_out_ids, d_out_scores, d_out_pos,
+    CU(launch_merge_topk(G, nq, k, d_ids, d_scores, d_pos, d_counts, 0, d_out_ids, d_out_scores, d_out_pos,
                          d_out_counts, static_cast<cudaStream_t>(cuda_stream)));
     return VL_OK;
+}
+
+int vl_merge_topk_packed_device(int device, uint32_t G, uint32_t nq, uint32_t k, const void* d_packed,
+                                uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                                uint32_t* d_out_counts, void* cuda_stream) {
+    if (!d_packed || !d_out_ids || !d_out_scores || !d_out_counts) return fail(VL_ERR_INVALID, "null argument");
+    DeviceGuard dg(device);
+    const uint64_t nk8 = static_cast<uint64_t>(nq) * k * 8;
+    const uint64_t stride = vl_packed_result_bytes(nq, k);
+    const char* b = static_cast<const char*>(d_packed);
+    CU(launch_merge_topk(G, nq, k, reinterpret_cast<const uint64_t*>(b), reinterpret_cast<const double*>(b + nk8),
+                         reinterpret_cast<const uint64_t*>(b + 2 * nk8), reinterpret_cast<const uint32_t*>(b + 3 * nk8),
+                         stride, d_out_ids, d_out_scores, d_out_pos, d_out_counts,
+                         static_cast<cudaStream_t>(cuda_stream)));
+    return VL_OK;
+}
+
+uint64_t vl_packed_result_bytes(uint32_t nq, uint32_t k) {
+    return static_cast<uint64_t>(nq) * k * 24 + static_cast<uint64_t>(nq) * 8;
 }
 
 uint64_t vl_index_len(const vl_index* h) {

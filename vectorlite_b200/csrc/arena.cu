@@ -117,37 +117,46 @@ __device__ __forceinline__ bool better(double sa, uint64_t pa, double sb, uint64
     return sa > sb || (sa == sb && pa < pb);
 }
 
+// rank_stride: bytes between consecutive shards' arrays (0 = dense [G][nq][k] / [G][nq])
 __global__ void __launch_bounds__(256) merge_topk_kernel(uint32_t G, uint32_t nq, uint32_t k,
-                                                         const uint64_t* __restrict__ ids,
-                                                         const double* __restrict__ scores,
-                                                         const uint64_t* __restrict__ pos,
-                                                         const uint32_t* __restrict__ counts,
+                                                         const uint64_t* __restrict__ ids0,
+                                                         const double* __restrict__ scores0,
+                                                         const uint64_t* __restrict__ pos0,
+                                                         const uint32_t* __restrict__ counts0, uint64_t rank_stride,
                                                          uint64_t* out_ids, double* out_scores,
                                                          uint64_t* out_pos, uint32_t* out_counts) {
     const uint32_t q = blockIdx.x;
+    const uint64_t st8 = rank_stride ? rank_stride : static_cast<uint64_t>(nq) * k * 8;
+    const uint64_t st4 = rank_stride ? rank_stride : static_cast<uint64_t>(nq) * 4;
+    auto ids_of = [&](uint32_t g) { return reinterpret_cast<const uint64_t*>(reinterpret_cast<const char*>(ids0) + g * st8); };
+    auto sc_of = [&](uint32_t g) { return reinterpret_cast<const double*>(reinterpret_cast<const char*>(scores0) + g * st8); };
+    auto pos_of = [&](uint32_t g) { return reinterpret_cast<const uint64_t*>(reinterpret_cast<const char*>(pos0) + g * st8); };
+    auto cnt_of = [&](uint32_t g) { return reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(counts0) + g * st4); };
     uint32_t total = 0;
-    for (uint32_t g = 0; g < G; ++g) total += counts[g * nq + q];
+    for (uint32_t g = 0; g < G; ++g) total += cnt_of(g)[q];
     const uint32_t cnt = total < k ? total : k;
     for (uint32_t e = threadIdx.x; e < G * k; e += blockDim.x) {
         const uint32_t g = e / k, i = e - g * k;
-        if (i >= counts[g * nq + q]) continue;
-        const size_t me = (static_cast<size_t>(g) * nq + q) * k + i;
-        const double sc = scores[me];
-        const uint64_t pp = pos[me];
+        if (i >= cnt_of(g)[q]) continue;
+        const size_t me = static_cast<size_t>(q) * k + i;
+        const double sc = sc_of(g)[me];
+        const uint64_t pp = pos_of(g)[me];
         uint32_t rank = i;
         for (uint32_t g2 = 0; g2 < G; ++g2) {
             if (g2 == g) continue;
-            const size_t base = (static_cast<size_t>(g2) * nq + q) * k;
-            uint32_t lo = 0, hi = counts[g2 * nq + q];  // first index in list g2 NOT better than me
+            const size_t base = static_cast<size_t>(q) * k;
+            const double* s2 = sc_of(g2);
+            const uint64_t* p2 = pos_of(g2);
+            uint32_t lo = 0, hi = cnt_of(g2)[q];  // first index in list g2 NOT better than me
             while (lo < hi) {
                 const uint32_t mid = (lo + hi) >> 1;
-                if (better(scores[base + mid], pos[base + mid], sc, pp)) lo = mid + 1; else hi = mid;
+                if (better(s2[base + mid], p2[base + mid], sc, pp)) lo = mid + 1; else hi = mid;
             }
             rank += lo;
         }
         if (rank < cnt) {
             const size_t o = static_cast<size_t>(q) * k + rank;
-            out_ids[o] = ids[me];
+            out_ids[o] = ids_of(g)[me];
             out_scores[o] = sc;
             if (out_pos) out_pos[o] = pp;
         }
@@ -163,11 +172,11 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(uint32_t G, uint32_t nq
 
 cudaError_t launch_merge_topk(uint32_t G, uint32_t nq, uint32_t k, const uint64_t* ids,
                               const double* scores, const uint64_t* pos, const uint32_t* counts,
-                              uint64_t* out_ids, double* out_scores, uint64_t* out_pos,
+                              uint64_t rank_stride, uint64_t* out_ids, double* out_scores, uint64_t* out_pos,
                               uint32_t* out_counts, cudaStream_t s) {
     if (nq == 0 || k == 0) return cudaSuccess;
-    merge_topk_kernel<<<nq, 256, 0, s>>>(G, nq, k, ids, scores, pos, counts, out_ids, out_scores, out_pos,
-                                         out_counts);
+    merge_topk_kernel<<<nq, 256, 0, s>>>(G, nq, k, ids, scores, pos, counts, rank_stride, out_ids, out_scores,
+                                         out_pos, out_counts);
     return cudaGetLastError();
 }
 

@@ -83,7 +83,7 @@ cudaError_t launch_synth_fill(float* rows, uint64_t first_pos, uint64_t n, uint3
                               uint64_t seed, uint64_t first_row, uint32_t clusters, cudaStream_t s);
 cudaError_t launch_merge_topk(uint32_t G, uint32_t nq, uint32_t k, const uint64_t* ids,
                               const double* scores, const uint64_t* pos, const uint32_t* counts,
-                              uint64_t* out_ids, double* out_scores, uint64_t* out_pos,
+                              uint64_t rank_stride, uint64_t* out_ids, double* out_scores, uint64_t* out_pos,
                               uint32_t* out_counts, cudaStream_t s);
 
 }  // namespace vl

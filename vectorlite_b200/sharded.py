@@ -59,23 +59,23 @@ class ShardedFlatIndex:
         if key not in self._bufs:
             dev = torch.device("cuda", self.device)
             G = self.world
+            blk = int(lib().vl_packed_result_bytes(nq, k))       # bytes per shard block (multiple of 8)
+            packed = torch.zeros((G, blk // 8), dtype=torch.int64, device=dev)
             self._bufs[key] = dict(
-                ids=torch.zeros((G, nq, k), dtype=torch.int64, device=dev),
-                sc=torch.zeros((G, nq, k), dtype=torch.float64, device=dev),
-                pos=torch.zeros((G, nq, k), dtype=torch.int64, device=dev),
-                cnt=torch.zeros((G, nq), dtype=torch.int32, device=dev),
-                flg=torch.zeros((G, nq), dtype=torch.int32, device=dev),
+                packed=packed, blk=blk,
                 o_ids=torch.zeros((nq, k), dtype=torch.int64, device=dev),
                 o_sc=torch.zeros((nq, k), dtype=torch.float64, device=dev),
                 o_pos=torch.zeros((nq, k), dtype=torch.int64, device=dev),
                 o_cnt=torch.zeros((nq,), dtype=torch.int32, device=dev),
+                flg=torch.zeros((G, nq), dtype=torch.int32, device=dev),
             )
         return self._bufs[key]
 
     def search_device(self, d_queries: torch.Tensor, k: int, metric: SimilarityMetric):
         """d_queries: [nq, dim] fp32 CUDA tensor (replicated on every rank).  The shard kernel writes
-        its top-k straight into this rank's slot of the all-gather buffer; returns device tensors
-        (ids, scores, counts, flags) valid on every rank.  No host synchronisation."""
+        its top-k straight into this rank's block of the all-gather buffer; ONE all-gather and the
+        merge kernel follow.  Returns device tensors (ids, scores, counts, flags[G, nq]) valid on
+        every rank.  No host synchronisation."""
         nq = d_queries.shape[0]
         b = self._buffers(nq, k)
         r = self.rank
@@ -85,20 +85,20 @@ class ShardedFlatIndex:
                                      b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
                                      b["flg"][0].data_ptr(), stream)
             return b["o_ids"], b["o_sc"], b["o_cnt"], b["flg"]
-        self.local.search_device(d_queries.data_ptr(), nq, k, metric, b["ids"][r].data_ptr(),
-                                 b["sc"][r].data_ptr(), b["pos"][r].data_ptr(), b["cnt"][r].data_ptr(),
-                                 b["flg"][r].data_ptr(), stream)
-        if self.world > 1:
-            for name in ("ids", "sc", "pos", "cnt", "flg"):
-                t = b[name]
-                dist.all_gather_into_tensor(t.view(-1), t[r].reshape(-1).clone(), group=self.group)
-        st = lib().vl_merge_topk_device(self.device, self.world, nq, k, b["ids"].data_ptr(), b["sc"].data_ptr(),
-                                        b["pos"].data_ptr(), b["cnt"].data_ptr(), b["o_ids"].data_ptr(),
-                                        b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
-                                        C.c_void_p(stream))
+        packed = b["packed"]
+        base = packed[r].data_ptr()
+        nk8 = nq * k * 8
+        self.local.search_device(d_queries.data_ptr(), nq, k, metric, base, base + nk8, base + 2 * nk8,
+                                 base + 3 * nk8, base + 3 * nk8 + nq * 4, stream)
+        dist.all_gather_into_tensor(packed.view(-1), packed[r].clone(), group=self.group)
+        st = lib().vl_merge_topk_packed_device(self.device, self.world, nq, k, packed.data_ptr(),
+                                               b["o_ids"].data_ptr(), b["o_sc"].data_ptr(), b["o_pos"].data_ptr(),
+                                               b["o_cnt"].data_ptr(), C.c_void_p(stream))
         if st != VL_OK:
             raise VectorLiteError(st, _err())
-        return b["o_ids"], b["o_sc"], b["o_cnt"], b["flg"]
+        # flags of every shard: the last nq u32 of each block
+        flg = packed.view(torch.int32)[:, (3 * nk8 + nq * 4) // 4:(3 * nk8 + nq * 8) // 4]
+        return b["o_ids"], b["o_sc"], b["o_cnt"], flg
 
     def search(self, queries: np.ndarray, k: int, metric: SimilarityMetric):
         """Host in / host out (the e2e path): H2D of the queries, sharded search, D2H of the merged
@@ -107,7 +107,7 @@ class ShardedFlatIndex:
         d_q = q.to(torch.device("cuda", self.device), non_blocking=True)
         ids, sc, cnt, flg = self.search_device(d_q, k, metric)
         h_ids, h_sc, h_cnt, h_flg = ids.cpu(), sc.cpu(), cnt.cpu(), flg.cpu()
-        if int(h_flg.max()) != 0:
+        if int((h_flg & 1).max()) != 0:
             return self._search_exact(queries, k, metric)
         return h_ids.numpy().view(np.uint64), h_sc.numpy(), h_cnt.numpy().view(np.uint32)
 
@@ -118,20 +118,20 @@ class ShardedFlatIndex:
         b = self._buffers(nq, k)
         r = self.rank
         dev = torch.device("cuda", self.device)
-        b["ids"][r].copy_(torch.from_numpy(gi.view(np.int64)).to(dev))
-        b["sc"][r].copy_(torch.from_numpy(gs).to(dev))
-        pos = gi.astype(np.int64)  # sharded stores use id == global position
-        b["pos"][r].copy_(torch.from_numpy(pos).to(dev))
-        b["cnt"][r].copy_(torch.from_numpy(gc.view(np.int32)).to(dev))
-        if self.world > 1:
-            for name in ("ids", "sc", "pos", "cnt"):
-                t = b[name]
-                dist.all_gather_into_tensor(t.view(-1), t[r].reshape(-1).clone(), group=self.group)
+        if self.world == 1:
+            return gi, gs, gc
+        nk = nq * k
+        blk = torch.zeros(b["blk"] // 8, dtype=torch.int64)
+        blk[0:nk] = torch.from_numpy(gi.view(np.int64).reshape(-1))
+        blk[nk:2 * nk] = torch.from_numpy(gs.view(np.int64).reshape(-1))
+        blk[2 * nk:3 * nk] = torch.from_numpy(gi.astype(np.int64).reshape(-1))   # sharded stores: id == global position
+        blk.view(torch.int32)[6 * nk:6 * nk + nq] = torch.from_numpy(gc.view(np.int32))
+        b["packed"][r].copy_(blk.to(dev))
+        dist.all_gather_into_tensor(b["packed"].view(-1), b["packed"][r].clone(), group=self.group)
         stream = _current_stream()
-        st = lib().vl_merge_topk_device(self.device, self.world, nq, k, b["ids"].data_ptr(), b["sc"].data_ptr(),
-                                        b["pos"].data_ptr(), b["cnt"].data_ptr(), b["o_ids"].data_ptr(),
-                                        b["o_sc"].data_ptr(), b["o_pos"].data_ptr(), b["o_cnt"].data_ptr(),
-                                        C.c_void_p(stream))
+        st = lib().vl_merge_topk_packed_device(self.device, self.world, nq, k, b["packed"].data_ptr(),
+                                               b["o_ids"].data_ptr(), b["o_sc"].data_ptr(), b["o_pos"].data_ptr(),
+                                               b["o_cnt"].data_ptr(), C.c_void_p(stream))
         if st != VL_OK:
             raise VectorLiteError(st, _err())
         return (b["o_ids"].cpu().numpy().view(np.uint64), b["o_sc"].cpu().numpy(),
