@@ -297,21 +297,27 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     }
     batch_init_kernel<<<(nq + 255) / 256, 256, 0, s>>>(nq, w.count, w.tau, w.qflags);
     uint64_t nl = 1;
-    const uint32_t S0 = min(v.n, min(w.capq, 4096u));
-    const uint32_t S1 = min(v.n, 65536u);
-    const uint32_t bounds[4] = {0u, S0, S1, v.n};
+    // Geometric stage schedule: after a select, tau is the K'-th best of the first S rows, so the next
+    // stage over rows [S, r·S) keeps ≈ K'·(r−1) survivors per query; r is chosen so that this stays
+    // below half the candidate buffer (capq = 4096 → r = 16 for K' = 64, 9 for K' = 224, 4 for K' = 512).
+    const bool use_tc = tc && tc->usable && metric != MANHATTAN;
     uint32_t sel_len = 2;
     while (sel_len < w.capq) sel_len <<= 1;
-    const bool use_tc = tc && tc->usable && metric != MANHATTAN;
-    for (int st = 0; st < 3; ++st) {
-        const uint32_t lo = bounds[st], hi = bounds[st + 1];
-        if (hi <= lo) continue;
+    uint32_t ratio = w.capq / (2u * static_cast<uint32_t>(Kp));
+    ratio = ratio < 2u ? 2u : (ratio > 16u ? 16u : ratio);
+    uint32_t lo = 0;
+    uint64_t hi64 = min(v.n, min(w.capq, 4096u));   // stage 0: everything is kept
+    while (lo < v.n) {
+        uint32_t hi = static_cast<uint32_t>(hi64 > v.n ? v.n : hi64);
+        if (lo > 0) hi = min(v.n, (hi + 255u) & ~255u);   // later stages start on 256-row tile boundaries
         if (use_tc) e = batch_scan_tensor(v, *tc, d_queries, nq, metric, lo, hi, w, s);
         else e = batch_scan_cuda_cores(v, d_queries, nq, metric, lo, hi, w, s);
         if (e != cudaSuccess) return e;
-        const uint32_t n_override = (use_tc && lo == 0 && hi <= w.capq) ? hi - lo : 0u;  // stage 0 of the tensor path is atomics-free
+        const uint32_t n_override = (use_tc && lo == 0 && hi <= w.capq) ? hi - lo : 0u;  // tensor stage 0 is atomics-free
         batch_select_kernel<<<nq, 256, sel_len * sizeof(uint64_t), s>>>(w.cand, w.count, w.tau, w.capq, Kp, n_override);
         nl += 2;
+        lo = hi;
+        hi64 = static_cast<uint64_t>(hi) * ratio;
     }
     // rescore + certify
     const size_t budget = 180 * 1024;

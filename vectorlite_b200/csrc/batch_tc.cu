@@ -24,15 +24,19 @@
 namespace vl {
 
 namespace tc {
-constexpr int BM = 128, BN = 256, BK = 64, NSTAGE = 3, THREADS = 192, KCH_MAX = 6;
+constexpr int BM = 128, BN = 256, BK = 64, NSTAGE = 3, KCH_MAX = 6;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, half of the tile's columns each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;    // warp 0 = TMA producer, warp 1 = MMA issuer
+constexpr int TMEM_BUF_COLS = 256;   // accumulator buffers sit 256 TMEM columns apart (2 × 256 = all 512)
 constexpr uint32_t A_CHUNK_BYTES = BM * BK * 2;   // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr uint32_t SMEM_A = KCH_MAX * A_CHUNK_BYTES;          // 96 KB
 constexpr uint32_t SMEM_B = NSTAGE * B_STAGE_BYTES;           // 96 KB
 constexpr uint32_t SMEM_XN = 2 * BN * 4;                      // 2 KB
 constexpr uint32_t SMEM_BAR = 256;
-constexpr int QCAP = 16;                                      // survivor queue entries per epilogue thread
-constexpr uint32_t SMEM_PQ = QCAP * 128 * 8;                  // 16 KB, interleaved [QCAP][128]
+constexpr int QCAP = 8;                                       // survivor queue entries per epilogue thread
+constexpr uint32_t SMEM_PQ = QCAP * EPI_THREADS * 8;          // 16 KB, interleaved [QCAP][EPI_THREADS]
 constexpr uint32_t SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_XN + SMEM_BAR + SMEM_PQ + 1024;  // + alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -150,7 +154,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_init(bar_a, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4);   // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * i, EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -197,7 +201,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
                 mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + buf * BN;
+                const uint32_t d = tmem_base + buf * TMEM_BUF_COLS;
                 for (uint32_t kc = 0; kc < p.kch; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -217,7 +221,8 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     } else {
         // ================= epilogue: TMEM lane == query =================
         const int quarter = warp & 3;                       // TMEM lanes [32q, 32q+32) belong to this warp
-        const int etid = (warp - 2) * 32 + lane;            // 0..127 among the epilogue threads
+        const int etid = (warp - 2) * 32 + lane;            // 0..255 among the epilogue threads
+        const int cbase = ((warp - 2) >> 2) * (BN / 2);     // this warp's half of the tile's columns
         const uint32_t q = qblock * BM + quarter * 32 + lane;
         const bool qvalid = qblock < p.qblocks && q < p.nq;
         float tau = qvalid ? __ldg(p.tau + q) : INFINITY;
@@ -235,7 +240,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             if (nloc) {
                 const uint32_t idx0 = atomicAdd(p.count + q, static_cast<uint32_t>(nloc));
                 for (int i = 0; i < nloc; ++i) {
-                    if (idx0 + i < p.capq) p.cand[static_cast<size_t>(q) * p.capq + idx0 + i] = my_q[i * 128];
+                    if (idx0 + i < p.capq) p.cand[static_cast<size_t>(q) * p.capq + idx0 + i] = my_q[i * EPI_THREADS];
                     else atomicOr(p.qflags + q, FLAG_OVERFLOW);
                 }
                 nloc = 0;
@@ -247,15 +252,15 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const uint32_t row0 = p.row_lo + t * BN;
                 if (METRIC == EUCLIDEAN) {
                     // stage ‖x‖² of the tile's rows (all epilogue warps read all 256 of them)
-                    for (int i = etid; i < BN; i += 128) {
+                    for (int i = etid; i < BN; i += EPI_THREADS) {
                         const uint32_t r = row0 + i;
                         s_xn[buf * BN + i] = r < p.row_hi ? __ldg(p.sq_norm + r) : 0.f;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 }
                 mbar_wait(bar_tfull + 8 * buf, tphase);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+                const uint32_t tbase = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
                 const float* xn = s_xn + buf * BN;
                 // one 32-column chunk: branch-free survivor mask (2 instructions per score), then a
                 // compact loop over the (rare) set bits — keeps the hot loop inside the instruction cache
@@ -273,13 +278,14 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         }
                         return;
                     }
-                    uint32_t mask = 0;
+                    uint32_t m4[4] = {0u, 0u, 0u, 0u};   // independent partial masks: no 32-long dependent chain
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         float s = __uint_as_float(v[i]);
                         if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]);
-                        mask |= !(s < tau) ? (1u << i) : 0u;   // s >= tau, or NaN
+                        m4[i & 3] |= !(s < tau) ? (1u << i) : 0u;   // s >= tau, or NaN
                     }
+                    uint32_t mask = (m4[0] | m4[1]) | (m4[2] | m4[3]);
                     while (mask) {
                         const int i = __ffs(mask) - 1;
                         mask &= mask - 1;
@@ -288,20 +294,20 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                             float s = __uint_as_float(select32(v, i));
                             if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]) - qn;   // −‖x−q‖²
                             if (!isfinite(s)) nonfinite = true;
-                            my_q[nloc * 128] = make_key(s, r);
+                            my_q[nloc * EPI_THREADS] = make_key(s, r);
                             if (++nloc == QCAP) flush();
                         }
                     }
                 };
                 uint32_t va[32], vb[32];
-                tmem_ld32(tbase, va);
+                tmem_ld32(tbase + cbase, va);
                 tmem_ld_wait();
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64) {   // two chunks per iteration, loads double buffered
+                for (int c0 = cbase; c0 < cbase + BN / 2; c0 += 64) {   // two chunks per iteration, loads double buffered
                     tmem_ld32(tbase + c0 + 32, vb);
                     process(va, c0);
                     tmem_ld_wait();
-                    if (c0 + 64 < BN) tmem_ld32(tbase + c0 + 64, va);
+                    if (c0 + 64 < cbase + BN / 2) tmem_ld32(tbase + c0 + 64, va);
                     process(vb, c0 + 32);
                     tmem_ld_wait();
                 }
