@@ -129,6 +129,53 @@ def synth_host_rows(oracle, seed, n, dim, threads):
     return out
 
 
+def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
+    """HNSW default profile (M/M0 = 16/32) on the 1024-centre mixture: build on the host cores, then
+    QPS (host API, 4096-query batches, copies included), recall@10 vs the exact flat result and
+    evaluated nodes per query over the ef sweep.  ef = 0 is the reference's own setting (ef = k)."""
+    metric = vl.SimilarityMetric.Cosine
+    flat = vl.FlatIndex(DIM, device=device)
+    flat.fill_synthetic(42, n, clusters=clusters)
+    qsrc = vl.FlatIndex(DIM, device=device)
+    qsrc.fill_synthetic(43, nq, clusters=clusters)
+    queries = qsrc.export()[1]
+    truth, _, _ = flat.search_batch(queries, k, metric)          # exact, certified (tensor-core batched path)
+    ids, rows = flat.export()
+    flat.close()
+    h = vl.HNSWIndex(DIM, metric, M=16, M0=32, ef_construction=efc, device=device)
+    t0 = time.perf_counter()
+    h.add_batch(ids, rows)
+    h.build()
+    build_s = time.perf_counter() - t0
+    del rows
+    sweep = {}
+    for ef in (0, 16, 32, 64, 128, 256):
+        h.search_batch(queries[:512], k, metric, ef)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            gi, gs, gc = h.search_batch(queries, k, metric, ef)
+        dt = (time.perf_counter() - t0) / reps
+        hit = sum(len(set(map(int, gi[i, :gc[i]])) & set(map(int, truth[i]))) for i in range(nq))
+        sweep[str(ef)] = {"recall_at_10": hit / (nq * k), "qps_e2e": nq / dt,
+                          "visited_per_query": h.stats()["hnsw_visited"] / nq, "beam": 8 * (ef or k)}
+    ref = {}
+    for name in ("hnsw_reference_recall_n20000_c1024_M16.json", "hnsw_reference_recall_n20000_c0_M16.json",
+                 "hnsw_reference_recall_n50000_c1024_M16.json"):
+        pth = os.path.join(ROOT, "tests", "golden", name)
+        if os.path.exists(pth):
+            d = json.load(open(pth))
+            ref[name] = {e: round(v["recall_at_10"], 4) for e, v in d["sweep"].items()}
+    h.close()
+    return {"rows": n, "dim": DIM, "data": f"synthetic {clusters}-centre mixture, unit norm", "M": 16, "M0": 32,
+            "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "build_threads": cpu_threads(),
+            "sweep": sweep,
+            "reference_restatement_recall": ref,
+            "note": "reference recall = oracle restatement of crate hnsw 0.11 + u64-quantised functors at "
+                    "efC=400 on smaller N (CPU build is single-threaded); parity at equal parameters is "
+                    "asserted in tests/test_hnsw_gpu.py"}
+
+
 def run_reference(args):
     """The reference arm: CPU only, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +227,8 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time the other metrics / batch modes")
+    ap.add_argument("--hnsw-rows", type=int, default=1_000_000, help="HNSW section size (0 = skip; rank 0, N=1 only)")
+    ap.add_argument("--hnsw-efc", type=int, default=200)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -356,6 +405,11 @@ def main():
                "single_thread_qps": qps_1t}
         del rows
 
+    # ---- HNSW section (replicas only: one full graph per GPU; measured on rank 0 at N = 1) ---------------
+    hnsw = None
+    if rank == 0 and world == 1 and args.hnsw_rows > 0:
+        hnsw = hnsw_section(vl, args.hnsw_rows, args.hnsw_efc, local_rank)
+
     if rank == 0:
         line = {
             "metric": "flat_1m_384d_k10_qps", "value": value, "unit": "queries/s x 1M-row shards",
@@ -381,6 +435,7 @@ def main():
             "gpu_launches": int(launches + (merges if world > 1 else 0)),
             "clocks": clocks,
             "extras": extras,
+            "hnsw": hnsw,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

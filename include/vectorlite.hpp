@@ -1,0 +1,171 @@
+// vectorlite.hpp — header-only C++ host mirror of VectorLite's index interface over the C ABI
+// (include/vectorlite_cuda.h).  Same names, argument meaning and error behaviour as the reference:
+//   SimilarityMetric             src/lib.rs:363-378
+//   Vector / SearchResult        src/lib.rs:163-174, 193-203
+//   VectorIndex (abstract)       src/lib.rs:224-245
+//   FlatIndex                    src/index/flat.rs:59-136
+//   HNSWIndex                    src/index/hnsw.rs:197-518
+//   VectorIndexWrapper           src/lib.rs:270-346
+// `Result<(), String>` errors become std::runtime_error carrying the reference's message (the callers
+// at src/client.rs:334-345,366-377 substring-match "dimension" / "already exists" / "does not exist");
+// `VectorLiteError::{DimensionMismatch, MetricMismatch}` become the exception types below.
+// Text / metadata stay on the host and are attached to the <= k hits only.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "vectorlite_cuda.h"
+
+namespace vectorlite {
+
+enum class SimilarityMetric : int { Cosine = 0, Euclidean = 1, Manhattan = 2, DotProduct = 3 };
+enum class IndexType : int { Flat = 0, HNSW = 1 };
+
+struct Vector {
+    uint64_t id = 0;
+    std::vector<double> values;
+    std::string text;
+    std::optional<std::string> metadata;  // serialized JSON (serde_json::Value in the reference)
+};
+struct SearchResult {
+    uint64_t id = 0;
+    double score = 0.0;
+    std::string text;
+    std::optional<std::string> metadata;
+};
+
+struct VectorLiteError : std::runtime_error {
+    int code;
+    VectorLiteError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+struct DimensionMismatch : VectorLiteError {
+    size_t expected, actual;
+    DimensionMismatch(size_t e, size_t a)
+        : VectorLiteError(VL_ERR_DIM, "Dimension mismatch: expected " + std::to_string(e) + ", got " + std::to_string(a)),
+          expected(e), actual(a) {}
+};
+struct MetricMismatch : VectorLiteError {
+    SimilarityMetric requested, index;
+    MetricMismatch(SimilarityMetric r, SimilarityMetric i) : VectorLiteError(VL_ERR_METRIC_MISMATCH, "Metric mismatch"), requested(r), index(i) {}
+};
+
+class VectorIndex {  // src/lib.rs:224-245
+public:
+    virtual ~VectorIndex() = default;
+    virtual void add(const Vector& v) = 0;
+    virtual void remove(uint64_t id) = 0;  // `delete` is a C++ keyword
+    virtual std::vector<SearchResult> search(const std::vector<double>& query, size_t k, SimilarityMetric m) const = 0;
+    virtual size_t len() const = 0;
+    virtual bool is_empty() const { return len() == 0; }
+    virtual std::optional<Vector> get_vector(uint64_t id) const = 0;
+    virtual size_t dimension() const = 0;
+};
+
+class CudaIndex : public VectorIndex {
+protected:
+    vl_index* h_ = nullptr;
+    struct Meta { std::string text; std::optional<std::string> metadata; };
+    std::unordered_map<uint64_t, Meta> meta_;
+    static std::string err() { return vl_last_error(); }
+
+public:
+    CudaIndex() = default;
+    CudaIndex(const CudaIndex&) = delete;
+    CudaIndex& operator=(const CudaIndex&) = delete;
+    ~CudaIndex() override { vl_index_destroy(h_); }
+
+    void add(const Vector& v) override {
+        const int st = vl_index_add_f64(h_, v.id, v.values.data(), static_cast<uint32_t>(v.values.size()));
+        if (st != VL_OK) throw std::runtime_error(err());
+        meta_[v.id] = Meta{v.text, v.metadata};
+    }
+    void remove(uint64_t id) override {
+        if (vl_index_delete(h_, id) != VL_OK) throw std::runtime_error(err());
+        meta_.erase(id);
+    }
+    std::vector<SearchResult> search(const std::vector<double>& q, size_t k, SimilarityMetric m) const override {
+        return search_ef(q, k, m, 0);
+    }
+    std::vector<SearchResult> search_ef(const std::vector<double>& q, size_t k, SimilarityMetric m, uint32_t ef) const {
+        std::vector<uint64_t> ids(k);
+        std::vector<double> scores(k);
+        uint32_t count = 0;
+        const int st = vl_index_search_f64(h_, q.data(), 1, static_cast<uint32_t>(q.size()), static_cast<uint32_t>(k),
+                                           static_cast<int>(m), ef, ids.data(), scores.data(), &count);
+        if (st == VL_ERR_DIM) throw DimensionMismatch(dimension(), q.size());
+        if (st == VL_ERR_METRIC_MISMATCH) throw MetricMismatch(m, static_cast<SimilarityMetric>(vl_index_metric(h_)));
+        if (st != VL_OK) throw VectorLiteError(st, err());
+        std::vector<SearchResult> out(count);
+        for (uint32_t i = 0; i < count; ++i) {
+            out[i].id = ids[i];
+            out[i].score = scores[i];
+            auto it = meta_.find(ids[i]);
+            if (it != meta_.end()) { out[i].text = it->second.text; out[i].metadata = it->second.metadata; }
+        }
+        return out;
+    }
+    size_t len() const override { return static_cast<size_t>(vl_index_len(h_)); }
+    std::optional<Vector> get_vector(uint64_t id) const override {
+        std::vector<float> f(dimension());
+        if (vl_index_get_vector(h_, id, f.data()) != VL_OK) return std::nullopt;
+        Vector v;
+        v.id = id;
+        v.values.assign(f.begin(), f.end());
+        auto it = meta_.find(id);
+        if (it != meta_.end()) { v.text = it->second.text; v.metadata = it->second.metadata; }
+        return v;
+    }
+    size_t dimension() const override { return vl_index_dim(h_); }
+    std::optional<uint64_t> max_id() const {  // flat.rs:76-78, hnsw.rs:267-269
+        uint64_t id = 0;
+        if (vl_index_max_id(h_, &id) != VL_OK) return std::nullopt;
+        return id;
+    }
+    vl_index* handle() const { return h_; }
+};
+
+class FlatIndex : public CudaIndex {  // src/index/flat.rs:59-136
+public:
+    explicit FlatIndex(size_t dim, const std::vector<Vector>& data = {}, int device = 0) {
+        if (vl_flat_create(static_cast<uint32_t>(dim), device, &h_) != VL_OK) throw VectorLiteError(VL_ERR_CUDA, err());
+        for (const Vector& v : data) add(v);  // FlatIndex::new takes the vectors as given (flat.rs:68)
+    }
+    std::optional<SimilarityMetric> metric() const { return std::nullopt; }
+    IndexType index_type() const { return IndexType::Flat; }
+};
+
+class HNSWIndex : public CudaIndex {  // src/index/hnsw.rs:197-518
+public:
+    // profiles of hnsw.rs:95-109 are runtime parameters: 16/32 default, 8/16 memory-optimized, 32/64 high-accuracy
+    HNSWIndex(size_t dim, SimilarityMetric metric, uint32_t M = 16, uint32_t M0 = 32, uint32_t ef_construction = 400,
+              int device = 0) {
+        if (dim == 0) throw std::invalid_argument("HNSW index dimension cannot be 0");  // hnsw.rs:217-219 panics
+        if (vl_hnsw_create(static_cast<uint32_t>(dim), static_cast<int>(metric), M, M0, ef_construction, device, &h_) != VL_OK)
+            throw VectorLiteError(VL_ERR_CUDA, err());
+    }
+    SimilarityMetric metric() const { return static_cast<SimilarityMetric>(vl_index_metric(h_)); }
+    IndexType index_type() const { return IndexType::HNSW; }
+};
+
+class VectorIndexWrapper {  // src/lib.rs:270-346
+    std::unique_ptr<CudaIndex> idx_;
+    IndexType type_;
+
+public:
+    explicit VectorIndexWrapper(std::unique_ptr<FlatIndex> f) : idx_(std::move(f)), type_(IndexType::Flat) {}
+    explicit VectorIndexWrapper(std::unique_ptr<HNSWIndex> h) : idx_(std::move(h)), type_(IndexType::HNSW) {}
+    VectorIndex& operator*() { return *idx_; }
+    CudaIndex* operator->() { return idx_.get(); }
+    IndexType index_type() const { return type_; }
+    std::optional<SimilarityMetric> metric() const {
+        if (type_ == IndexType::Flat) return std::nullopt;
+        return static_cast<SimilarityMetric>(vl_index_metric(idx_->handle()));
+    }
+};
+
+}  // namespace vectorlite

@@ -359,3 +359,17 @@ def test_tensor_core_batched_path(vl, oracle_mod):
     idx.set_mode(vl.Mode.Fp32)
     gi2, gs2, _ = idx.search_batch(queries[:77], 100, vl.SimilarityMetric.Cosine)
     assert np.array_equal(gi2, oi) and np.array_equal(gs2.view(np.uint64), os_.view(np.uint64))
+
+
+def test_cpp_host_mirror(vl, tmp_path):
+    """include/vectorlite.hpp (the C++ mirror of the reference interface) replays the reference's own
+    flat / hnsw unit tests against the C ABI."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_mirror_test")
+    libdir = os.path.join(root, "vectorlite_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "host_mirror_test.cpp"), "-o", exe, "-L" + libdir,
+                    "-lvectorlite_cuda", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "CPP_MIRROR PASS" in out.stdout, out.stdout + out.stderr
