@@ -272,8 +272,15 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
+        # a stream of independent single-query searches; with N > 1 the per-query exchange (one packed
+        # all-gather + merge) runs on a side stream and overlaps the next query's scan
         for qi in range(QUERIES_PER_STEP):
-            idx.search_device(d_queries[qi:qi + 1], k, metric)
+            if world > 1:
+                idx.search_device_pipelined(d_queries[qi:qi + 1], k, metric)
+            else:
+                idx.search_device(d_queries[qi:qi + 1], k, metric)
+        if world > 1:
+            idx.drain()
 
     def timed(fn, steps):
         barrier()

@@ -42,6 +42,9 @@ class ShardedFlatIndex:
         self.local = FlatIndex(dim, device=self.device)
         self.base = 0
         self._bufs = {}
+        self._ring = {}          # (nq, k) -> pipelined buffer sets
+        self._side = None        # side stream for the exchange (all-gather + merge)
+        self._seq = 0
 
     def fill_synthetic(self, seed: int, n_total: int, clusters: int = 0):
         lo, hi = shard_range(n_total, self.world, self.rank)
@@ -99,6 +102,63 @@ class ShardedFlatIndex:
         # flags of every shard: the last nq u32 of each block
         flg = packed.view(torch.int32)[:, (3 * nk8 + nq * 4) // 4:(3 * nk8 + nq * 8) // 4]
         return b["o_ids"], b["o_sc"], b["o_cnt"], flg
+
+    # ---- throughput mode: the exchange of search i overlaps the scan of search i+1 -----------------------
+    def search_device_pipelined(self, d_queries: torch.Tensor, k: int, metric: SimilarityMetric, depth: int = 4):
+        """Like search_device, but the all-gather + merge run on a side stream so the next search's
+        scan can start immediately.  Results land in a ring of `depth` buffer sets; the returned tensors
+        are valid once `drain()` (or the returned event) has been waited on."""
+        if self.world == 1:
+            return self.search_device(d_queries, k, metric) + (None,)
+        nq = d_queries.shape[0]
+        key = (nq, k)
+        if key not in self._ring:
+            saved = self._bufs.pop(key, None)
+            sets = []
+            for _ in range(depth):
+                self._bufs.pop(key, None)
+                sets.append(self._buffers(nq, k))
+            self._bufs.pop(key, None)
+            if saved is not None:
+                self._bufs[key] = saved
+            self._ring[key] = dict(sets=sets, events=[None] * depth)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ring = self._ring[key]
+        slot = self._seq % len(ring["sets"])
+        self._seq += 1
+        b = ring["sets"][slot]
+        main = torch.cuda.current_stream()
+        if ring["events"][slot] is not None:
+            main.wait_event(ring["events"][slot])          # this buffer set's previous exchange is done
+        r = self.rank
+        packed = b["packed"]
+        base = packed[r].data_ptr()
+        nk8 = nq * k * 8
+        self.local.search_device(d_queries.data_ptr(), nq, k, metric, base, base + nk8, base + 2 * nk8,
+                                 base + 3 * nk8, base + 3 * nk8 + nq * 4, _current_stream())
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            dist.all_gather_into_tensor(packed.view(-1), packed[r].clone(), group=self.group)
+            st = lib().vl_merge_topk_packed_device(self.device, self.world, nq, k, packed.data_ptr(),
+                                                   b["o_ids"].data_ptr(), b["o_sc"].data_ptr(), b["o_pos"].data_ptr(),
+                                                   b["o_cnt"].data_ptr(), C.c_void_p(self._side.cuda_stream))
+            if st != VL_OK:
+                raise VectorLiteError(st, _err())
+            done = torch.cuda.Event()
+            done.record(self._side)
+        ring["events"][slot] = done
+        flg = packed.view(torch.int32)[:, (3 * nk8 + nq * 4) // 4:(3 * nk8 + nq * 8) // 4]
+        return b["o_ids"], b["o_sc"], b["o_cnt"], flg, done
+
+    def drain(self):
+        """Make the current stream wait for every exchange issued by search_device_pipelined."""
+        if self._side is not None:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
 
     def search(self, queries: np.ndarray, k: int, metric: SimilarityMetric):
         """Host in / host out (the e2e path): H2D of the queries, sharded search, D2H of the merged
