@@ -23,6 +23,22 @@ for metric in vl.SimilarityMetric:
             good = np.array_equal(gi, oi) and np.array_equal(gs.view(np.uint64), os_.view(np.uint64))
             ok = ok and good
             print(f"metric={metric.name} nq={qs.shape[0]} {'OK' if good else 'MISMATCH'}", flush=True)
+# pipelined exchange (side stream, ring of buffers) must give the same answers as the blocking one
+d_q = torch.from_numpy(queries).cuda()
+outs = []
+for i in range(12):
+    outs.append(idx.search_device_pipelined(d_q[i:i + 1], k, vl.SimilarityMetric.Cosine))
+    if i % 4 == 3:            # consume a ring's worth before its slots are reused
+        idx.drain(); torch.cuda.synchronize()
+        for j, o in enumerate(outs):
+            qi = i - len(outs) + 1 + j
+            ref_ids, ref_sc, _, _ = idx.search_device(d_q[qi:qi + 1], k, vl.SimilarityMetric.Cosine)
+            torch.cuda.synchronize()
+            good = torch.equal(o[0], ref_ids) and torch.equal(o[1], ref_sc)
+            ok = ok and good
+        outs = []
+if rank == 0:
+    print("pipelined exchange", "OK" if ok else "MISMATCH", flush=True)
 if rank == 0:
     print("SHARDED_CHECK", "PASS" if ok else "FAIL", "world", world)
 dist.barrier()

@@ -284,6 +284,17 @@ class _CudaIndex:
         return None if m < 0 else SimilarityMetric(m)
 
     # -- extras ------------------------------------------------------------------------------
+    def export(self, first: int = 0, count: Optional[int] = None):
+        n = self.len() - first if count is None else count
+        n = max(n, 0)
+        ids = np.empty(n, dtype=np.uint64)
+        rows = np.empty((n, self.dimension()), dtype=np.float32)
+        got = C.c_uint64(0)
+        st = self._L.vl_index_export(self._h, first, n, _ptr(ids, C.c_uint64), _ptr(rows, C.c_float), C.byref(got))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        return ids[:got.value], rows[:got.value]
+
     def stats(self) -> dict:
         out = np.zeros(8, dtype=np.uint64)
         self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 8)
@@ -331,17 +342,6 @@ class FlatIndex(_CudaIndex):
                                              first_row if first_id is None else first_id)
         if st != VL_OK:
             raise VectorLiteError(st, _err())
-
-    def export(self, first: int = 0, count: Optional[int] = None):
-        n = self.len() - first if count is None else count
-        n = max(n, 0)
-        ids = np.empty(n, dtype=np.uint64)
-        rows = np.empty((n, self.dimension()), dtype=np.float32)
-        got = C.c_uint64(0)
-        st = self._L.vl_index_export(self._h, first, n, _ptr(ids, C.c_uint64), _ptr(rows, C.c_float), C.byref(got))
-        if st != VL_OK:
-            raise VectorLiteError(st, _err())
-        return ids[:got.value], rows[:got.value]
 
     def set_pos_base(self, base: int):
         self._L.vl_index_set_pos_base(self._h, int(base))

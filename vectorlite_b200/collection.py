@@ -1,0 +1,446 @@
+"""Collection / client / persistence layer over the CUDA indexes — SURVEY §8(f) rows 1 and 2.
+
+Mirrors, name for name, the reference's host-side routing so that a CUDA-backed index drops in
+behind the same library surface:
+
+* ``EmbeddingFunction``                       — src/embeddings.rs:135-141 (protocol only; Candle is out of scope)
+* ``Collection``                              — src/client.rs:243-431
+* ``VectorLiteClient``                        — src/client.rs:65-192
+* ``save_collection_to_file`` / ``load_collection_from_file`` — src/persistence.rs:129-176, same
+  ``.vlc`` JSON document (header / metadata / externally-tagged ``VectorIndexWrapper``), so files
+  written by the reference load here and vice versa.  Loading is the second way vectors reach the
+  device arena: rows are uploaded with ONE bulk ``vl_index_add_batch`` (the reference re-inserts).
+
+Additive (the reference has text search only): ``Collection.search_vector``,
+``Collection.search_batch`` and ``MicroBatcher``, which coalesces concurrent single-query callers
+(the HTTP handlers of src/server.rs:258-275 each hold the read lock, client.rs:398) into one batched
+launch so they share a tensor-core pass instead of each paying a full HBM scan.
+"""
+from __future__ import annotations
+
+import datetime as _dt
+import json
+import os
+import threading
+from concurrent.futures import Future
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Protocol, Sequence
+
+import numpy as np
+
+from . import (DimensionMismatch, FlatIndex, HNSWIndex, IndexType, SearchResult, SimilarityMetric, Vector,
+               VectorLiteError, _CudaIndex)
+
+FORMAT_NAME = "vectorlite-collection"      # persistence.rs:92
+FORMAT_VERSION = "1.0.0"                   # persistence.rs:91
+
+
+class EmbeddingFunction(Protocol):  # src/embeddings.rs:135-141
+    def generate_embedding(self, text: str) -> Sequence[float]: ...
+    def dimension(self) -> int: ...
+
+
+# ---- errors (src/errors.rs:10-67, the variants this layer raises) ------------------------------------
+class DuplicateVectorId(VectorLiteError):
+    def __init__(self, id_: int):
+        super().__init__(2, f"Vector with ID {id_} already exists")
+        self.id = id_
+
+
+class VectorNotFound(VectorLiteError):
+    def __init__(self, id_: int):
+        super().__init__(3, f"Vector with ID {id_} not found")
+        self.id = id_
+
+
+class CollectionNotFound(VectorLiteError):
+    def __init__(self, name: str):
+        super().__init__(3, f"Collection '{name}' not found")
+        self.name = name
+
+
+class CollectionAlreadyExists(VectorLiteError):
+    def __init__(self, name: str):
+        super().__init__(2, f"Collection '{name}' already exists")
+        self.name = name
+
+
+class InvalidRequest(VectorLiteError):
+    def __init__(self, msg: str):
+        super().__init__(5, msg)
+
+
+class PersistenceError(Exception):  # src/persistence.rs:29-58
+    pass
+
+
+class FileNotFound(PersistenceError):
+    pass
+
+
+class VersionMismatch(PersistenceError):
+    def __init__(self, expected: str, actual: str):
+        super().__init__(f"Version mismatch: expected {expected}, got {actual}")
+        self.expected, self.actual = expected, actual
+
+
+class InvalidFormat(PersistenceError):
+    pass
+
+
+# ---- a small writer-preferring RW lock: Arc<RwLock<VectorIndexWrapper>> (client.rs:245) ---------------
+class _RWLock:
+    def __init__(self):
+        self._c = threading.Condition()
+        self._readers = 0
+        self._writer = False
+
+    def read(self):
+        lock = self
+
+        class _R:
+            def __enter__(self_inner):
+                with lock._c:
+                    while lock._writer:
+                        lock._c.wait()
+                    lock._readers += 1
+
+            def __exit__(self_inner, *a):
+                with lock._c:
+                    lock._readers -= 1
+                    lock._c.notify_all()
+        return _R()
+
+    def write(self):
+        lock = self
+
+        class _W:
+            def __enter__(self_inner):
+                with lock._c:
+                    while lock._writer or lock._readers:
+                        lock._c.wait()
+                    lock._writer = True
+
+            def __exit__(self_inner, *a):
+                with lock._c:
+                    lock._writer = False
+                    lock._c.notify_all()
+        return _W()
+
+
+@dataclass
+class CollectionInfo:  # client.rs:272-282
+    name: str
+    count: int
+    is_empty: bool
+    dimension: int
+
+
+class Collection:
+    """client.rs:243-431.  ``index`` is a FlatIndex or HNSWIndex of this package."""
+
+    def __init__(self, name: str, index: _CudaIndex):
+        self._name = name
+        self._index = index
+        self._lock = _RWLock()
+        m = index.max_id()                       # client.rs:297-308: next_id = max_id + 1, else 0
+        self._next_id = 0 if m is None else m + 1
+        self._id_lock = threading.Lock()
+        self._batcher: Optional[MicroBatcher] = None
+
+    # -- ids ---------------------------------------------------------------------------------------
+    def _fetch_add(self) -> int:                 # AtomicU64::fetch_add(1, Relaxed), client.rs:318,350
+        with self._id_lock:
+            i = self._next_id
+            self._next_id += 1
+            return i
+
+    # -- mutation ------------------------------------------------------------------------------------
+    def add_text(self, text: str, embedding_function: EmbeddingFunction) -> int:
+        return self.add_text_with_metadata(text, None, embedding_function)
+
+    def add_text_with_metadata(self, text: str, metadata: Optional[Any], embedding_function: EmbeddingFunction) -> int:
+        id_ = self._fetch_add()                  # the id is consumed even if the add fails (client.rs:350)
+        embedding = list(embedding_function.generate_embedding(text))   # outside the lock (client.rs:353)
+        with self._lock.write():
+            try:
+                self._index.add(Vector(id=id_, values=embedding, text=text, metadata=metadata))
+            except ValueError as e:              # client.rs:366-377: substring-matched error translation
+                msg = str(e)
+                if "dimension" in msg:
+                    raise DimensionMismatch(self._index.dimension(), len(embedding)) from None
+                if "already exists" in msg:
+                    raise DuplicateVectorId(id_) from None
+                raise VectorLiteError(5, msg) from None
+        return id_
+
+    def add_vectors(self, rows, texts: Optional[Sequence[str]] = None, metadata: Optional[Sequence[Any]] = None) -> range:
+        """Additive bulk path: one device upload for many pre-computed embeddings."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        with self._id_lock:
+            first = self._next_id
+            self._next_id += rows.shape[0]
+        with self._lock.write():
+            self._index.add_batch(np.arange(first, first + rows.shape[0], dtype=np.uint64), rows, texts, metadata)
+        return range(first, first + rows.shape[0])
+
+    def delete(self, id: int) -> None:
+        with self._lock.write():
+            try:
+                self._index.delete(id)
+            except ValueError as e:              # client.rs:384-390
+                if "does not exist" in str(e):
+                    raise VectorNotFound(id) from None
+                raise VectorLiteError(5, str(e)) from None
+
+    # -- queries ---------------------------------------------------------------------------------------
+    def search_text(self, query_text: str, k: int, similarity_metric: SimilarityMetric,
+                    embedding_function: EmbeddingFunction) -> List[SearchResult]:
+        q = list(embedding_function.generate_embedding(query_text))      # outside the lock (client.rs:395)
+        return self.search_vector(q, k, similarity_metric)
+
+    def search_vector(self, query: Sequence[float], k: int, similarity_metric: SimilarityMetric, ef: int = 0) -> List[SearchResult]:
+        if self._batcher is not None:
+            return self._batcher.submit(query, k, similarity_metric, ef).result()
+        with self._lock.read():
+            return self._index.search(query, k, similarity_metric, ef)
+
+    def search_batch(self, queries, k: int, similarity_metric: SimilarityMetric, ef: int = 0) -> List[List[SearchResult]]:
+        with self._lock.read():
+            ids, scores, counts = self._index.search_batch(queries, k, similarity_metric, ef)
+            return [[self._index._result(int(ids[q, i]), float(scores[q, i])) for i in range(int(counts[q]))]
+                    for q in range(ids.shape[0])]
+
+    def enable_micro_batching(self, max_batch: int = 256, max_wait_us: int = 200) -> None:
+        self._batcher = MicroBatcher(self, max_batch, max_wait_us)
+
+    def disable_micro_batching(self) -> None:
+        if self._batcher is not None:
+            self._batcher.close()
+            self._batcher = None
+
+    def get_vector(self, id: int) -> Optional[Vector]:
+        with self._lock.read():
+            return self._index.get_vector(id)
+
+    def get_info(self) -> CollectionInfo:
+        with self._lock.read():
+            return CollectionInfo(self._name, self._index.len(), self._index.is_empty(), self._index.dimension())
+
+    def name(self) -> str:
+        return self._name
+
+    def next_id(self) -> int:
+        return self._next_id
+
+    def index_read(self) -> _CudaIndex:
+        return self._index
+
+    def save_to_file(self, path: str) -> None:   # client.rs:434-440
+        save_collection_to_file(self, path)
+
+    @staticmethod
+    def load_from_file(path: str, device: int = 0) -> "Collection":
+        return load_collection_from_file(path, device)
+
+
+class MicroBatcher:
+    """Coalesces concurrent single-query searches into one batched device call."""
+
+    def __init__(self, collection: Collection, max_batch: int, max_wait_us: int):
+        self._c = collection
+        self._max_batch = max_batch
+        self._wait = max_wait_us * 1e-6
+        self._cv = threading.Condition()
+        self._pending: List[tuple] = []
+        self._closed = False
+        self.batches_served: List[int] = []
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def submit(self, query, k, metric, ef) -> Future:
+        f: Future = Future()
+        with self._cv:
+            self._pending.append((np.asarray(query, dtype=np.float32), int(k), metric, int(ef), f))
+            self._cv.notify()
+        return f
+
+    def close(self):
+        with self._cv:
+            self._closed = True
+            self._cv.notify()
+        self._t.join(timeout=5)
+
+    def _run(self):
+        while True:
+            with self._cv:
+                while not self._pending and not self._closed:
+                    self._cv.wait()
+                if self._closed and not self._pending:
+                    return
+                if len(self._pending) < self._max_batch:
+                    self._cv.wait(self._wait)        # give concurrent callers a moment to pile up
+                head = self._pending[0]
+                group = [p for p in self._pending if p[1:4] == head[1:4] and p[0].shape == head[0].shape][:self._max_batch]
+                for p in group:
+                    self._pending.remove(p)
+            try:
+                res = self._c.search_batch(np.stack([p[0] for p in group]), head[1], head[2], head[3])
+                self.batches_served.append(len(group))
+                for p, r in zip(group, res):
+                    p[4].set_result(r)
+            except Exception as e:  # noqa: BLE001 — every waiter must be released
+                for p in group:
+                    p[4].set_exception(e)
+
+
+# ---- VectorLiteClient (client.rs:65-192) ----------------------------------------------------------------
+class VectorLiteClient:
+    def __init__(self, embedding_function: EmbeddingFunction, device: int = 0):
+        self._collections: Dict[str, Collection] = {}
+        self._ef = embedding_function
+        self._device = device
+        self._lock = threading.Lock()
+
+    def create_collection(self, name: str, index_type: IndexType, metric: Optional[SimilarityMetric] = None) -> None:
+        with self._lock:
+            if name in self._collections:
+                raise CollectionAlreadyExists(name)                      # client.rs:84-86
+            dim = self._ef.dimension()
+            if index_type == IndexType.Flat:
+                index = FlatIndex(dim, device=self._device)
+            else:
+                if metric is None:                                       # client.rs:92-97
+                    raise InvalidRequest("HNSW index requires a similarity metric")
+                index = HNSWIndex(dim, metric, device=self._device)
+            self._collections[name] = Collection(name, index)
+
+    def get_collection(self, name: str) -> Optional[Collection]:
+        return self._collections.get(name)
+
+    def list_collections(self) -> List[str]:
+        return list(self._collections)
+
+    def has_collection(self, name: str) -> bool:
+        return name in self._collections
+
+    def delete_collection(self, name: str) -> None:
+        with self._lock:
+            if name not in self._collections:
+                raise CollectionNotFound(name)
+            self._collections.pop(name).index_read().close()
+
+    def _get(self, name: str) -> Collection:
+        c = self._collections.get(name)
+        if c is None:
+            raise CollectionNotFound(name)
+        return c
+
+    def add_text_to_collection(self, name: str, text: str, metadata: Optional[Any] = None) -> int:
+        return self._get(name).add_text_with_metadata(text, metadata, self._ef)
+
+    def search_text_in_collection(self, name: str, query_text: str, k: int,
+                                  similarity_metric: Optional[SimilarityMetric] = None) -> List[SearchResult]:
+        c = self._get(name)
+        if similarity_metric is None:            # client.rs:143-155: HNSW's own metric, else Cosine
+            similarity_metric = c.index_read().metric() or SimilarityMetric.Cosine
+        return c.search_text(query_text, k, similarity_metric, self._ef)
+
+    def delete_from_collection(self, name: str, id: int) -> None:
+        self._get(name).delete(id)
+
+    def get_vector_from_collection(self, name: str, id: int) -> Optional[Vector]:
+        return self._get(name).get_vector(id)
+
+    def get_collection_info(self, name: str) -> CollectionInfo:
+        return self._get(name).get_info()
+
+    def add_collection(self, collection: Collection) -> None:
+        with self._lock:
+            if collection.name() in self._collections:
+                raise CollectionAlreadyExists(collection.name())
+            self._collections[collection.name()] = collection
+
+
+# ---- persistence (src/persistence.rs) ---------------------------------------------------------------------
+def _now() -> str:
+    return _dt.datetime.now(_dt.timezone.utc).isoformat().replace("+00:00", "Z")
+
+
+def collection_to_document(collection: Collection) -> dict:
+    """CollectionData::from_collection (persistence.rs:101-123) in serde's JSON shape."""
+    idx = collection.index_read()
+    if isinstance(idx, HNSWIndex):
+        eids, rows = idx.export()
+        ids = [int(i) for i in eids]
+        vals, meta = {}, {}
+        for i, r in zip(ids, rows):
+            text, md = idx._meta.get(i, ("", None))
+            vals[str(i)] = [float(x) for x in r]
+            meta[str(i)] = {"text": text, "metadata": md}
+        index = {"HNSW": {"dim": idx.dimension(), "metric": idx.metric().name,
+                          "id_to_index": {str(i): n for n, i in enumerate(ids)},
+                          "index_to_id": {str(n): i for n, i in enumerate(ids)},
+                          "metadata": meta, "vector_values": vals}}
+        kind = "HNSW"
+    else:
+        ids, rows = idx.export()
+        data = []
+        for i, r in zip(ids, rows):
+            text, md = idx._meta.get(int(i), ("", None))
+            data.append({"id": int(i), "values": [float(x) for x in r], "text": text, "metadata": md})
+        index = {"Flat": {"dim": idx.dimension(), "data": data}}
+        kind = "Flat"
+    return {"header": {"version": FORMAT_VERSION, "format": FORMAT_NAME, "created_at": _now()},
+            "metadata": {"name": collection.name(), "created_at": _now(), "vector_count": idx.len(),
+                         "dimension": idx.dimension(), "index_type": kind},
+            "index": index}
+
+
+def save_collection_to_file(collection: Collection, path: str) -> None:
+    doc = collection_to_document(collection)
+    parent = os.path.dirname(os.path.abspath(path))
+    os.makedirs(parent, exist_ok=True)                                   # persistence.rs:133-135
+    tmp = os.path.splitext(path)[0] + ".tmp"                             # Path::with_extension("tmp")
+    with open(tmp, "w") as f:
+        json.dump(doc, f, indent=2)                                      # to_string_pretty
+    os.replace(tmp, path)                                                # atomic rename
+
+
+def load_collection_from_file(path: str, device: int = 0) -> Collection:
+    try:
+        with open(path) as f:
+            doc = json.load(f)
+    except FileNotFoundError:
+        raise FileNotFound(path) from None
+    except json.JSONDecodeError as e:
+        raise PersistenceError(f"Serialization error: {e}") from None
+    header = doc["header"]
+    if header["version"] != FORMAT_VERSION:                              # persistence.rs:160-165
+        raise VersionMismatch(FORMAT_VERSION, header["version"])
+    if header["format"] != FORMAT_NAME:                                  # persistence.rs:168-173
+        raise InvalidFormat(f"Expected format '{FORMAT_NAME}', got '{header['format']}'")
+    name = doc["metadata"]["name"]
+    (kind, body), = doc["index"].items()
+    if kind == "Flat":
+        data = body["data"]
+        index = FlatIndex(int(body["dim"]), device=device)
+        if data:                                                         # ONE bulk upload into the device arena
+            ids = np.array([d["id"] for d in data], dtype=np.uint64)
+            rows = np.array([d["values"] for d in data], dtype=np.float32)
+            index.add_batch(ids, rows, [d.get("text", "") for d in data], [d.get("metadata") for d in data])
+    elif kind == "HNSW":
+        if int(body["dim"]) == 0:
+            raise PersistenceError("Invalid dimension: cannot be 0")      # hnsw.rs:288-290
+        index = HNSWIndex(int(body["dim"]), SimilarityMetric[body["metric"]], device=device)
+        vv = body["vector_values"]
+        if vv:                                                           # hnsw.rs:322-348 re-inserts every vector
+            keys = sorted(vv, key=int)                                   # (deterministic order here; HashMap order there)
+            ids = np.array([int(k) for k in keys], dtype=np.uint64)
+            rows = np.array([vv[k] for k in keys], dtype=np.float32)
+            md = body.get("metadata", {})
+            index.add_batch(ids, rows, [md.get(k, {}).get("text", "") for k in keys],
+                            [md.get(k, {}).get("metadata") for k in keys])
+    else:
+        raise InvalidFormat(f"unknown index variant '{kind}'")
+    return Collection(name, index)

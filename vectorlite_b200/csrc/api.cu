@@ -870,7 +870,10 @@ int vl_index_get_vector(const vl_index* h, uint64_t id, float* out_values) {
 int vl_index_export(const vl_index* h, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows,
                     uint64_t* out_n) {
     if (!h || !out_n) return fail(VL_ERR_INVALID, "null argument");
-    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "export: flat indexes only");
+    if (h->type == VL_INDEX_HNSW) {  // live rows only, insertion order (what HNSWIndex serialises, hnsw.rs:197-213)
+        *out_n = hnsw_export(h->hnsw.get(), first, cap, out_ids, out_rows);
+        return VL_OK;
+    }
     const uint64_t m = first >= h->n ? 0 : std::min(cap, h->n - first);
     *out_n = m;
     if (m == 0) return VL_OK;

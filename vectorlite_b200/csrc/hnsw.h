@@ -23,6 +23,8 @@ uint64_t hnsw_live(const HnswState* s);
 // append n rows (host f32 [n][dim]) to the graph; internal index == arena position
 int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n);
 bool hnsw_soft_delete(HnswState* s, uint64_t id);
+// live rows in insertion order: up to `cap` starting at live position `first` (rows come from the host copy)
+uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows);
 // flatten + upload the graph if it changed since the last upload
 int hnsw_upload(HnswState* s, cudaStream_t stream);
 int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,

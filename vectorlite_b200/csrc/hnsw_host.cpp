@@ -370,6 +370,19 @@ bool hnsw_soft_delete(HnswState* s, uint64_t id) {  // hnsw.rs:400-414
     return true;
 }
 
+uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows) {
+    uint64_t live_pos = 0, written = 0;
+    const size_t n = s->level.size();
+    for (size_t i = 0; i < n && written < cap; ++i) {
+        if (s->deleted[i]) continue;
+        if (live_pos++ < first) continue;
+        if (out_ids) out_ids[written] = s->id_of[i];
+        if (out_rows) std::memcpy(out_rows + written * s->dim, s->vecs.data() + i * s->dim, s->dim * sizeof(float));
+        ++written;
+    }
+    return written;
+}
+
 int hnsw_upload(HnswState* s, cudaStream_t stream) {
     const size_t n = s->level.size();
     if (n == 0) return 0;
