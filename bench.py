@@ -203,8 +203,10 @@ def run_reference(args):
         "unit": "queries/s x 1M-row shards", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"flat {n}x{DIM} f32 rows widened to f64, {args.metric}, k={args.k}, "
-                               f"{nq} queries per step, one per host thread",
+        "config": {"workload": f"flat {n}x{DIM} f32 per GPU shard, {args.metric}, k={args.k}, B=1 "
+                               f"({QUERIES_PER_STEP} single-query searches per step)",
+                   "reference_arm": f"CPU: f32 rows widened to f64, {nq} queries per step, one per host thread "
+                                    "(bounded sample of the same workload)",
                    "note": "reference is Rust (no toolchain here): C++ oracle restatement of "
                            "flat.rs:98-119 + lib.rs:425-572, -O2 -ffp-contract=off"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
@@ -415,7 +417,10 @@ def main():
     # ---- HNSW section (replicas only: one full graph per GPU; measured on rank 0 at N = 1) ---------------
     hnsw = None
     if rank == 0 and world == 1 and args.hnsw_rows > 0:
-        hnsw = hnsw_section(vl, args.hnsw_rows, args.hnsw_efc, local_rank)
+        try:
+            hnsw = hnsw_section(vl, args.hnsw_rows, args.hnsw_efc, local_rank)
+        except Exception as e:  # noqa: BLE001 — the headline line must still be printed
+            hnsw = {"error": repr(e)}
 
     if rank == 0:
         line = {
