@@ -5,8 +5,9 @@
 // Appendix C): upper layers are walked greedily (beam 1), layer 0 with a beam of `ef`.
 //
 //  - the query lives in registers (12 floats per lane at 384-d), every warp owns a copy;
-//  - the beam is a sorted array of 64-bit keys (orderable fp32 distance | node<<1 | expanded) in
-//    shared memory, maintained by warp 0 with warp-parallel lower-bound + shift insertion;
+//  - the beam is an unsorted pool of 64-bit keys (orderable fp32 distance | node<<1 | expanded) in
+//    shared memory: warp 0 selects the closest unexpanded entry and replaces the worst entry with
+//    warp-wide argmin / argmax reductions (no binary search, no shifting), sorted once at the end;
 //  - visited set: a direct-mapped, lossy tag cache in shared memory (no probing, no overflow).
 //    Losing a tag only costs a redundant distance evaluation: a re-evaluated node is either
 //    rejected by the beam threshold or found as an exact duplicate key at its insertion point;
@@ -28,6 +29,8 @@ namespace vl {
 constexpr int HN_THREADS = 128;
 constexpr int HN_WARPS = HN_THREADS / 32;
 constexpr int HN_MAX_DEG = 64;
+constexpr int HN_MAX_EXPAND = 4;                 // pool entries expanded per step
+constexpr int HN_MAX_CAND = HN_MAX_DEG * HN_MAX_EXPAND;
 constexpr int HN_EF_MAX = 2048;   // widest internal beam
 constexpr int HN_K_MAX = 256;
 constexpr int HN_BEAM_MULT = 8;     // internal beam = 8 x nominal ef (see hnsw_launch_search)
@@ -44,6 +47,10 @@ struct HnswParams {
 };
 
 __device__ __forceinline__ uint32_t vis_hash(uint32_t id) { return (id * 2654435761u) >> 7; }
+// 16-bit tag of a node in the visited cache (never 0 = empty); a tag collision in the SAME slot with a
+// different node (p ≈ 2^-15 per occupied-slot lookup) makes that node look visited — a negligible recall cost
+// that halves the cache's shared memory and doubles the resident CTAs for wide beams
+__device__ __forceinline__ uint16_t vis_tag(uint32_t id) { return static_cast<uint16_t>(((id * 0x9E3779B1u) >> 16) | 1u); }
 
 template <int METRIC>
 __device__ __forceinline__ float acc4(float acc, const float4& v, const float4& q) {
@@ -92,9 +99,9 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     // layout: q[pitch] f32 | beam[ef_cap] u64 | vis[vis_mask+1] u32
     float4* s_q = reinterpret_cast<float4*>(smem_raw);
     unsigned long long* s_beam = reinterpret_cast<unsigned long long*>(smem_raw + static_cast<size_t>(p.pitch) * 4);
-    uint32_t* s_vis = reinterpret_cast<uint32_t*>(s_beam + p.beam_cap);
-    __shared__ unsigned long long s_ck[HN_MAX_DEG];  // candidate keys of this step
-    __shared__ uint32_t s_cid[HN_MAX_DEG];
+    uint16_t* s_vis = reinterpret_cast<uint16_t*>(s_beam + p.beam_cap);
+    __shared__ unsigned long long s_ck[HN_MAX_CAND];  // candidate keys of this step
+    __shared__ uint32_t s_cid[HN_MAX_CAND];
     __shared__ int s_nc, s_size, s_done;
     __shared__ float s_invq;
     __shared__ double s_ex[HN_K_MAX];
@@ -170,6 +177,30 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     };
 
     // ---- entry point ---------------------------------------------------------------------
+    // The beam is an UNSORTED pool of up to `ef` keys.  Warp 0 picks the closest unexpanded entry
+    // (argmin by warp reduction) and replaces the worst entry on insertion (argmax by warp reduction):
+    // no binary searches, no shifting; the pool is sorted once at the end.
+    __shared__ unsigned long long s_worst;   // largest (key >> 1) in the pool once it is full, else ~0
+    __shared__ int s_worst_idx;
+    auto pool_recompute_worst = [&](int size, uint32_t ef) {   // warp 0, all lanes
+        unsigned long long w = 0ull;
+        int wi = -1;
+        for (int i = lane; i < size; i += 32) {
+            const unsigned long long kk = s_beam[i] >> 1;
+            if (kk >= w) { w = kk; wi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ow = __shfl_xor_sync(0xFFFFFFFFu, w, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, wi, o);
+            if (ow > w || (ow == w && oi > wi)) { w = ow; wi = oi; }
+        }
+        if (lane == 0) {
+            s_worst = size == static_cast<int>(ef) ? w : ~0ull;
+            s_worst_idx = wi;
+        }
+        __syncwarp();
+    };
     if (warp == 0) {
         if (lane == 0) s_cid[0] = p.g.entry;
         __syncwarp();
@@ -178,31 +209,41 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
         if (lane == 0) {
             s_beam[0] = s_ck[0];
             s_size = 1;
-            s_vis[vis_hash(p.g.entry) & p.vis_mask] = p.g.entry + 1;
+            s_vis[vis_hash(p.g.entry) & p.vis_mask] = vis_tag(p.g.entry);
         }
+        __syncwarp();
+        pool_recompute_worst(1, p.g.max_level > 0 ? 1u : p.ef);
     }
     __syncthreads();
 
     unsigned long long n_eval = 1;
-    int cursor = 0;  // warp 0: all beam entries before `cursor` are expanded
     for (int lvl = p.g.max_level; lvl >= 0; --lvl) {
         const uint32_t ef = lvl == 0 ? p.ef : 1u;
         const uint32_t deg = lvl == 0 ? p.g.M0 : p.g.M;
         for (;;) {
-            // ---- warp 0: pick the closest unexpanded beam entry, gather its unvisited neighbours
+            // ---- warp 0: the `expand` closest unexpanded pool entries, then their unvisited neighbours
             if (warp == 0) {
                 const int size = s_size;
-                int first = 0x7FFFFFFF;
-                for (int i = cursor + lane; i < size; i += 32)
-                    if (!(s_beam[i] & 1ull)) { first = i; break; }
-                first = __reduce_min_sync(0xFFFFFFFFu, first);
-                if (first != 0x7FFFFFFF) cursor = first + 1;  // everything before is expanded
-                int nc = 0;
-                if (first != 0x7FFFFFFF) {
-                    const unsigned long long key = s_beam[first];
-                    const uint32_t node = static_cast<uint32_t>(key >> 1) & 0x7FFFFFFFu;
+                const int expand = ef >= 64u ? HN_MAX_EXPAND : (ef >= 32u ? 2 : 1);
+                int nc = 0, picked = 0;
+                for (int e = 0; e < expand; ++e) {
+                    unsigned long long best = ~0ull;
+                    int bi = -1;
+                    for (int i = lane; i < size; i += 32) {
+                        const unsigned long long kk = s_beam[i];
+                        if (!(kk & 1ull) && (kk >> 1) < best) { best = kk >> 1; bi = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+                        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+                        if (ob < best) { best = ob; bi = oi; }
+                    }
+                    if (bi < 0) break;
+                    ++picked;
+                    const uint32_t node = static_cast<uint32_t>(best) & 0x7FFFFFFFu;
+                    if (lane == 0) s_beam[bi] |= 1ull;
                     __syncwarp();
-                    if (lane == 0) s_beam[first] = key | 1ull;
                     const uint32_t* adj = lvl == 0 ? p.g.adj0 + static_cast<size_t>(node) * p.g.M0
                                                    : p.g.upper + (static_cast<size_t>(__ldg(p.g.upper_off + node)) + lvl - 1) * p.g.M;
                     for (uint32_t j0 = 0; j0 < deg; j0 += 32) {
@@ -211,7 +252,9 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
                         bool fresh = false;
                         if (v != HNSW_NONE) {
                             const uint32_t slot = vis_hash(v) & p.vis_mask;
-                            fresh = atomicExch(&s_vis[slot], v + 1) != v + 1;
+                            const uint16_t tag = vis_tag(v);
+                            fresh = s_vis[slot] != tag;      // only warp 0 touches the cache
+                            s_vis[slot] = tag;
                         }
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, fresh);
                         if (fresh) s_cid[nc + __popc(m & ((1u << lane) - 1))] = v;
@@ -220,42 +263,42 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
                 }
                 if (lane == 0) {
                     s_nc = nc;
-                    s_done = first == 0x7FFFFFFF;
+                    s_done = picked == 0;
                 }
             }
             __syncthreads();
             if (s_done) break;
             const int nc = s_nc;
-            // ---- all warps: distances, 8 candidates per warp per round
-            for (int g0 = warp * 8; g0 < nc; g0 += HN_WARPS * 8) score8(s_cid + g0, min(8, nc - g0), s_ck + g0);
+            // ---- all warps: distances, 8 candidates per warp per round; candidates that cannot enter
+            // the pool (not closer than its current worst entry) are dropped right here
+            const unsigned long long worst_now = s_worst;
+            for (int g0 = warp * 8; g0 < nc; g0 += HN_WARPS * 8) {
+                const int cnt = min(8, nc - g0);
+                score8(s_cid + g0, cnt, s_ck + g0);
+                __syncwarp();
+                if (lane < cnt && (s_ck[g0 + lane] >> 1) >= worst_now) s_ck[g0 + lane] = ~0ull;
+            }
             n_eval += (tid == 0) ? nc : 0;
             __syncthreads();
-            // ---- warp 0: insert the candidates that beat the beam's worst entry
+            // ---- warp 0: insert the survivors (append while the pool is filling, else replace the worst)
             if (warp == 0) {
                 int size = s_size;
                 for (int j = 0; j < nc; ++j) {
                     const unsigned long long key = s_ck[j];
-                    if (size == static_cast<int>(ef) && (key >> 1) >= (s_beam[size - 1] >> 1)) continue;
-                    int pos = 0, hi_b = size;  // lower bound by (distance, node), flag bit ignored
-                    while (pos < hi_b) {
-                        const int mid = (pos + hi_b) >> 1;
-                        if ((s_beam[mid] >> 1) < (key >> 1)) pos = mid + 1; else hi_b = mid;
-                    }
-                    if (pos < size && (s_beam[pos] >> 1) == (key >> 1)) continue;  // duplicate (lossy cache)
-                    const int nsize = min(size + 1, static_cast<int>(ef));
-                    // shift [pos, nsize-1) right by one, highest chunk first
-                    for (int hi = nsize - 1; hi > pos; hi -= 32) {
-                        const int idx = hi - lane;
-                        unsigned long long t = 0;
-                        if (idx > pos) t = s_beam[idx - 1];
+                    if (key == ~0ull || (key >> 1) >= s_worst) continue;
+                    bool dup = false;                       // the visited cache is lossy: exact de-duplication here
+                    for (int i = lane; i < size; i += 32) dup |= (s_beam[i] >> 1) == (key >> 1);
+                    if (__any_sync(0xFFFFFFFFu, dup)) continue;
+                    if (size < static_cast<int>(ef)) {
+                        if (lane == 0) s_beam[size] = key;
+                        ++size;
                         __syncwarp();
-                        if (idx > pos) s_beam[idx] = t;
+                        if (size == static_cast<int>(ef)) pool_recompute_worst(size, ef);
+                    } else {
+                        if (lane == 0) s_beam[s_worst_idx] = key;
                         __syncwarp();
+                        pool_recompute_worst(size, ef);
                     }
-                    if (lane == 0) s_beam[pos] = key;
-                    __syncwarp();
-                    size = nsize;
-                    if (pos < cursor) cursor = pos;
                 }
                 if (lane == 0) s_size = size;
             }
@@ -265,18 +308,40 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
         if (lvl > 0) {
             __syncthreads();
             if (tid == 0) {
-                s_beam[0] &= ~1ull;
+                s_beam[0] &= ~1ull;          // upper levels run with a pool of one entry
                 s_size = 1;
+                const uint32_t next_ef = lvl == 1 ? p.ef : 1u;
+                s_worst = next_ef == 1u ? (s_beam[0] >> 1) : ~0ull;
+                s_worst_idx = 0;
             }
-            cursor = 0;
             for (uint32_t i = tid; i <= p.vis_mask; i += HN_THREADS) s_vis[i] = 0u;
             __syncthreads();
             if (tid == 0) {
                 const uint32_t node = static_cast<uint32_t>(s_beam[0] >> 1) & 0x7FFFFFFFu;
-                s_vis[vis_hash(node) & p.vis_mask] = node + 1;
+                s_vis[vis_hash(node) & p.vis_mask] = vis_tag(node);
             }
             __syncthreads();
         }
+    }
+
+    // ---- sort the pool once (ascending by distance, node) for the result extraction ------------
+    {
+        const int size = s_size;
+        int len = 2;
+        while (len < size) len <<= 1;
+        for (int i = size + tid; i < len; i += HN_THREADS) s_beam[i] = ~0ull;
+        __syncthreads();
+        for (int k2 = 2; k2 <= len; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (len >> 1); t += HN_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int pp = i | j;
+                    const bool asc = (i & k2) == 0;
+                    const unsigned long long x = s_beam[i], y = s_beam[pp];
+                    if ((x > y) == asc) { s_beam[i] = y; s_beam[pp] = x; }
+                }
+                __syncthreads();
+            }
     }
 
     // ---- results: first k non-deleted beam entries (hnsw.rs:472-475), exact f64 re-score ------
@@ -391,16 +456,16 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     uint32_t bcap = 64;
     while (bcap < p.ef) bcap <<= 1;
     p.beam_cap = bcap;
-    // visited tag cache: ~2 slots per expected evaluation (~W·M0/2 fresh nodes), 1K..16K entries
+    // visited tag cache (16-bit tags): ~2 slots per expected evaluation (~W·M0/2 fresh nodes), 2K..32K entries
     const uint32_t want = p.ef * g.M0;
-    uint32_t cap = 1024;
-    while (cap < want && cap < 16384) cap <<= 1;
+    uint32_t cap = 2048;
+    while (cap < want && cap < 32768) cap <<= 1;
     p.vis_mask = cap - 1;
     p.out_ids = d_out_ids;
     p.out_scores = d_out_scores;
     p.out_counts = d_out_counts;
     p.visited = d_visited;
-    const size_t smem = static_cast<size_t>(pitch) * 4 + static_cast<size_t>(bcap) * 8 + static_cast<size_t>(cap) * 4;
+    const size_t smem = static_cast<size_t>(pitch) * 4 + static_cast<size_t>(bcap) * 8 + static_cast<size_t>(cap) * 2;
     switch (metric) {
         case COSINE: return launch_metric<COSINE>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN>(p, nq, smem, stream);
