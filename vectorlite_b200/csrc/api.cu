@@ -450,6 +450,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
         const size_t qbytes = static_cast<size_t>(m) * h->pitch * sizeof(float);
         CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
         h->stats[ST_H2D] += qbytes;
+        bool zero_copy = false;
         if (fast) {
             SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
             if (batched) {
@@ -470,18 +471,23 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
                 }
                 h->stats[ST_LAUNCHES] += nl;
             } else {
+                // few queries: the finalize kernel writes its (tiny) results straight into the pinned host
+                // mirror (UVA zero-copy), which saves the D2H copy operation on the latency path
+                zero_copy = true;
+                SearchOut hout{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
                 ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
                 CU(launch_flat_scan(v, s.d_q, m, metric, w, false, s.stream));
-                CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, out, 1.0f, s.stream));
+                CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, hout, 1.0f, s.stream));
                 h->stats[ST_LAUNCHES] += 2;
             }
-            CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
+            if (!zero_copy) CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
             bool any_fail = false;
             for (uint32_t q = 0; q < m; ++q) {
                 if (s.h_flags[q] & FLAG_CERT_FAIL) any_fail = true; else h->stats[ST_FAST] += 1;
             }
             if (any_fail) {
+                if (zero_copy) CU(cudaMemcpyAsync(s.d_out, s.h_out, s.out_used, cudaMemcpyHostToDevice, s.stream));
                 for (uint32_t q = 0; q < m; ++q)
                     if (s.h_flags[q] & FLAG_CERT_FAIL) {
                         st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
