@@ -430,7 +430,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"flat {n_shard}x{DIM} f32 per GPU shard, {args.metric}, k={k}, B=1 "
                                    f"({QUERIES_PER_STEP} single-query searches per step)",
-                       "rows_total": n_total, "parallelism": f"row-sharded x{world}, NCCL all-gather + merge kernel",
+                       "rows_total": n_total, "parallelism": (f"row-sharded x{world}, " + ("single shard" if world == 1 else
+                                       "per-shard top-k pushed into peer HBM over NVLink by the finalize kernel + "
+                                       "stamp-waiting merge kernel (no collective call)" if idx.exchange == "p2p"
+                                       else "NCCL all-gather + merge kernel")),
                        "l2": "inputs larger than L2 (1.536 GB store vs 126 MB)",
                        "pipelining": "programmatic dependent launch between consecutive searches", "exactness":
                        "ids == oracle, f64 scores bit-identical (fp32 scan + fp64 rescore + certificate)"},
@@ -444,7 +447,7 @@ def main():
             "e2e": {"value": e2e_qps, "unit": "queries/s x 1M-row shards",
                     "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
                     "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8)},
-            "gpu_launches": int(launches + (merges if world > 1 else 0)),
+            "gpu_launches": int(launches + (merges if (world > 1 and idx.exchange == "nccl") else 0)),
             "clocks": clocks,
             "extras": extras,
             "hnsw": hnsw,

@@ -113,7 +113,8 @@ int vl_index_search_f64(vl_index* h, const double* queries, uint32_t nq, uint32_
  * d_out_pos (may be NULL) receives storage positions (+ the handle's position base, see
  * vl_index_set_pos_base) — what a row-sharded merge tie-breaks on.  d_out_flags[q]: bit0 = the
  * optimality certificate failed (caller must re-run that query through vl_index_search or in
- * VL_MODE_EXACT), bit1 = non-finite fp32 score seen, bit2 = NaN similarity. */
+ * VL_MODE_EXACT), bit1 = non-finite fp32 score seen, bit2 = NaN similarity, bit3 = candidate buffer
+ * overflow (implies bit0), bit4 = a peer shard's results did not arrive (vl_index_search_exchange). */
 int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric,
                            uint32_t ef, uint64_t* d_out_ids, double* d_out_scores,
                            uint64_t* d_out_pos, uint32_t* d_out_counts, uint32_t* d_out_flags,
@@ -134,6 +135,37 @@ uint64_t vl_packed_result_bytes(uint32_t nq, uint32_t k);
 int vl_merge_topk_packed_device(int device, uint32_t G, uint32_t nq, uint32_t k, const void* d_packed,
                                 uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
                                 uint32_t* d_out_counts, void* cuda_stream);
+
+/* ---- row-sharded exchange over NVLink peer memory (one process per GPU) ----------------------
+ * The reference has a single in-process index (client.rs:243-247); shard-aware routing is the
+ * addition the north star names.  A vl_exchange owns, on this rank's device, a ring of slots with one
+ * block per shard plus per-(shard, query) stamps, exported to the peer processes with CUDA IPC.
+ * vl_index_search_exchange runs the local shard search with the kernel that produces the final top-k
+ * storing it directly into every peer's slot (peer-mapped HBM, NVLink stores + system-scope release),
+ * then a merge kernel waits for the G stamps of each query and merges from local memory: no
+ * collective call and no host synchronisation on the data path.  Every rank must issue the same
+ * sequence of calls (same nq, k).  Bounded waits: a peer that never arrives sets bit4 of the flags.
+ *
+ * Setup: every rank creates its exchange, publishes vl_exchange_local_handle (64 bytes) to all ranks
+ * through any host channel, calls vl_exchange_connect with the [world][64] handle table, and passes a
+ * host barrier before the first search.  vl_exchange_connect_local wires exchanges that live in ONE
+ * process (tests; several GPUs driven by one process). */
+#define VL_EXCHANGE_HANDLE_BYTES 64
+typedef struct vl_exchange vl_exchange;
+int vl_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_nq, uint32_t max_k,
+                       vl_exchange** out);
+void vl_exchange_destroy(vl_exchange* x);
+int vl_exchange_local_handle(const vl_exchange* x, void* out_handle);
+int vl_exchange_connect(vl_exchange* x, const void* handles);
+int vl_exchange_connect_local(vl_exchange** all, uint32_t n);
+/* Sharded search: d_queries [nq][dim] replicated on every rank; outputs (device, [nq][k] / [nq]) hold
+ * the GLOBAL top-k on every rank; d_out_flags[q] = OR of all shards' flags (bit0: some shard's
+ * certificate failed → re-run exact).  Everything is enqueued on `cuda_stream`; on a pipelined handle
+ * (vl_index_set_pipelined) the merge joins the programmatic-dependent-launch chain, so the next
+ * search's scan streams rows while the merge is still waiting for the slowest peer. */
+int vl_index_search_exchange(vl_index* h, vl_exchange* x, const float* d_queries, uint32_t nq, uint32_t k,
+                             int metric, uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                             uint32_t* d_out_counts, uint32_t* d_out_flags, void* cuda_stream);
 
 /* ---- accessors ------------------------------------------------------------------------ */
 uint64_t vl_index_len(const vl_index* h);          /* VectorIndex::len */

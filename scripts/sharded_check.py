@@ -10,7 +10,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 n, dim, k = 200_000, 384, 10
-idx = ShardedFlatIndex(dim, rank=rank, world=world, device=lr)
+idx = ShardedFlatIndex(dim, rank=rank, world=world, device=lr)   # VL_EXCHANGE=p2p (default) | nccl
 idx.fill_synthetic(42, n)
 rows = oracle.synth_rows(42, 0, n, dim) if rank == 0 else None
 queries = oracle.synth_rows(43, 0, 40, dim)
@@ -40,7 +40,7 @@ for i in range(12):
 if rank == 0:
     print("pipelined exchange", "OK" if ok else "MISMATCH", flush=True)
 if rank == 0:
-    print("SHARDED_CHECK", "PASS" if ok else "FAIL", "world", world)
+    print("SHARDED_CHECK", "PASS" if ok else "FAIL", "world", world, "exchange", idx.exchange)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -264,6 +264,96 @@ def test_search_device_and_sharded_merge(vl, oracle_mod):
         shards.clear()
 
 
+def test_peer_exchange_three_shards_one_gpu(vl, oracle_mod):
+    """The peer-memory exchange protocol (csrc/exchange.cu) with three shards living in ONE process on
+    one GPU (vl_exchange_connect_local): each shard's final-top-k kernel stores its block into every
+    peer's slot and stamps it, each shard's merge kernel waits for the stamps.  Shards run on separate
+    streams (a merge kernel spins until its peers have pushed).  Result on EVERY shard == the unsharded
+    oracle, cross-shard ties included; repeated past the slot ring depth (slot reuse + acknowledgements),
+    single-query, chunked small-batch and batched (tensor-core) paths, plain and PDL-pipelined handles."""
+    import torch
+    from vectorlite_b200.sharded import PeerExchange
+    n, dim, k, G = 9000, 384, 10, 3
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    rows[3000:3005] = rows[10]
+    rows[6000:6003] = rows[10]
+    queries = np.concatenate([oracle_mod.synth_rows(43, 0, 39, dim), rows[10:11]])
+    dev = torch.device("cuda:0")
+    d_q = torch.from_numpy(queries).to(dev)
+    per = n // G
+    shards, xs, streams = [], [], []
+    for g in range(G):
+        s = vl.FlatIndex(dim)
+        s.add_batch(np.arange(g * per, (g + 1) * per, dtype=np.uint64), rows[g * per:(g + 1) * per])
+        s.set_pos_base(g * per)
+        shards.append(s)
+        xs.append(PeerExchange(0, G, g, max_nq=64, max_k=16))
+        streams.append(torch.cuda.Stream(device=dev))
+    PeerExchange.connect_local(xs)
+    torch.cuda.synchronize()
+
+    def outs(nq):
+        return dict(o_ids=torch.zeros((nq, k), dtype=torch.int64, device=dev),
+                    o_sc=torch.zeros((nq, k), dtype=torch.float64, device=dev),
+                    o_pos=torch.zeros((nq, k), dtype=torch.int64, device=dev),
+                    o_cnt=torch.zeros((nq,), dtype=torch.int32, device=dev),
+                    xflg=torch.zeros((1, nq), dtype=torch.int32, device=dev))
+
+    expected = {}
+
+    def oracle_of(metric, lo, hi):
+        key = (int(metric), lo, hi)
+        if key not in expected:
+            st, oi, os_ = oracle_mod.flat_search_batch(rows, None, queries[lo:hi], k, int(metric))
+            assert st == 0
+            expected[key] = (oi, os_)
+        return expected[key]
+
+    rounds = [(vl.SimilarityMetric.Cosine, 39, 40, False), (vl.SimilarityMetric.Cosine, 0, 1, False),
+              (vl.SimilarityMetric.Euclidean, 0, 5, False), (vl.SimilarityMetric.Manhattan, 0, 40, False),
+              (vl.SimilarityMetric.DotProduct, 0, 40, False)]
+    rounds += [(vl.SimilarityMetric.Cosine, i, i + 1, True) for i in range(10)]   # overlapped, > ring depth
+    rounds += [(vl.SimilarityMetric.Cosine, 0, 40, True), (vl.SimilarityMetric.Cosine, 3, 4, False)]
+    # Warm-up without the exchange: scratch (re)allocations synchronise the whole device, which in this
+    # one-process emulation would stall a shard behind a peer's spinning merge kernel (separate processes
+    # on separate GPUs, the real deployment, do not share that dependency).
+    for metric, lo, hi, _ in rounds:
+        for g in range(G):
+            o = outs(hi - lo)
+            shards[g].search_device(d_q[lo:hi].data_ptr(), hi - lo, k, metric, o["o_ids"].data_ptr(),
+                                    o["o_sc"].data_ptr(), o["o_pos"].data_ptr(), o["o_cnt"].data_ptr(),
+                                    o["xflg"].data_ptr(), streams[g].cuda_stream)
+    torch.cuda.synchronize()
+    pending = []
+    for metric, lo, hi, overlap in rounds:
+        res = []
+        for g in range(G):
+            o = outs(hi - lo)
+            shards[g].set_pipelined(overlap)
+            xs[g].search(shards[g], d_q[lo:hi], k, metric, o, streams[g].cuda_stream)
+            res.append(o)
+        pending.append((metric, lo, hi, res))
+        if not overlap or len(pending) == 4:
+            torch.cuda.synchronize()
+            for metric_, lo_, hi_, res_ in pending:
+                oi, os_ = oracle_of(metric_, lo_, hi_)
+                for g in range(G):
+                    assert int(res_[g]["xflg"].max()) == 0, (metric_, lo_, g, res_[g]["xflg"])
+                    assert np.array_equal(res_[g]["o_ids"].cpu().numpy().astype(np.uint64), oi), (metric_, lo_, g)
+                    assert np.array_equal(res_[g]["o_sc"].cpu().numpy().view(np.uint64), os_.view(np.uint64))
+                    assert np.array_equal(res_[g]["o_pos"].cpu().numpy().astype(np.uint64), oi)
+                    assert int(res_[g]["o_cnt"].min()) == k
+            pending = []
+    torch.cuda.synchronize()
+    # a peer that never shows up: bounded wait, FLAG_EXCHANGE (bit 4), no hang
+    o = outs(1)
+    xs[0].search(shards[0], d_q[0:1], k, vl.SimilarityMetric.Cosine, o, streams[0].cuda_stream)
+    torch.cuda.synchronize()
+    assert int(o["xflg"][0, 0]) & 16
+    for x in xs:
+        x.close()
+
+
 def test_full_size_1m_properties_and_sampled_oracle(vl, oracle_mod):
     """BASELINE config 2 size (1M × 384): size-independent properties on the device-generated
     store + full-oracle check on sampled queries."""

@@ -132,6 +132,12 @@ def lib():
         "vl_merge_topk_device": (i32, [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "vl_packed_result_bytes": (u64, [u32, u32]),
         "vl_merge_topk_packed_device": (i32, [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]),
+        "vl_exchange_create": (i32, [i32, u32, u32, u32, u32, C.POINTER(vp)]),
+        "vl_exchange_destroy": (None, [vp]),
+        "vl_exchange_local_handle": (i32, [vp, vp]),
+        "vl_exchange_connect": (i32, [vp, vp]),
+        "vl_exchange_connect_local": (i32, [C.POINTER(vp), u32]),
+        "vl_index_search_exchange": (i32, [vp, vp, vp, u32, u32, i32, vp, vp, vp, vp, vp, vp]),
         "vl_index_len": (u64, [vp]),
         "vl_index_dim": (u32, [vp]),
         "vl_index_type_of": (i32, [vp]),

@@ -734,23 +734,25 @@ int vl_index_search_f64(vl_index* h, const double* queries, uint32_t nq, uint32_
     return vl_index_search(h, f.data(), nq, qdim, k, metric, ef, out_ids, out_scores, out_counts);
 }
 
-int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric, uint32_t ef,
-                           uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
-                           uint32_t* d_out_counts, uint32_t* d_out_flags, void* cuda_stream) {
-    (void)ef;
-    if (!h || !d_queries || !d_out_ids || !d_out_scores || !d_out_counts || !d_out_flags)
-        return fail(VL_ERR_INVALID, "null argument");
-    if (metric < 0 || metric > 3) return fail(VL_ERR_INVALID, "unknown metric %d", metric);
-    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "search_device: flat indexes only");
-    if (h->n == 0 || k == 0 || nq == 0) return fail(VL_ERR_INVALID, "empty index, k == 0 or nq == 0");
-    if (k > 256) return fail(VL_ERR_UNSUPPORTED, "search_device supports k <= 256");
-    DeviceGuard dg(h->device);
+// device-resident search shared by vl_index_search_device and vl_index_search_exchange: `o` carries the
+// output pointers for query 0 (and, for a row-sharded exchange, the peer mirrors of those outputs)
+static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric,
+                              const SearchOut& o, cudaStream_t stream) {
     Slot& s = h->dev_slot;
-    cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s.stream;
     const FlatView v = view_of(h);
     const int Kp = pick_kp(k);
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
+    auto out_at = [&](uint32_t q0) {
+        SearchOut out = o;
+        out.ids = o.ids + static_cast<size_t>(q0) * k;
+        out.scores = o.scores + static_cast<size_t>(q0) * k;
+        out.pos = o.pos ? o.pos + static_cast<size_t>(q0) * k : nullptr;
+        out.counts = o.counts + q0;
+        out.flags = o.flags + q0;
+        out.peers.q_off = o.peers.q_off + q0;
+        return out;
+    };
     if (nq >= BATCH_MIN) {
         const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
         for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
@@ -758,9 +760,7 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
             BatchWork bw;
             int st = slot_reserve_batch(s, m, &bw);
             if (st) return st;
-            SearchOut out{d_out_ids + static_cast<size_t>(q0) * k, d_out_scores + static_cast<size_t>(q0) * k,
-                          d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
-                          d_out_flags + q0};
+            const SearchOut out = out_at(q0);
             uint64_t nl = 0;
             BatchTensor bt;
             if (want_tc) {  // device API: calls on one handle are caller-ordered, no lock needed
@@ -790,9 +790,7 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
         QueryCtl* ctl = s.ctl + (h->dev_parity & 1) * NQ_CHUNK;
         h->dev_parity ^= 1;
         ScanWork w{s.cand, s.cand_count, s.cand_max, ctl, grid_x, Kp};
-        SearchOut out{d_out_ids + static_cast<size_t>(q0) * k, d_out_scores + static_cast<size_t>(q0) * k,
-                      d_out_pos ? d_out_pos + static_cast<size_t>(q0) * k : nullptr, d_out_counts + q0,
-                      d_out_flags + q0};
+        const SearchOut out = out_at(q0);
         const float* dq = d_queries + static_cast<size_t>(q0) * h->pitch;
         const bool prof = h->profiling && h->prof_n < h->prof_ev.size() / 2;
         if (prof) CU(cudaEventRecord(h->prof_ev[2 * h->prof_n], stream));
@@ -804,6 +802,175 @@ int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uin
         CU(launch_flat_finalize(v, dq, m, k, metric, w, out, 1.0f, stream));
         h->stats[ST_LAUNCHES] += 2;
     }
+    return VL_OK;
+}
+
+int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric, uint32_t ef,
+                           uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
+                           uint32_t* d_out_counts, uint32_t* d_out_flags, void* cuda_stream) {
+    (void)ef;
+    if (!h || !d_queries || !d_out_ids || !d_out_scores || !d_out_counts || !d_out_flags)
+        return fail(VL_ERR_INVALID, "null argument");
+    if (metric < 0 || metric > 3) return fail(VL_ERR_INVALID, "unknown metric %d", metric);
+    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "search_device: flat indexes only");
+    if (h->n == 0 || k == 0 || nq == 0) return fail(VL_ERR_INVALID, "empty index, k == 0 or nq == 0");
+    if (k > 256) return fail(VL_ERR_UNSUPPORTED, "search_device supports k <= 256");
+    DeviceGuard dg(h->device);
+    cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->dev_slot.stream;
+    SearchOut o{d_out_ids, d_out_scores, d_out_pos, d_out_counts, d_out_flags};
+    return search_device_impl(h, d_queries, nq, k, metric, o, stream);
+}
+
+// ---- peer-memory exchange of a row-sharded flat index ---------------------------------------------------
+struct vl_exchange {
+    static constexpr uint32_t DEPTH = 4;
+    int device = 0;
+    uint32_t G = 0, rank = 0, nq_cap = 0, k_cap = 0;
+    uint64_t blk_cap = 0;
+    char* base = nullptr;
+    size_t bytes = 0, ready_off = 0, ack_off = 0;
+    char* peer[EXCH_MAX_PEERS] = {};
+    bool ipc_open[EXCH_MAX_PEERS] = {};
+    bool connected = false;
+    uint64_t seq = 0;
+    uint32_t merged[DEPTH] = {};   // merge CTAs launched on each slot so far (same on every rank)
+};
+
+int vl_exchange_create(int device, uint32_t world, uint32_t rank, uint32_t max_nq, uint32_t max_k, vl_exchange** out) {
+    if (!out) return fail(VL_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (world < 1 || world > static_cast<uint32_t>(EXCH_MAX_PEERS) || rank >= world || !max_nq || !max_k || max_k > 256)
+        return fail(VL_ERR_INVALID, "exchange: need 1 <= world <= %d, rank < world, 1 <= max_k <= 256", EXCH_MAX_PEERS);
+    DeviceGuard dg(device);
+    vl_exchange* x = new (std::nothrow) vl_exchange();
+    if (!x) return fail(VL_ERR_OOM, "host allocation failed");
+    x->device = device; x->G = world; x->rank = rank; x->nq_cap = max_nq; x->k_cap = max_k;
+    x->blk_cap = (vl_packed_result_bytes(max_nq, max_k) + 255) / 256 * 256;
+    const size_t data = static_cast<size_t>(vl_exchange::DEPTH) * world * x->blk_cap;
+    const size_t sig = static_cast<size_t>(vl_exchange::DEPTH) * world * max_nq * sizeof(uint32_t);
+    x->ready_off = data;
+    x->ack_off = data + (sig + 255) / 256 * 256;
+    x->bytes = x->ack_off + static_cast<size_t>(vl_exchange::DEPTH) * world * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc(&x->base, x->bytes);   // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        const int code = e == cudaErrorMemoryAllocation ? VL_ERR_OOM : VL_ERR_CUDA;
+        vl_exchange_destroy(x);
+        return fail(code, "exchange create: %s", cudaGetErrorString(e));
+    }
+    x->peer[rank] = x->base;
+    x->connected = world == 1;
+    *out = x;
+    return VL_OK;
+}
+
+void vl_exchange_destroy(vl_exchange* x) {
+    if (!x) return;
+    DeviceGuard dg(x->device);
+    cudaDeviceSynchronize();
+    for (uint32_t g = 0; g < x->G; ++g)
+        if (x->ipc_open[g]) cudaIpcCloseMemHandle(x->peer[g]);
+    cudaFree(x->base);
+    delete x;
+}
+
+int vl_exchange_local_handle(const vl_exchange* x, void* out_handle) {
+    if (!x || !out_handle) return fail(VL_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VL_EXCHANGE_HANDLE_BYTES, "handle size");
+    DeviceGuard dg(x->device);
+    cudaIpcMemHandle_t hnd;
+    CU(cudaIpcGetMemHandle(&hnd, x->base));
+    memcpy(out_handle, &hnd, sizeof hnd);
+    return VL_OK;
+}
+
+int vl_exchange_connect(vl_exchange* x, const void* handles) {
+    if (!x || !handles) return fail(VL_ERR_INVALID, "null argument");
+    DeviceGuard dg(x->device);
+    for (uint32_t g = 0; g < x->G; ++g) {
+        if (g == x->rank || x->ipc_open[g]) continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, static_cast<const char*>(handles) + static_cast<size_t>(g) * VL_EXCHANGE_HANDLE_BYTES, sizeof hnd);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        x->peer[g] = static_cast<char*>(p);
+        x->ipc_open[g] = true;
+    }
+    x->connected = true;
+    return VL_OK;
+}
+
+int vl_exchange_connect_local(vl_exchange** all, uint32_t n) {
+    if (!all || !n || n > static_cast<uint32_t>(EXCH_MAX_PEERS)) return fail(VL_ERR_INVALID, "bad argument");
+    for (uint32_t i = 0; i < n; ++i)
+        if (!all[i] || all[i]->G != n || all[i]->rank != i || all[i]->bytes != all[0]->bytes)
+            return fail(VL_ERR_INVALID, "connect_local: exchange %u does not match (world, rank, capacities)", i);
+    for (uint32_t i = 0; i < n; ++i) {
+        DeviceGuard dg(all[i]->device);
+        for (uint32_t g = 0; g < n; ++g) {
+            if (all[g]->device != all[i]->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[g]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(VL_ERR_CUDA, "peer access %d -> %d: %s", all[i]->device, all[g]->device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            all[i]->peer[g] = all[g]->base;
+        }
+        all[i]->connected = true;
+    }
+    return VL_OK;
+}
+
+int vl_index_search_exchange(vl_index* h, vl_exchange* x, const float* d_queries, uint32_t nq, uint32_t k, int metric,
+                             uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos, uint32_t* d_out_counts,
+                             uint32_t* d_out_flags, void* cuda_stream) {
+    if (!h || !x || !d_queries || !d_out_ids || !d_out_scores || !d_out_counts || !d_out_flags)
+        return fail(VL_ERR_INVALID, "null argument");
+    if (metric < 0 || metric > 3) return fail(VL_ERR_INVALID, "unknown metric %d", metric);
+    if (h->type != VL_INDEX_FLAT) return fail(VL_ERR_UNSUPPORTED, "search_exchange: flat indexes only");
+    if (h->n == 0 || k == 0 || nq == 0) return fail(VL_ERR_INVALID, "empty shard, k == 0 or nq == 0");
+    if (!x->connected) return fail(VL_ERR_INVALID, "exchange is not connected to its peers");
+    if (x->device != h->device) return fail(VL_ERR_INVALID, "exchange and index live on different devices");
+    if (nq > x->nq_cap || k > x->k_cap)
+        return fail(VL_ERR_INVALID, "exchange capacity exceeded: nq %u > %u or k %u > %u", nq, x->nq_cap, k, x->k_cap);
+    DeviceGuard dg(h->device);
+    cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->dev_slot.stream;
+    const uint32_t G = x->G, r = x->rank;
+    const uint32_t slot = static_cast<uint32_t>(x->seq % vl_exchange::DEPTH);
+    const uint32_t stamp = static_cast<uint32_t>(x->seq / vl_exchange::DEPTH) + 1u;
+    x->seq += 1;
+    const size_t my_block = (static_cast<size_t>(slot) * G + r) * x->blk_cap;
+    const size_t nk8 = static_cast<size_t>(nq) * k * 8;
+    char* lb = x->base + my_block;
+    SearchOut o{reinterpret_cast<uint64_t*>(lb), reinterpret_cast<double*>(lb + nk8),
+                reinterpret_cast<uint64_t*>(lb + 2 * nk8), reinterpret_cast<uint32_t*>(lb + 3 * nk8),
+                reinterpret_cast<uint32_t*>(lb + 3 * nk8 + static_cast<size_t>(nq) * 4)};
+    o.peers.G = G; o.peers.self = r; o.peers.stamp = stamp; o.peers.q_off = 0;
+    o.peers.ack_want = x->merged[slot];
+    x->merged[slot] += nq;
+    for (uint32_t g = 0; g < G; ++g) {
+        o.peers.delta[g] = static_cast<long long>(x->peer[g] - x->base);
+        o.peers.ready[g] = reinterpret_cast<uint32_t*>(x->peer[g] + x->ready_off) + (static_cast<size_t>(slot) * G + r) * x->nq_cap;
+        o.peers.ack[g] = reinterpret_cast<const uint32_t*>(x->base + x->ack_off) + (static_cast<size_t>(slot) * G + g);
+    }
+    int st = search_device_impl(h, d_queries, nq, k, metric, o, stream);
+    if (st) return st;
+    ExchangeMerge m;
+    m.G = G; m.self = r; m.nq = nq; m.k = k; m.stamp = stamp;
+    m.slot = x->base + static_cast<size_t>(slot) * G * x->blk_cap;
+    m.blk = x->blk_cap;
+    m.ready = reinterpret_cast<const uint32_t*>(x->base + x->ready_off) + static_cast<size_t>(slot) * G * x->nq_cap;
+    for (uint32_t g = 0; g < static_cast<uint32_t>(EXCH_MAX_PEERS); ++g)
+        m.ack[g] = g < G ? reinterpret_cast<uint32_t*>(x->peer[g] + x->ack_off) + (static_cast<size_t>(slot) * G + r)
+                         : nullptr;
+    m.nq_cap = x->nq_cap;
+    m.out_ids = d_out_ids; m.out_scores = d_out_scores; m.out_pos = d_out_pos; m.out_counts = d_out_counts;
+    m.out_flags = d_out_flags;
+    // Pipelined handles: the merge joins the programmatic-dependent-launch chain scan → finalize → merge →
+    // next scan, so the next search's scan streams rows while this (tiny) kernel waits for the peers.
+    CU(launch_exchange_merge(m, h->pipelined && nq < BATCH_MIN, stream));
+    h->stats[ST_LAUNCHES] += 1;
     return VL_OK;
 }
 

@@ -334,6 +334,7 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = 1.0;
     p.tc_abs = use_tc ? tc->tc_abs : 0.0;
+    p.peers = out.peers;
     batch_rescore_kernel<<<nq, FIN_THREADS, rescore_smem(Kp, CH), s>>>(p, w.count, w.qflags, w.capq);
     nl += 1;
     if (launches) *launches += nl;

@@ -13,6 +13,7 @@ constexpr uint32_t FLAG_CERT_FAIL = 1u;   // optimality certificate failed → r
 constexpr uint32_t FLAG_NONFINITE = 2u;   // a non-finite approximate score was seen
 constexpr uint32_t FLAG_NAN = 4u;         // an exact similarity is NaN (reference panics)
 constexpr uint32_t FLAG_OVERFLOW = 8u;    // a candidate buffer overflowed → re-run exact
+constexpr uint32_t FLAG_EXCHANGE = 16u;   // a peer's results did not arrive in time (row-sharded exchange)
 
 constexpr uint32_t INVALID_POS = 0xFFFFFFFFu;
 
@@ -89,5 +90,35 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 // the stream start early (it only matters if THAT kernel carries the attribute).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- system-scope signalling for the peer-memory exchange (flags live in peer-mapped HBM) --------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p reaches `want` (stamps only grow); false after `limit_ns` — never hangs the GPU
+__device__ __forceinline__ bool wait_stamp(const uint32_t* p, uint32_t want, unsigned long long limit_ns) {
+    if (static_cast<int32_t>(ld_acquire_sys(p) - want) >= 0) return true;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        if (static_cast<int32_t>(ld_acquire_sys(p) - want) >= 0) return true;
+        if (global_timer_ns() - t0 > limit_ns) return false;
+        __nanosleep(64);
+    }
+}
+constexpr unsigned long long EXCH_TIMEOUT_NS = 2000000000ull;  // 2 s
+
 
 }  // namespace vl

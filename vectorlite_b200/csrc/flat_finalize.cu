@@ -176,6 +176,7 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = eps_scale;
     p.tc_abs = 0.0;
+    p.peers = out.peers;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nq);
     cfg.blockDim = dim3(FIN_THREADS);

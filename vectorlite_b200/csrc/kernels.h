@@ -38,12 +38,29 @@ struct ScanWork {          // per workspace slot
     int Kp;
 };
 
+// Peer-memory exchange of a row-sharded search (exchange.cu).  When G > 0 the kernel that writes a
+// query's final results stores them not only at the local SearchOut pointers (this shard's block of
+// the local exchange slot) but also, through NVLink peer mappings, at the same offsets of every
+// peer's slot (ptr + delta[g]), then publishes `stamp` in ready[g][q] with system-scope release.
+constexpr int EXCH_MAX_PEERS = 8;
+struct PeerPush {
+    uint32_t G = 0;        // shards (0 = no exchange)
+    uint32_t self = 0;
+    uint32_t stamp = 0;    // use count of the slot (1, 2, ...)
+    uint32_t q_off = 0;    // index of the launch's first query inside the signal arrays
+    uint32_t ack_want = 0; // merge CTAs every peer must have completed on this slot before it is rewritten
+    long long delta[EXCH_MAX_PEERS] = {};    // peer g's copy of my block − my local block (bytes)
+    uint32_t* ready[EXCH_MAX_PEERS] = {};    // peer g's ready[slot][self][·]  (ready[self] is local)
+    const uint32_t* ack[EXCH_MAX_PEERS] = {};// local ack[slot][g]: number of merge CTAs peer g has completed on this slot
+};
+
 struct SearchOut {         // device outputs, [nq][k]
     uint64_t* ids;
     double* scores;
     uint64_t* pos;         // may be nullptr
     uint32_t* counts;      // [nq]
     uint32_t* flags;       // [nq]
+    PeerPush peers{};      // row-sharded exchange (G == 0: local outputs only)
 };
 
 // single-query-per-CTA-column fp32 streaming scan (grid = grid_x × nq)
@@ -81,6 +98,20 @@ cudaError_t launch_row_norms(float* rows, uint64_t first, uint64_t n, uint32_t d
                              float* inv_norm, ArenaStats* stats, cudaStream_t s);
 cudaError_t launch_synth_fill(float* rows, uint64_t first_pos, uint64_t n, uint32_t dim, uint32_t pitch,
                               uint64_t seed, uint64_t first_row, uint32_t clusters, cudaStream_t s);
+// exchange.cu: wait for every shard's block of the slot (ready stamps), merge, acknowledge.
+struct ExchangeMerge {
+    uint32_t G, self, nq, k, stamp;
+    const char* slot;              // local slot: G blocks of `blk` bytes, packed layout (vl_packed_result_bytes)
+    uint64_t blk;
+    const uint32_t* ready;         // local ready[slot][g][q], stride nq_cap
+    uint32_t* ack[EXCH_MAX_PEERS]; // peer g's ack[slot][self] counter
+    uint32_t nq_cap;
+    uint64_t* out_ids; double* out_scores; uint64_t* out_pos; uint32_t* out_counts; uint32_t* out_flags;
+};
+// pipelined: launch with the PDL attribute (the kernel releases its dependents at once and ends with
+// griddepcontrol.wait, so "merge complete" still implies "the finalize before it is complete")
+cudaError_t launch_exchange_merge(const ExchangeMerge& m, bool pipelined, cudaStream_t s);
+
 cudaError_t launch_merge_topk(uint32_t G, uint32_t nq, uint32_t k, const uint64_t* ids,
                               const double* scores, const uint64_t* pos, const uint32_t* counts,
                               uint64_t rank_stride, uint64_t* out_ids, double* out_scores, uint64_t* out_pos,

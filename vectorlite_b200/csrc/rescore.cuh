@@ -25,7 +25,16 @@ struct FinalizeParams {
     uint32_t* out_flags;
     double eps_scale;  // multiplies the per-term rounding unit (1 = fp32 scan)
     double tc_abs;     // > 0: bf16 tensor-core scan, |approx − exact| <= tc_abs·‖x‖·‖q‖ (absolute)
+    PeerPush peers;    // G > 0: mirror the results into every peer shard's exchange slot (NVLink stores)
 };
+
+// result store: local, plus the same offset inside every peer's copy of this shard's block
+template <typename T>
+__device__ __forceinline__ void out_store(const FinalizeParams& p, T* ptr, T val) {
+    *ptr = val;
+    for (uint32_t g = 0; g < p.peers.G; ++g)
+        if (g != p.peers.self) *reinterpret_cast<T*>(reinterpret_cast<char*>(ptr) + p.peers.delta[g]) = val;
+}
 
 __device__ __forceinline__ double sim_from_l2(double ss) {  // lib.rs:485-488
     return __ddiv_rn(1.0, __dadd_rn(1.0, __dsqrt_rn(ss)));
@@ -136,6 +145,16 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
     if (p.metric != COSINE && p.metric != MANHATTAN && tid == FIN_THREADS - 1) s_qnorm = __dsqrt_rn(qn2);
     __syncthreads();
 
+    // ---- exchange: the peers must have finished reading the previous use of this slot ----------
+    __shared__ int s_xfail;
+    if (p.peers.G) {
+        if (tid == 0) s_xfail = 0;
+        __syncthreads();
+        if (tid < static_cast<int>(p.peers.G) && tid != static_cast<int>(p.peers.self) && p.peers.stamp > 1u)
+            if (!wait_stamp(p.peers.ack[tid], p.peers.ack_want, EXCH_TIMEOUT_NS)) s_xfail = 1;
+        __syncthreads();
+    }
+
     // ---- (3) final order: score desc, position asc (stable sort of flat.rs:116) -------------
     const int cnt = min(static_cast<int>(p.k), nc);
     if (tid < nc) {
@@ -148,17 +167,17 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
         }
         if (rank < cnt) {
             const size_t o = static_cast<size_t>(qi) * p.k + rank;
-            p.out_ids[o] = p.ids ? p.ids[mp] : p.id_base + mp;
-            p.out_scores[o] = me;
-            if (p.out_pos) p.out_pos[o] = p.pos_base + mp;
+            out_store<uint64_t>(p, p.out_ids + o, p.ids ? p.ids[mp] : p.id_base + mp);
+            out_store<double>(p, p.out_scores + o, me);
+            if (p.out_pos) out_store<uint64_t>(p, p.out_pos + o, p.pos_base + mp);
             if (rank == cnt - 1) s_kth = me;
         }
     }
     for (int i = cnt + tid; i < static_cast<int>(p.k); i += FIN_THREADS) {
         const size_t o = static_cast<size_t>(qi) * p.k + i;
-        p.out_ids[o] = ~0ull;
-        p.out_scores[o] = 0.0;
-        if (p.out_pos) p.out_pos[o] = ~0ull;
+        out_store<uint64_t>(p, p.out_ids + o, ~0ull);
+        out_store<double>(p, p.out_scores + o, 0.0);
+        if (p.out_pos) out_store<uint64_t>(p, p.out_pos + o, ~0ull);
     }
     __syncthreads();
 
@@ -212,8 +231,15 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
             if (!ok) flags |= FLAG_CERT_FAIL;
         }
         if (flags & (FLAG_NONFINITE | FLAG_OVERFLOW)) flags |= FLAG_CERT_FAIL;
-        p.out_counts[qi] = static_cast<uint32_t>(cnt);
-        p.out_flags[qi] = flags;
+        if (p.peers.G && s_xfail) flags |= FLAG_EXCHANGE;
+        out_store<uint32_t>(p, p.out_counts + qi, static_cast<uint32_t>(cnt));
+        out_store<uint32_t>(p, p.out_flags + qi, flags);
+        if (p.peers.G) {
+            // every thread's remote stores precede the barrier above; this fence makes them (and the two
+            // stores just issued) visible system-wide before the stamps that announce them
+            __threadfence_system();
+            for (uint32_t g = 0; g < p.peers.G; ++g) st_release_sys(p.peers.ready[g] + p.peers.q_off + qi, p.peers.stamp);
+        }
         if (ctl) {  // re-arm the control block for the next search on this slot
             ctl->tau = 0ull;
             ctl->flags = 0u;
