@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint3
     uint64_t* s_k = reinterpret_cast<uint64_t*>(sm);  // [capq]
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_bin, s_need, s_out;
+    __shared__ uint32_t s_bin, s_need, s_out, s_all;
+    __shared__ unsigned long long s_min;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = static_cast<int>(n_override ? n_override : min(count[q], capq));
@@ -203,9 +204,21 @@ __global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint3
         if (incl >= need && incl - mycount < need) {  // exactly one thread: the bin holding the need-th key
             s_bin = 255 - tid;
             s_need = need - (incl - mycount);
+            s_all = (mycount == need - (incl - mycount)) ? 1u : 0u;   // every key of the bin is needed
+            s_min = ~0ull;
         }
         __syncthreads();
         prefix |= static_cast<uint64_t>(s_bin) << shift;
+        if (s_all && pass < 7) {
+            // early exit (typically after 3 passes): the Kp-th largest key is the smallest key of this bin
+            for (int i = tid; i < n; i += 256) {
+                const uint64_t key = s_k[i];
+                if ((key >> shift) == (prefix >> shift)) atomicMin(&s_min, static_cast<unsigned long long>(key));
+            }
+            __syncthreads();
+            prefix = s_min;
+            break;
+        }
     }
     // prefix is now the exact Kp-th largest key
     for (int i = tid; i < n; i += 256) {
@@ -246,6 +259,151 @@ __global__ void __launch_bounds__(FIN_THREADS) batch_rescore_kernel(FinalizePara
     }
     __syncthreads();
     rescore_rank_certify(p, qi, n, s_keys, s_exact, s_pos, s_q, s_tile, qflags[qi]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched rescore, streaming form (Kp <= 512): one CTA of KpR + 32 threads per query, KpR = Kp rounded
+// up to a warp.  Thread t < nc owns candidate t and walks its row in reference order (a serial f64
+// chain, lib.rs:425-572); the row data arrives through a double-buffered cp.async pipeline of CH-column
+// chunks ([KpR][CH+4] fp32, (CH+4)/4 odd → conflict-free 128-bit reads), the query is widened to f64 once,
+// and the query-only chain Σy² runs on the spare warp.  Small CTAs (9 per SM at Kp = 64) put all B
+// queries of a batch on the machine in a single wave, where the 512-thread tile kernel needed 3.5.
+constexpr int RS_SPARE = 32;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))),
+                 "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int METRIC>
+__global__ void batch_rescore_stream_kernel(FinalizeParams p, const uint32_t* count, const uint32_t* qflags,
+                                            uint32_t capq, int KpR) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int CH = p.CH, TS = CH + 4;
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);                 // [KpR]
+    double* s_exact = reinterpret_cast<double*>(s_keys + KpR);                // [KpR]
+    double* s_qd = s_exact + KpR;                                             // [pitch]
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_qd + p.pitch);            // [KpR]
+    float* s_tile = reinterpret_cast<float*>(s_pos + KpR);                    // [2][KpR][TS]
+    __shared__ double s_qnorm, s_qn2;
+    __shared__ int s_nan;
+    const uint32_t qi = blockIdx.x;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int nc = static_cast<int>(min(count[qi], static_cast<uint32_t>(p.Kp)));
+    // ---- sort the (<= Kp, unordered) survivors by key, descending: rank by counting ------------------
+    const uint64_t* mine = p.cand + static_cast<size_t>(qi) * capq;
+    uint64_t* s_tmp = reinterpret_cast<uint64_t*>(s_exact);
+    uint64_t key = 0;
+    if (tid < nc) {
+        key = mine[tid];
+        s_tmp[tid] = key;
+    }
+    if (tid == 0) s_nan = 0;
+    const float* q = p.queries + static_cast<size_t>(qi) * p.pitch;
+    for (uint32_t i = tid; i < p.pitch; i += nthreads) s_qd[i] = i < p.dim ? static_cast<double>(q[i]) : 0.0;
+    __syncthreads();
+    if (tid < nc) {
+        int r = 0;
+        for (int j = 0; j < nc; ++j) r += s_tmp[j] > key;
+        s_keys[r] = key;
+        s_pos[r] = key_pos(key);
+    }
+    __syncthreads();
+
+    // ---- (2) exact f64 rescore ----------------------------------------------------------------------
+    const int nchunks = static_cast<int>((p.dim + CH - 1) / CH);
+    auto issue = [&](int c, int buf) {
+        const uint32_t c0 = static_cast<uint32_t>(c) * CH;
+        const int w4 = (min(static_cast<uint32_t>(CH), p.dim - c0) + 3) >> 2;
+        float* dst = s_tile + static_cast<size_t>(buf) * KpR * TS;
+        const int total = nc * w4;
+        for (int i = tid; i < total; i += nthreads) {
+            const int r = i / w4, cc = i - r * w4;
+            cp_async16(dst + r * TS + cc * 4, p.rows + static_cast<size_t>(s_pos[r]) * p.pitch + c0 + cc * 4);
+        }
+        cp_async_commit();
+    };
+    double a0 = 0.0, a1 = 0.0, qn2 = 0.0;
+    issue(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) issue(c + 1, (c + 1) & 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint32_t c0 = static_cast<uint32_t>(c) * CH;
+        const int w = static_cast<int>(min(static_cast<uint32_t>(CH), p.dim - c0));
+        if (tid < nc) {
+            const float4* t4 = reinterpret_cast<const float4*>(s_tile + (static_cast<size_t>(c & 1) * KpR + tid) * TS);
+            const double* yq = s_qd + c0;
+            for (int j4 = 0; j4 * 4 < w; ++j4) {
+                const float4 v = t4[j4];
+                const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j4 * 4 + e;
+                    if (j < w) {
+                        const double x = static_cast<double>(xs[e]), y = yq[j];
+                        if (METRIC == COSINE) {
+                            a0 = __dadd_rn(a0, __dmul_rn(x, y));
+                            a1 = __dadd_rn(a1, __dmul_rn(x, x));
+                        } else if (METRIC == EUCLIDEAN) {
+                            const double d = __dsub_rn(x, y);
+                            a0 = __dadd_rn(a0, __dmul_rn(d, d));
+                        } else if (METRIC == MANHATTAN) {
+                            a0 = __dadd_rn(a0, fabs(__dsub_rn(x, y)));
+                        } else {
+                            a0 = __dadd_rn(a0, __dmul_rn(x, y));
+                        }
+                    }
+                }
+            }
+        } else if (tid == nthreads - 1) {   // query-only chain Σy² (cosine: lib.rs:433; others: certificate)
+            const double* yq = s_qd + c0;
+            for (int j = 0; j < w; ++j) qn2 = __dadd_rn(qn2, __dmul_rn(yq[j], yq[j]));
+        }
+        __syncthreads();   // buffer (c & 1) may be refilled by the next iteration's issue
+    }
+    if (tid == nthreads - 1) {
+        s_qn2 = qn2;
+        s_qnorm = __dsqrt_rn(qn2);
+    }
+    __syncthreads();
+    if (tid < nc) {
+        double sc;
+        if (METRIC == COSINE) {
+            const double na = __dsqrt_rn(a1), nb = s_qnorm;
+            sc = (na == 0.0 || nb == 0.0) ? 0.0 : __ddiv_rn(a0, __dmul_rn(na, nb));
+        } else if (METRIC == EUCLIDEAN) {
+            sc = sim_from_l2(a0);
+        } else if (METRIC == MANHATTAN) {
+            sc = sim_from_l1(a0);
+        } else {
+            sc = a0;
+        }
+        s_exact[tid] = sc;
+        if (sc != sc) s_nan = 1;
+    }
+    __syncthreads();
+    rank_and_certify(p, qi, nc, s_keys, s_exact, s_pos, &s_qnorm, &s_nan, qflags[qi]);
+}
+
+static size_t rescore_stream_smem(int KpR, int CH, uint32_t pitch) {
+    return static_cast<size_t>(KpR) * (8 + 8 + 4) + static_cast<size_t>(pitch) * 8 +
+           2ull * KpR * (CH + 4) * sizeof(float);
+}
+
+template <int METRIC>
+static cudaError_t launch_rescore_stream(const FinalizeParams& p, const BatchWork& w, uint32_t nq, int KpR,
+                                         size_t smem, cudaStream_t s) {
+    auto kern = batch_rescore_stream_kernel<METRIC>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<nq, KpR + RS_SPARE, smem, s>>>(p, w.count, w.qflags, w.capq, KpR);
+    return cudaGetLastError();
 }
 
 static size_t rescore_smem(int Kp, int CH) {
@@ -335,7 +493,20 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     p.eps_scale = 1.0;
     p.tc_abs = use_tc ? tc->tc_abs : 0.0;
     p.peers = out.peers;
-    batch_rescore_kernel<<<nq, FIN_THREADS, rescore_smem(Kp, CH), s>>>(p, w.count, w.qflags, w.capq);
+    const int KpR = (Kp + 31) & ~31;
+    if (nq >= 8 && KpR + RS_SPARE <= 1024) {   // many queries: small streaming CTAs, one wave
+        p.CH = KpR <= 64 ? 32 : 16;
+        const size_t smem = rescore_stream_smem(KpR, p.CH, v.pitch);
+        switch (metric) {
+            case COSINE: e = launch_rescore_stream<COSINE>(p, w, nq, KpR, smem, s); break;
+            case EUCLIDEAN: e = launch_rescore_stream<EUCLIDEAN>(p, w, nq, KpR, smem, s); break;
+            case MANHATTAN: e = launch_rescore_stream<MANHATTAN>(p, w, nq, KpR, smem, s); break;
+            default: e = launch_rescore_stream<DOT>(p, w, nq, KpR, smem, s); break;
+        }
+        if (e != cudaSuccess) return e;
+    } else {
+        batch_rescore_kernel<<<nq, FIN_THREADS, rescore_smem(Kp, CH), s>>>(p, w.count, w.qflags, w.capq);
+    }
     nl += 1;
     if (launches) *launches += nl;
     return cudaGetLastError();

@@ -93,6 +93,11 @@ __device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int i) {
     for (int j = 1; j < 32; ++j) r = (j == i) ? v[j] : r;
     return r;
 }
+__device__ __forceinline__ bool elect_one() {   // one deterministic leader lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -194,9 +199,13 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && active) {
+        // The whole warp runs the loop (warp-uniform control flow and descriptors stay in uniform
+        // registers); one elected lane issues the MMAs and their commits.  Descriptors are advanced
+        // by adding to the encoded 16-byte address field instead of being rebuilt per instruction.
+        if (active) {
             mbar_wait(bar_a, 0);
             tc_fence_after();
+            const uint64_t adesc0 = make_desc(smem_u32(s_a)), bdesc0 = make_desc(smem_u32(s_b));
             uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
                 mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);
@@ -205,15 +214,20 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 for (uint32_t kc = 0; kc < p.kch; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(s_a + kc * A_CHUNK_BYTES), b0 = smem_u32(s_b + stage * B_STAGE_BYTES);
+                    if (elect_one()) {
+                        const uint64_t ad = adesc0 + static_cast<uint64_t>(kc * (A_CHUNK_BYTES >> 4));
+                        const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (B_STAGE_BYTES >> 4));
 #pragma unroll
-                    for (int j = 0; j < BK / 16; ++j)
-                        umma_bf16(d, make_desc(a0 + j * 32), make_desc(b0 + j * 32), IDESC, (kc | j) != 0 ? 1u : 0u);
-                    if (CS == 1) umma_commit(bar_empty + 8 * stage);
-                    else umma_commit_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << CS) - 1));
+                        for (int j = 0; j < BK / 16; ++j)
+                            umma_bf16(d, ad + 2 * j, bd + 2 * j, IDESC, (kc | j) != 0 ? 1u : 0u);
+                        if (CS == 1) umma_commit(bar_empty + 8 * stage);
+                        else umma_commit_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << CS) - 1));
+                    }
+                    __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * buf);
+                if (elect_one()) umma_commit(bar_tfull + 8 * buf);
+                __syncwarp();
                 buf ^= 1;
                 if (buf == 0) tphase ^= 1;
             }
@@ -266,15 +280,31 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 // compact loop over the (rare) set bits — keeps the hot loop inside the instruction cache
                 auto process = [&](const uint32_t (&v)[32], int c0) {
                     if (p.direct) {
-                        if (qvalid) {
+                        // stage 0 keeps every score: transpose 32 queries × 16 columns through this warp's 2 KB of
+                        // the (idle) survivor queue so that each half-warp stores 16 consecutive keys of ONE
+                        // query (128 contiguous bytes) instead of 32 keys 8·capq bytes apart
+                        float* st = reinterpret_cast<float*>(s_pq) + (warp - 2) * 512;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const uint32_t r = row0 + c0 + i;
-                                float s = __uint_as_float(v[i]);
-                                if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]) - qn;
+                        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float s = __uint_as_float(v[half * 16 + i]);
+                                if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + half * 16 + i]) - qn;
                                 if (!isfinite(s)) nonfinite = true;
-                                if (r < p.row_hi) p.cand[static_cast<size_t>(q) * p.capq + (r - p.row_lo)] = make_key(s, r);
+                                st[lane * 16 + (i ^ (lane & 15))] = s;
                             }
+                            __syncwarp();
+                            const int c = lane & 15;
+                            const uint32_t r = row0 + c0 + half * 16 + c;
+#pragma unroll 4
+                            for (int it = 0; it < 16; ++it) {
+                                const int row = 2 * it + (lane >> 4);
+                                const float s = st[row * 16 + (c ^ (row & 15))];
+                                const uint32_t qq = qblock * BM + quarter * 32 + row;
+                                if (qblock < p.qblocks && qq < p.nq && r < p.row_hi)
+                                    p.cand[static_cast<size_t>(qq) * p.capq + (r - p.row_lo)] = make_key(s, r);
+                            }
+                            __syncwarp();
                         }
                         return;
                     }
@@ -295,9 +325,13 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                             if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]) - qn;   // −‖x−q‖²
                             if (!isfinite(s)) nonfinite = true;
                             my_q[nloc * EPI_THREADS] = make_key(s, r);
-                            if (++nloc == QCAP) flush();
+                            if (++nloc == QCAP) flush();   // rare: a lane filled its queue inside one chunk
                         }
                     }
+                    // Convergent flush: as soon as ANY lane's queue is half full, every lane reserves its slots
+                    // in the same instruction, so the warp pays one L2 round trip for 32 queues instead of one
+                    // per lane at 32 different (divergent) moments.
+                    if (__any_sync(0xFFFFFFFFu, nloc >= QCAP / 2)) flush();
                 };
                 uint32_t va[32], vb[32];
                 tmem_ld32(tbase + cbase, va);

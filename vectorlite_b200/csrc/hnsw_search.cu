@@ -44,6 +44,12 @@ struct HnswParams {
     double* out_scores;
     uint32_t* out_counts;
     unsigned long long* visited;
+    // ---- construction mode (hnsw_build.cu): the queries are rows of the arena -------------------------
+    const uint32_t* order = nullptr;      // [nq] node whose row is query qi
+    int stop_level = 0;                   // beam search on this level; greedy descent above it
+    uint32_t entry_only = 0;              // skip the descent: seed the beam with the entry point
+    unsigned long long* out_keys = nullptr;  // [nq][out_stride] sorted beam (orderable distance << 32 | node << 1 | flag)
+    uint32_t out_stride = 0;
 };
 
 __device__ __forceinline__ uint32_t vis_hash(uint32_t id) { return (id * 2654435761u) >> 7; }
@@ -93,7 +99,7 @@ __device__ __forceinline__ unsigned long long beam_key(float d, uint32_t node) {
     return (static_cast<unsigned long long>(f32_orderable(d)) << 32) | (static_cast<unsigned long long>(node) << 1);
 }
 
-template <int METRIC, int NCH>
+template <int METRIC, int NCH, bool BUILD>
 __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: q[pitch] f32 | beam[ef_cap] u64 | vis[vis_mask+1] u32
@@ -111,8 +117,11 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t qi = blockIdx.x;
     const uint32_t pitch4 = p.pitch / 4;
-    const float4* q4 = reinterpret_cast<const float4*>(p.queries) + static_cast<size_t>(qi) * pitch4;
     const float4* rows4 = reinterpret_cast<const float4*>(p.rows);
+    const float4* q4 = BUILD ? rows4 + static_cast<size_t>(__ldg(p.order + qi)) * pitch4
+                             : reinterpret_cast<const float4*>(p.queries) + static_cast<size_t>(qi) * pitch4;
+    const int top_level = BUILD ? (p.entry_only ? p.stop_level : p.g.max_level) : p.g.max_level;
+    const int bottom_level = BUILD ? p.stop_level : 0;
 
     for (uint32_t i = tid; i < pitch4; i += HN_THREADS) s_q[i] = q4[i];
     for (uint32_t i = tid; i <= p.vis_mask; i += HN_THREADS) s_vis[i] = 0u;
@@ -212,13 +221,13 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
             s_vis[vis_hash(p.g.entry) & p.vis_mask] = vis_tag(p.g.entry);
         }
         __syncwarp();
-        pool_recompute_worst(1, p.g.max_level > 0 ? 1u : p.ef);
+        pool_recompute_worst(1, top_level > bottom_level ? 1u : p.ef);
     }
     __syncthreads();
 
     unsigned long long n_eval = 1;
-    for (int lvl = p.g.max_level; lvl >= 0; --lvl) {
-        const uint32_t ef = lvl == 0 ? p.ef : 1u;
+    for (int lvl = top_level; lvl >= bottom_level; --lvl) {
+        const uint32_t ef = lvl == bottom_level ? p.ef : 1u;
         const uint32_t deg = lvl == 0 ? p.g.M0 : p.g.M;
         for (;;) {
             // ---- warp 0: the `expand` closest unexpanded pool entries, then their unvisited neighbours
@@ -305,12 +314,12 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
             __syncthreads();
         }
         // ---- descend: keep the best entry only (greedy levels), un-expand it, forget the cache
-        if (lvl > 0) {
+        if (lvl > bottom_level) {
             __syncthreads();
             if (tid == 0) {
                 s_beam[0] &= ~1ull;          // upper levels run with a pool of one entry
                 s_size = 1;
-                const uint32_t next_ef = lvl == 1 ? p.ef : 1u;
+                const uint32_t next_ef = lvl == bottom_level + 1 ? p.ef : 1u;
                 s_worst = next_ef == 1u ? (s_beam[0] >> 1) : ~0ull;
                 s_worst_idx = 0;
             }
@@ -344,6 +353,12 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
             }
     }
 
+    if (BUILD) {   // construction: hand the whole sorted beam (ascending distance) to the neighbour selection
+        const int size = s_size;
+        for (int i = tid; i < size; i += HN_THREADS) p.out_keys[static_cast<size_t>(qi) * p.out_stride + i] = s_beam[i];
+        if (tid == 0) p.out_counts[qi] = static_cast<uint32_t>(size);
+        return;
+    }
     // ---- results: first k non-deleted beam entries (hnsw.rs:472-475), exact f64 re-score ------
     if (warp == 0) {
         const int size = s_size;
@@ -415,22 +430,64 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     }
     if (tid == 0) {
         p.out_counts[qi] = static_cast<uint32_t>(rc);
-        atomicAdd(p.visited, n_eval);
+        if (p.visited) atomicAdd(p.visited, n_eval);
     }
 }
 
-template <int METRIC>
+template <int METRIC, bool BUILD>
 static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
     if (p.pitch == 384) {
-        auto k = hnsw_search_kernel<METRIC, 3>;
+        auto k = hnsw_search_kernel<METRIC, 3, BUILD>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         k<<<nq, HN_THREADS, smem, s>>>(p);
     } else {
-        auto k = hnsw_search_kernel<METRIC, 0>;
+        auto k = hnsw_search_kernel<METRIC, 0, BUILD>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         k<<<nq, HN_THREADS, smem, s>>>(p);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 6;
+}
+
+// beam / visited-cache sizing shared by search and construction; returns the dynamic smem bytes
+static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t pitch) {
+    p.ef = W;
+    uint32_t bcap = 64;
+    while (bcap < p.ef) bcap <<= 1;
+    p.beam_cap = bcap;
+    // visited tag cache (16-bit tags): ~2 slots per expected evaluation (~W·M0/2 fresh nodes), 2K..32K entries
+    const uint32_t want = p.ef * M0;
+    uint32_t cap = 2048;
+    while (cap < want && cap < 32768) cap <<= 1;
+    p.vis_mask = cap - 1;
+    return static_cast<size_t>(pitch) * 4 + static_cast<size_t>(bcap) * 8 + static_cast<size_t>(cap) * 2;
+}
+
+// construction-time search (hnsw_build.cu): node order[i]'s row is query i; greedy descent from the entry
+// point through the levels above `level` (or none when entry_only), beam of exactly `ef` on `level`; the
+// sorted beam goes to out_keys[i][0..out_counts[i]).
+int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
+                             const uint32_t* d_order, uint32_t nq, int level, bool entry_only, uint32_t ef,
+                             unsigned long long* d_out_keys, uint32_t out_stride, uint32_t* d_out_counts,
+                             cudaStream_t stream) {
+    if (ef > HN_EF_MAX || ef > out_stride || ef == 0) return 9;
+    HnswParams p;
+    p.g = g;
+    p.rows = d_rows;
+    p.queries = nullptr;
+    p.pitch = pitch;
+    p.dim = dim;
+    p.k = 0;
+    p.out_ids = nullptr; p.out_scores = nullptr; p.out_counts = d_out_counts; p.visited = nullptr;
+    p.order = d_order; p.stop_level = level; p.entry_only = entry_only ? 1u : 0u;
+    p.out_keys = d_out_keys; p.out_stride = out_stride;
+    const size_t smem = size_pool(p, ef, level == 0 ? g.M0 : g.M, pitch);
+    switch (metric) {
+        case COSINE: return launch_metric<COSINE, true>(p, nq, smem, stream);
+        case EUCLIDEAN: return launch_metric<EUCLIDEAN, true>(p, nq, smem, stream);
+        case MANHATTAN: return launch_metric<MANHATTAN, true>(p, nq, smem, stream);
+        case DOT: return launch_metric<DOT, true>(p, nq, smem, stream);
+        default: return 5;
+    }
 }
 
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
@@ -452,25 +509,16 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     uint64_t W = static_cast<uint64_t>(ef < 1 ? 1 : ef) * HN_BEAM_MULT;
     if (W < k) W = k;
     if (W > HN_EF_MAX) W = HN_EF_MAX;
-    p.ef = static_cast<uint32_t>(W);
-    uint32_t bcap = 64;
-    while (bcap < p.ef) bcap <<= 1;
-    p.beam_cap = bcap;
-    // visited tag cache (16-bit tags): ~2 slots per expected evaluation (~W·M0/2 fresh nodes), 2K..32K entries
-    const uint32_t want = p.ef * g.M0;
-    uint32_t cap = 2048;
-    while (cap < want && cap < 32768) cap <<= 1;
-    p.vis_mask = cap - 1;
     p.out_ids = d_out_ids;
     p.out_scores = d_out_scores;
     p.out_counts = d_out_counts;
     p.visited = d_visited;
-    const size_t smem = static_cast<size_t>(pitch) * 4 + static_cast<size_t>(bcap) * 8 + static_cast<size_t>(cap) * 2;
+    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, pitch);
     switch (metric) {
-        case COSINE: return launch_metric<COSINE>(p, nq, smem, stream);
-        case EUCLIDEAN: return launch_metric<EUCLIDEAN>(p, nq, smem, stream);
-        case MANHATTAN: return launch_metric<MANHATTAN>(p, nq, smem, stream);
-        case DOT: return launch_metric<DOT>(p, nq, smem, stream);
+        case COSINE: return launch_metric<COSINE, false>(p, nq, smem, stream);
+        case EUCLIDEAN: return launch_metric<EUCLIDEAN, false>(p, nq, smem, stream);
+        case MANHATTAN: return launch_metric<MANHATTAN, false>(p, nq, smem, stream);
+        case DOT: return launch_metric<DOT, false>(p, nq, smem, stream);
         default: return 5;
     }
 }

@@ -44,13 +44,126 @@ __device__ __forceinline__ double sim_from_l1(double s) {   // lib.rs:528-531
 }
 
 
+// Phases (3)-(4) + the exchange hand-shake.  Expects s_exact[0..nc) (exact scores), s_pos[0..nc), s_keys[0..nc)
+// (sorted by key, descending), *s_qnorm = ‖q‖ and *s_nan already written and made visible by a barrier.
+// All threads of the block call; blockDim.x >= nc.
+__device__ __forceinline__ void rank_and_certify(const FinalizeParams& p, uint32_t qi, int nc, const uint64_t* s_keys,
+                                                 const double* s_exact, const uint32_t* s_pos, const double* s_qnorm,
+                                                 const int* s_nan, uint32_t extra_flags) {
+    __shared__ double s_kth;
+    const int tid = threadIdx.x;
+    QueryCtl* ctl = p.ctl ? p.ctl + qi : nullptr;
+    // ---- exchange: the peers must have finished reading the previous use of this slot ----------
+    __shared__ int s_xfail;
+    if (p.peers.G) {
+        if (tid == 0) s_xfail = 0;
+        __syncthreads();
+        if (tid < static_cast<int>(p.peers.G) && tid != static_cast<int>(p.peers.self) && p.peers.stamp > 1u)
+            if (!wait_stamp(p.peers.ack[tid], p.peers.ack_want, EXCH_TIMEOUT_NS)) s_xfail = 1;
+        __syncthreads();
+    }
+
+    // ---- (3) final order: score desc, position asc (stable sort of flat.rs:116) -------------
+    const int cnt = min(static_cast<int>(p.k), nc);
+    if (tid < nc) {
+        const double me = s_exact[tid];
+        const uint32_t mp = s_pos[tid];
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) {
+            const double o = s_exact[j];
+            rank += (o > me) || (o == me && s_pos[j] < mp);
+        }
+        if (rank < cnt) {
+            const size_t o = static_cast<size_t>(qi) * p.k + rank;
+            out_store<uint64_t>(p, p.out_ids + o, p.ids ? p.ids[mp] : p.id_base + mp);
+            out_store<double>(p, p.out_scores + o, me);
+            if (p.out_pos) out_store<uint64_t>(p, p.out_pos + o, p.pos_base + mp);
+            if (rank == cnt - 1) s_kth = me;
+        }
+    }
+    for (int i = cnt + tid; i < static_cast<int>(p.k); i += static_cast<int>(blockDim.x)) {
+        const size_t o = static_cast<size_t>(qi) * p.k + i;
+        out_store<uint64_t>(p, p.out_ids + o, ~0ull);
+        out_store<double>(p, p.out_scores + o, 0.0);
+        if (p.out_pos) out_store<uint64_t>(p, p.out_pos + o, ~0ull);
+    }
+    __syncthreads();
+
+    // ---- (4) certificate ---------------------------------------------------------------
+    if (tid == 0) {
+        uint32_t flags = (ctl ? ctl->flags : 0u) | extra_flags;
+        if (*s_nan) flags |= FLAG_NAN;
+        const bool excluded_exist = p.n > static_cast<uint32_t>(nc);
+        if (excluded_exist && cnt > 0) {
+            // every excluded row has approximate score <= worst (in scan units)
+            const double worst = static_cast<double>(key_score(s_keys[nc - 1]));
+            const double u = 5.9604644775390625e-08 * p.eps_scale;  // 2^-24 × scale
+            const double nn = static_cast<double>(p.pitch);
+            const double kth = s_kth;
+            bool ok;
+            if (p.tc_abs > 0.0) {
+                // bf16 inputs: x̃ = x(1+δ), |δ| <= 2^-9 each side → |Σx̃q̃ − Σxq| <= (2^-8+2^-18)·‖x‖‖q‖,
+                // plus fp32 accumulation in the tensor core; tc_abs covers both with margin.
+                const double qn = *s_qnorm;
+                const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
+                if (p.metric == COSINE) {       // rows pre-normalised: scan units are cos·‖q‖
+                    ok = qn >= 1e-15 && kth > worst / qn + p.tc_abs;
+                } else if (p.metric == DOT) {
+                    ok = kth > worst + p.tc_abs * maxn * qn + 1e-30;
+                } else {                        // −‖x−q‖² from ‖x‖² + ‖q‖² − 2x·q
+                    double L = (-worst) - 2.0 * p.tc_abs * maxn * qn - 2e-6 * (maxn * maxn + qn * qn) - 1e-36;
+                    L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                    ok = kth > sim_from_l2(L);
+                }
+            } else if (p.metric == COSINE) {
+                // |fl32(dot)·fl32(1/‖a‖) − dot/‖a‖| <= ((nn+8)·u)·‖q‖ ; cosine = that / ‖q‖
+                const double qn = *s_qnorm;
+                const double min_nz = __longlong_as_double(p.stats->min_nz_norm_sq_bits);
+                const bool scale_ok = qn >= 1e-15 && !(min_nz < 1e-30);
+                const double bound = worst / qn + (nn + 8.0) * u * 1.01 + 1e-30;
+                ok = scale_ok && kth > bound;
+            } else if (p.metric == DOT) {
+                const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
+                const double bound = worst + (nn + 2.0) * u * 1.01 * maxn * (*s_qnorm) + 1e-30;
+                ok = kth > bound;
+            } else if (p.metric == EUCLIDEAN) {
+                // Σ(a−q)² has only non-negative terms → RELATIVE error <= (nn+4)·u
+                double L = (-worst) * (1.0 - (nn + 4.0) * u * 1.01) - 1e-36;
+                L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                ok = kth > sim_from_l2(L);
+            } else {
+                double L = (-worst) * (1.0 - (nn + 2.0) * u * 1.01) - 1e-36;
+                L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                ok = kth > sim_from_l1(L);
+            }
+            if (!ok) flags |= FLAG_CERT_FAIL;
+        }
+        if (flags & (FLAG_NONFINITE | FLAG_OVERFLOW)) flags |= FLAG_CERT_FAIL;
+        if (p.peers.G && s_xfail) flags |= FLAG_EXCHANGE;
+        out_store<uint32_t>(p, p.out_counts + qi, static_cast<uint32_t>(cnt));
+        out_store<uint32_t>(p, p.out_flags + qi, flags);
+        if (p.peers.G) {
+            // every thread's remote stores precede the barrier above; this fence makes them (and the two
+            // stores just issued) visible system-wide before the stamps that announce them
+            __threadfence_system();
+            for (uint32_t g = 0; g < p.peers.G; ++g) st_release_sys(p.peers.ready[g] + p.peers.q_off + qi, p.peers.stamp);
+        }
+        if (ctl) {  // re-arm the control block for the next search on this slot
+            ctl->tau = 0ull;
+            ctl->flags = 0u;
+            ctl->done = 0u;
+        }
+    }
+}
+
+
 // Shared-memory carve-up expected by rescore_rank_certify (dynamic smem of the calling kernel):
 //   keys[SCAN_CAP] u64 | exact[KP_MAX] f64 | pos[KP_MAX] u32 | q[CH] f32 | tile[Kp][CH+1] f32
 // s_keys[0..nc) must hold the candidates sorted by key, descending.  All FIN_THREADS threads call.
 __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, uint32_t qi, int nc,
                                                      uint64_t* s_keys, double* s_exact, uint32_t* s_pos,
                                                      float* s_q, float* s_tile, uint32_t extra_flags) {
-    __shared__ double s_kth, s_qnorm;
+    __shared__ double s_qnorm;
     __shared__ int s_nan;
     const int tid = threadIdx.x;
     QueryCtl* ctl = p.ctl ? p.ctl + qi : nullptr;
@@ -145,107 +258,7 @@ __device__ __forceinline__ void rescore_rank_certify(const FinalizeParams& p, ui
     if (p.metric != COSINE && p.metric != MANHATTAN && tid == FIN_THREADS - 1) s_qnorm = __dsqrt_rn(qn2);
     __syncthreads();
 
-    // ---- exchange: the peers must have finished reading the previous use of this slot ----------
-    __shared__ int s_xfail;
-    if (p.peers.G) {
-        if (tid == 0) s_xfail = 0;
-        __syncthreads();
-        if (tid < static_cast<int>(p.peers.G) && tid != static_cast<int>(p.peers.self) && p.peers.stamp > 1u)
-            if (!wait_stamp(p.peers.ack[tid], p.peers.ack_want, EXCH_TIMEOUT_NS)) s_xfail = 1;
-        __syncthreads();
-    }
-
-    // ---- (3) final order: score desc, position asc (stable sort of flat.rs:116) -------------
-    const int cnt = min(static_cast<int>(p.k), nc);
-    if (tid < nc) {
-        const double me = s_exact[tid];
-        const uint32_t mp = s_pos[tid];
-        int rank = 0;
-        for (int j = 0; j < nc; ++j) {
-            const double o = s_exact[j];
-            rank += (o > me) || (o == me && s_pos[j] < mp);
-        }
-        if (rank < cnt) {
-            const size_t o = static_cast<size_t>(qi) * p.k + rank;
-            out_store<uint64_t>(p, p.out_ids + o, p.ids ? p.ids[mp] : p.id_base + mp);
-            out_store<double>(p, p.out_scores + o, me);
-            if (p.out_pos) out_store<uint64_t>(p, p.out_pos + o, p.pos_base + mp);
-            if (rank == cnt - 1) s_kth = me;
-        }
-    }
-    for (int i = cnt + tid; i < static_cast<int>(p.k); i += FIN_THREADS) {
-        const size_t o = static_cast<size_t>(qi) * p.k + i;
-        out_store<uint64_t>(p, p.out_ids + o, ~0ull);
-        out_store<double>(p, p.out_scores + o, 0.0);
-        if (p.out_pos) out_store<uint64_t>(p, p.out_pos + o, ~0ull);
-    }
-    __syncthreads();
-
-    // ---- (4) certificate ---------------------------------------------------------------
-    if (tid == 0) {
-        uint32_t flags = (ctl ? ctl->flags : 0u) | extra_flags;
-        if (s_nan) flags |= FLAG_NAN;
-        const bool excluded_exist = p.n > static_cast<uint32_t>(nc);
-        if (excluded_exist && cnt > 0) {
-            // every excluded row has approximate score <= worst (in scan units)
-            const double worst = static_cast<double>(key_score(s_keys[nc - 1]));
-            const double u = 5.9604644775390625e-08 * p.eps_scale;  // 2^-24 × scale
-            const double nn = static_cast<double>(p.pitch);
-            const double kth = s_kth;
-            bool ok;
-            if (p.tc_abs > 0.0) {
-                // bf16 inputs: x̃ = x(1+δ), |δ| <= 2^-9 each side → |Σx̃q̃ − Σxq| <= (2^-8+2^-18)·‖x‖‖q‖,
-                // plus fp32 accumulation in the tensor core; tc_abs covers both with margin.
-                const double qn = s_qnorm;
-                const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
-                if (p.metric == COSINE) {       // rows pre-normalised: scan units are cos·‖q‖
-                    ok = qn >= 1e-15 && kth > worst / qn + p.tc_abs;
-                } else if (p.metric == DOT) {
-                    ok = kth > worst + p.tc_abs * maxn * qn + 1e-30;
-                } else {                        // −‖x−q‖² from ‖x‖² + ‖q‖² − 2x·q
-                    double L = (-worst) - 2.0 * p.tc_abs * maxn * qn - 2e-6 * (maxn * maxn + qn * qn) - 1e-36;
-                    L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
-                    ok = kth > sim_from_l2(L);
-                }
-            } else if (p.metric == COSINE) {
-                // |fl32(dot)·fl32(1/‖a‖) − dot/‖a‖| <= ((nn+8)·u)·‖q‖ ; cosine = that / ‖q‖
-                const double qn = s_qnorm;
-                const double min_nz = __longlong_as_double(p.stats->min_nz_norm_sq_bits);
-                const bool scale_ok = qn >= 1e-15 && !(min_nz < 1e-30);
-                const double bound = worst / qn + (nn + 8.0) * u * 1.01 + 1e-30;
-                ok = scale_ok && kth > bound;
-            } else if (p.metric == DOT) {
-                const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
-                const double bound = worst + (nn + 2.0) * u * 1.01 * maxn * s_qnorm + 1e-30;
-                ok = kth > bound;
-            } else if (p.metric == EUCLIDEAN) {
-                // Σ(a−q)² has only non-negative terms → RELATIVE error <= (nn+4)·u
-                double L = (-worst) * (1.0 - (nn + 4.0) * u * 1.01) - 1e-36;
-                L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
-                ok = kth > sim_from_l2(L);
-            } else {
-                double L = (-worst) * (1.0 - (nn + 2.0) * u * 1.01) - 1e-36;
-                L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
-                ok = kth > sim_from_l1(L);
-            }
-            if (!ok) flags |= FLAG_CERT_FAIL;
-        }
-        if (flags & (FLAG_NONFINITE | FLAG_OVERFLOW)) flags |= FLAG_CERT_FAIL;
-        if (p.peers.G && s_xfail) flags |= FLAG_EXCHANGE;
-        out_store<uint32_t>(p, p.out_counts + qi, static_cast<uint32_t>(cnt));
-        out_store<uint32_t>(p, p.out_flags + qi, flags);
-        if (p.peers.G) {
-            // every thread's remote stores precede the barrier above; this fence makes them (and the two
-            // stores just issued) visible system-wide before the stamps that announce them
-            __threadfence_system();
-            for (uint32_t g = 0; g < p.peers.G; ++g) st_release_sys(p.peers.ready[g] + p.peers.q_off + qi, p.peers.stamp);
-        }
-        if (ctl) {  // re-arm the control block for the next search on this slot
-            ctl->tau = 0ull;
-            ctl->flags = 0u;
-            ctl->done = 0u;
-        }
-    }
+    rank_and_certify(p, qi, nc, s_keys, s_exact, s_pos, &s_qnorm, &s_nan, extra_flags);
 }
 
 }  // namespace vl
