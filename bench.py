@@ -130,7 +130,7 @@ def synth_host_rows(oracle, seed, n, dim, threads):
 
 
 def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
-    """HNSW default profile (M/M0 = 16/32) on the 1024-centre mixture: build on the host cores, then
+    """HNSW default profile (M/M0 = 16/32) on the 1024-centre mixture: bulk build (device builder), then
     QPS (host API, 4096-query batches, copies included), recall@10 vs the exact flat result and
     evaluated nodes per query over the ef sweep.  ef = 0 is the reference's own setting (ef = k)."""
     metric = vl.SimilarityMetric.Cosine
@@ -144,9 +144,10 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
     flat.close()
     h = vl.HNSWIndex(DIM, metric, M=16, M0=32, ef_construction=efc, device=device)
     t0 = time.perf_counter()
-    h.add_batch(ids, rows)
+    h.add_batch(ids, rows)       # bulk add into an empty index: built on the device (csrc/hnsw_build.cu)
     h.build()
     build_s = time.perf_counter() - t0
+    build_info = h.build_info()
     del rows
     sweep = {}
     for ef in (0, 16, 32, 64, 128, 256):
@@ -168,7 +169,8 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
             ref[name] = {e: round(v["recall_at_10"], 4) for e, v in d["sweep"].items()}
     h.close()
     return {"rows": n, "dim": DIM, "data": f"synthetic {clusters}-centre mixture, unit norm", "M": 16, "M0": 32,
-            "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "build_threads": cpu_threads(),
+            "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "builder": build_info,
+            "host_threads": cpu_threads(),
             "sweep": sweep,
             "reference_restatement_recall": ref,
             "note": "reference recall = oracle restatement of crate hnsw 0.11 + u64-quantised functors at "

@@ -92,6 +92,16 @@ int vl_index_fill_synthetic(vl_index* h, uint64_t seed, uint64_t first_row, uint
                             uint32_t clusters, uint64_t first_id);
 /* HNSW only: (re)build / finish the device graph after bulk adds.  Called implicitly by search. */
 int vl_index_build(vl_index* h);
+/* HNSW construction (src/index/hnsw.rs:363-399 inserts one vector at a time on one CPU thread).  A bulk
+ * vl_index_add_batch into an EMPTY index (>= 4096 rows) is built on the device, layer by layer in batches
+ * (csrc/hnsw_build.cu); single adds and adds to a non-empty index use the parallel host builder.
+ * builder: 0 = auto (default), 1 = always host, 2 = device for any bulk add into an empty index. */
+int vl_hnsw_set_builder(vl_index* h, int builder);
+/* Builder used by the last bulk add (1 = host, 2 = device) and its wall time in microseconds. */
+int vl_hnsw_build_info(const vl_index* h, uint64_t* out_builder, uint64_t* out_micros);
+/* Structural audit of the graph (all levels): out6 = nodes, layer-0 edges, self loops, duplicate edges,
+ * invalid targets (out of range / absent from the level / after a gap), isolated layer-0 nodes. */
+int vl_hnsw_graph_check(const vl_index* h, uint64_t* out6);
 
 /* ---- queries (reader side) ------------------------------------------------------------ */
 /* VectorIndex::search (flat.rs:98-119, hnsw.rs:415-496) for nq queries at once (nq = 1 is the

@@ -20,9 +20,10 @@ queries = qidx.export()[1]
 t = time.time(); truth, _, _ = flat.search_batch(queries, k, metric); t_flat = time.time() - t
 ids, rows = flat.export()
 h = vl.HNSWIndex(dim, metric, M=M, M0=M0, ef_construction=efc)
+h.set_builder(os.environ.get("BUILDER", "auto"))
 t = time.time(); h.add_batch(ids, rows); h.build(); build_s = time.time() - t
 out = {"n": n, "clusters": clusters, "M": M, "M0": M0, "ef_construction": efc, "nq": nq, "build_seconds": build_s,
-       "build_threads": os.cpu_count(), "flat_exact_batch_seconds": t_flat, "sweep": {}}
+       "builder": h.build_info(), "graph": h.graph_check(), "build_threads": os.cpu_count(), "flat_exact_batch_seconds": t_flat, "sweep": {}}
 print("built in", build_s, flush=True)
 for ef in (0, 16, 32, 64, 128, 256):
     h.search_batch(queries[:256], k, metric, ef)

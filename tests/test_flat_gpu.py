@@ -324,6 +324,13 @@ def test_peer_exchange_three_shards_one_gpu(vl, oracle_mod):
                                     o["o_sc"].data_ptr(), o["o_pos"].data_ptr(), o["o_cnt"].data_ptr(),
                                     o["xflg"].data_ptr(), streams[g].cuda_stream)
     torch.cuda.synchronize()
+    # One unchecked round through the exchange itself: first use loads the merge kernel and sizes the
+    # exchange scratch, which may synchronise the device and (in this one-GPU emulation only) leave a
+    # shard's merge spinning until its time-out.  Stamps only grow, so the checked rounds below start clean.
+    for g in range(G):
+        shards[g].set_pipelined(False)
+        xs[g].search(shards[g], d_q[0:1], k, vl.SimilarityMetric.Cosine, outs(1), streams[g].cuda_stream)
+    torch.cuda.synchronize()
     pending = []
     for metric, lo, hi, overlap in rounds:
         res = []

@@ -160,3 +160,42 @@ def test_recall_vs_committed_reference_numbers_384d(vl, oracle_mod, clusters):
         report[ef_s] = (round(ours, 3), round(r["recall_at_10"], 3), h.stats()["hnsw_visited"] // nq, int(r["visited_per_query"]))
         assert ours >= r["recall_at_10"] - 0.01, (clusters, ef_s, ours, r["recall_at_10"])
     print(f"clusters={clusters} ef: (ours, reference, our visited/q, reference visited/q) = {report}")
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_device_builder_matches_host_builder(vl, oracle_mod, metric):
+    """bulk construction on the device (csrc/hnsw_build.cu) must give a structurally valid
+    graph whose recall@10 at equal (M, M0, ef_construction, ef) is on par with the host builder's."""
+    n, dim, k, nq = 30000, 96, 10, 300
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=128)
+    queries = oracle_mod.synth_rows(43, 0, nq, dim, clusters=128)
+    ids = np.arange(n, dtype=np.uint64)
+    st, truth, _ = oracle_mod.flat_search_batch(rows, ids, queries, k, metric, nthreads=8)
+    assert st == 0
+    rec, info = {}, {}
+    for builder in ("host", "device"):
+        h = vl.HNSWIndex(dim, vl.SimilarityMetric(metric), M=16, M0=32, ef_construction=100)
+        h.set_builder(builder)
+        h.add_batch(ids, rows)
+        info[builder] = h.build_info()
+        assert info[builder]["builder"] == builder
+        chk = h.graph_check()
+        assert chk["nodes"] == n and chk["self_loops"] == 0 and chk["duplicates"] == 0 and chk["invalid"] == 0, chk
+        assert chk["isolated0"] == 0 and chk["edges0"] >= 8 * n, chk
+        rec[builder] = {}
+        for ef in (0, 32, 128):
+            gi, gs, gc = h.search_batch(queries, k, vl.SimilarityMetric(metric), ef)
+            assert np.all(gc == k)
+            rec[builder][ef] = _recall(gi, gc, truth)
+        # incremental adds after a device build go through the host builder and stay searchable
+        if builder == "device":
+            extra = oracle_mod.synth_rows(44, 0, 8, dim, clusters=128)
+            for j in range(8):
+                h.add(vl.Vector(n + j, extra[j].tolist()))
+            res = h.search(extra[3].tolist(), 1, vl.SimilarityMetric(metric))
+            assert res and res[0].id == n + 3
+            assert h.graph_check()["invalid"] == 0
+    print(f"metric={metric} builders: {info} recall@10: {rec}")
+    for ef in (0, 32, 128):
+        assert rec["device"][ef] >= rec["host"][ef] - 0.02, (ef, rec)
+    assert rec["device"][128] >= 0.95

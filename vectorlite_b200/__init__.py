@@ -126,6 +126,9 @@ def lib():
         "vl_index_delete": (i32, [vp, u64]),
         "vl_index_fill_synthetic": (i32, [vp, u64, u64, u64, u32, u64]),
         "vl_index_build": (i32, [vp]),
+        "vl_hnsw_set_builder": (i32, [vp, i32]),
+        "vl_hnsw_build_info": (i32, [vp, u64p, u64p]),
+        "vl_hnsw_graph_check": (i32, [vp, u64p]),
         "vl_index_search": (i32, [vp, fp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
         "vl_index_search_f64": (i32, [vp, dp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
         "vl_index_search_device": (i32, [vp, vp, u32, u32, i32, u32, vp, vp, vp, vp, vp, vp]),
@@ -386,6 +389,29 @@ class HNSWIndex(_CudaIndex):
         st = self._L.vl_index_build(self._h)
         if st != VL_OK:
             raise VectorLiteError(st, _err())
+
+    BUILDERS = {"auto": 0, "host": 1, "device": 2}
+
+    def set_builder(self, builder: str) -> None:
+        """Where bulk adds into an empty index build the graph: "auto" (device from 4096 rows), "host", "device"."""
+        st = self._L.vl_hnsw_set_builder(self._h, self.BUILDERS[builder])
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+
+    def build_info(self) -> dict:
+        b, us = C.c_uint64(0), C.c_uint64(0)
+        st = self._L.vl_hnsw_build_info(self._h, C.byref(b), C.byref(us))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        return {"builder": {0: "none", 1: "host", 2: "device"}[int(b.value)], "seconds": us.value / 1e6}
+
+    def graph_check(self) -> dict:
+        out = np.zeros(6, dtype=np.uint64)
+        st = self._L.vl_hnsw_graph_check(self._h, _ptr(out, C.c_uint64))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        keys = ["nodes", "edges0", "self_loops", "duplicates", "invalid", "isolated0"]
+        return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def index_type(self):
         return IndexType.HNSW

@@ -607,8 +607,10 @@ int vl_index_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint
         int st = flat_add_batch(h, internal.data(), rows, n);
         if (st) return st;
         (void)was_identity;
-        st = hnsw_add_rows(h->hnsw.get(), ids, rows, n);
-        if (st) return fail(st, "hnsw insert failed");
+        uint64_t nl = 0;
+        st = hnsw_add_rows(h->hnsw.get(), ids, rows, n, h->d_rows, h->pitch, h->mut_stream, &nl);
+        if (st) return fail(st, "hnsw insert failed: %s", cudaGetErrorString(cudaGetLastError()));
+        h->stats[ST_LAUNCHES] += nl;
         return VL_OK;
     }
     return flat_add_batch(h, ids, rows, n);
@@ -687,6 +689,28 @@ int vl_index_fill_synthetic(vl_index* h, uint64_t seed, uint64_t first_row, uint
     const uint64_t last = first_id + n - 1;
     if (!h->have_max || last > h->max_id) { h->max_id = last; h->have_max = true; }
     h->n += n;
+    return VL_OK;
+}
+
+int vl_hnsw_set_builder(vl_index* h, int builder) {
+    if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
+    if (builder < 0 || builder > 2) return fail(VL_ERR_INVALID, "builder must be 0 (auto), 1 (host) or 2 (device)");
+    hnsw_set_builder(h->hnsw.get(), builder);
+    return VL_OK;
+}
+
+int vl_hnsw_build_info(const vl_index* h, uint64_t* out_builder, uint64_t* out_micros) {
+    if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
+    uint64_t info[2];
+    hnsw_build_info(h->hnsw.get(), info);
+    if (out_builder) *out_builder = info[0];
+    if (out_micros) *out_micros = info[1];
+    return VL_OK;
+}
+
+int vl_hnsw_graph_check(const vl_index* h, uint64_t* out6) {
+    if (!h || h->type != VL_INDEX_HNSW || !out6) return fail(VL_ERR_INVALID, "not an HNSW index");
+    hnsw_graph_check(h->hnsw.get(), out6);
     return VL_OK;
 }
 

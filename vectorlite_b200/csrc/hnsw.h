@@ -20,9 +20,18 @@ bool hnsw_has_id(const HnswState* s, uint64_t id);
 bool hnsw_index_of(const HnswState* s, uint64_t id, uint64_t* internal_index);
 bool hnsw_max_id(const HnswState* s, uint64_t* out);
 uint64_t hnsw_live(const HnswState* s);
-// append n rows (host f32 [n][dim]) to the graph; internal index == arena position
-int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n);
+// append n rows (host f32 [n][dim]) to the graph; internal index == arena position.  d_rows/pitch: the same
+// rows in the device arena (already uploaded on `stream`).  A bulk add into an EMPTY graph is built on the
+// device (hnsw_build.cu) unless the builder is pinned to the host; everything else is inserted by the
+// parallel host builder.
+enum { HNSW_BUILDER_AUTO = 0, HNSW_BUILDER_HOST = 1, HNSW_BUILDER_DEVICE = 2 };
+int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n, const float* d_rows,
+                  uint32_t pitch, cudaStream_t stream, uint64_t* launches);
+void hnsw_set_builder(HnswState* s, int builder);
+// [0] builder used by the last bulk add (1 host, 2 device), [1] its wall time in microseconds
+void hnsw_build_info(const HnswState* s, uint64_t out[2]);
 bool hnsw_soft_delete(HnswState* s, uint64_t id);
+void hnsw_graph_check(const HnswState* s, uint64_t out[6]);
 // live rows in insertion order: up to `cap` starting at live position `first` (rows come from the host copy)
 uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows);
 // flatten + upload the graph if it changed since the last upload

@@ -31,11 +31,6 @@
 
 namespace vl {
 
-int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
-                             const uint32_t* d_order, uint32_t nq, int level, bool entry_only, uint32_t ef,
-                             unsigned long long* d_out_keys, uint32_t out_stride, uint32_t* d_out_counts,
-                             cudaStream_t stream);
-
 namespace {
 
 constexpr int HB_WARPS = 4;                  // warps (= nodes / targets) per CTA

@@ -12,6 +12,7 @@
 // recall at equal (M, M0, ef_construction, ef) is >= the reference's.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <queue>
@@ -287,8 +288,16 @@ bool hnsw_max_id(const HnswState* s, uint64_t* out) {  // metadata.keys().max() 
 }
 uint64_t hnsw_live(const HnswState* s) { return s->live; }
 
-int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n) {
+void hnsw_set_builder(HnswState* s, int builder) { s->builder = builder; }
+void hnsw_build_info(const HnswState* s, uint64_t out[2]) {
+    out[0] = static_cast<uint64_t>(s->last_builder);
+    out[1] = s->last_build_us;
+}
+
+int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n, const float* d_rows,
+                  uint32_t pitch, cudaStream_t stream, uint64_t* launches) {
     if (n == 0) return 0;
+    const auto t_begin = std::chrono::steady_clock::now();
     const uint32_t first = static_cast<uint32_t>(s->level.size());
     const uint64_t total = first + n;
     if (total >= 0x7FFFFFFFull) return 9;
@@ -327,6 +336,26 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
     }
     s->live += n;
     s->dirty = true;
+    auto finish = [&](int builder) {
+        if (n >= 1024) {
+            s->last_builder = builder;
+            s->last_build_us = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::microseconds>(
+                                                          std::chrono::steady_clock::now() - t_begin).count());
+        }
+        return 0;
+    };
+
+    // ---- bulk add into an empty graph: build on the device (hnsw_build.cu) ----
+    int builder = s->builder;
+    if (const char* e = std::getenv("VL_HNSW_BUILDER")) {
+        if (!strcmp(e, "host")) builder = HNSW_BUILDER_HOST;
+        else if (!strcmp(e, "device")) builder = HNSW_BUILDER_DEVICE;
+    }
+    if (first == 0 && d_rows && builder != HNSW_BUILDER_HOST && (builder == HNSW_BUILDER_DEVICE || n >= 4096)) {
+        const int st = hnsw_build_device(s, d_rows, pitch, stream, launches);
+        if (st) return st;
+        return finish(HNSW_BUILDER_DEVICE);
+    }
 
     // ---- insert: the first few nodes sequentially, the rest over all host threads ----
     Builder b(*s);
@@ -341,7 +370,7 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
         for (; start < seq_end; ++start) b.insert(start, sc);
         if (nthreads == 1 || total - start < 1024) {
             for (; start < total; ++start) b.insert(start, sc);
-            return 0;
+            return finish(HNSW_BUILDER_HOST);
         }
     }
     std::atomic<uint32_t> next(start);
@@ -357,7 +386,37 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
             }
         });
     for (auto& x : th) x.join();
-    return 0;
+    return finish(HNSW_BUILDER_HOST);
+}
+
+// structural audit of the host copy of the graph (all levels): see vl_hnsw_graph_check
+void hnsw_graph_check(const HnswState* s, uint64_t out[6]) {
+    const size_t n = s->level.size();
+    uint64_t edges0 = 0, self = 0, dup = 0, invalid = 0, isolated = 0;
+    for (size_t i = 0; i < n; ++i) {
+        for (int l = 0; l <= s->level[i]; ++l) {
+            const uint32_t cap = l == 0 ? s->M0 : s->M;
+            const uint32_t* a = l == 0 ? s->adj0.data() + i * s->M0
+                                       : s->upper.data() + (static_cast<size_t>(s->upper_off[i]) + l - 1) * s->M;
+            uint32_t deg = 0;
+            bool gap = false;
+            for (uint32_t j = 0; j < cap; ++j) {
+                const uint32_t v = a[j];
+                if (v == HNSW_NONE) { gap = true; continue; }
+                if (gap) ++invalid;                       // lists must be dense prefixes
+                ++deg;
+                if (v == i) ++self;
+                if (v >= n || s->level[v] < l) { ++invalid; continue; }
+                for (uint32_t j2 = 0; j2 < j; ++j2)
+                    if (a[j2] == v) { ++dup; break; }
+            }
+            if (l == 0) {
+                edges0 += deg;
+                if (deg == 0 && n > 1) ++isolated;
+            }
+        }
+    }
+    out[0] = n; out[1] = edges0; out[2] = self; out[3] = dup; out[4] = invalid; out[5] = isolated;
 }
 
 bool hnsw_soft_delete(HnswState* s, uint64_t id) {  // hnsw.rs:400-414

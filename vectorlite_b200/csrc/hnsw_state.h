@@ -46,6 +46,9 @@ struct HnswState {
     std::unique_ptr<std::atomic<uint8_t>[]> locks;
     size_t locks_cap = 0;
     std::mutex entry_mu;
+    int builder = 0;                   // HNSW_BUILDER_*
+    int last_builder = 0;              // builder used by the last bulk add
+    uint64_t last_build_us = 0;
     // ---- device copy ----
     uint32_t* d_adj0 = nullptr; uint32_t* d_upper_off = nullptr; uint32_t* d_upper = nullptr;
     uint8_t* d_level = nullptr; uint8_t* d_deleted = nullptr; uint64_t* d_ids = nullptr; float* d_inv_norm = nullptr;
@@ -63,5 +66,13 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
                        cudaStream_t stream);
+
+// hnsw_search.cu, construction mode: node d_order[i]'s row is query i; beam of `ef` on `level`
+int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
+                             const uint32_t* d_order, uint32_t nq, int level, bool entry_only, uint32_t ef,
+                             unsigned long long* d_out_keys, uint32_t out_stride, uint32_t* d_out_counts,
+                             cudaStream_t stream);
+// hnsw_build.cu: build the whole (empty) graph of `s` on the device; adjacency is copied back to the host
+int hnsw_build_device(HnswState* s, const float* d_rows, uint32_t pitch, cudaStream_t stream, uint64_t* launches);
 
 }  // namespace vl
