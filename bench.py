@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time the other metrics / batch modes")
     ap.add_argument("--hnsw-rows", type=int, default=1_000_000, help="HNSW section size (0 = skip; rank 0, N=1 only)")
-    ap.add_argument("--hnsw-efc", type=int, default=200)
+    ap.add_argument("--hnsw-efc", type=int, default=400, help="ef_construction (reference default: 400)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -99,6 +99,11 @@ int vl_index_build(vl_index* h);
 int vl_hnsw_set_builder(vl_index* h, int builder);
 /* Builder used by the last bulk add (1 = host, 2 = device) and its wall time in microseconds. */
 int vl_hnsw_build_info(const vl_index* h, uint64_t* out_builder, uint64_t* out_micros);
+/* Scores returned by HNSW searches.  0 (default): the exact Flat similarity of each returned id (f64, lib.rs:425-572),
+ * so Flat and HNSW agree.  1: the reference's own HNSW score — the functor's u64 milli-unit distance
+ * (hnsw.rs:113-174) / 1000 (hnsw.rs:478) through convert_distance_to_similarity (hnsw.rs:51-75), bit for bit,
+ * including its second division by 1000 for cosine and dot product; results ordered by that score. */
+int vl_hnsw_set_score_mode(vl_index* h, int mode);
 /* Structural audit of the graph (all levels): out6 = nodes, layer-0 edges, self loops, duplicate edges,
  * invalid targets (out of range / absent from the level / after a gap), isolated layer-0 nodes. */
 int vl_hnsw_graph_check(const vl_index* h, uint64_t* out6);

@@ -199,3 +199,41 @@ def test_device_builder_matches_host_builder(vl, oracle_mod, metric):
     for ef in (0, 32, 128):
         assert rec["device"][ef] >= rec["host"][ef] - 0.02, (ef, rec)
     assert rec["device"][128] >= 0.95
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+def test_reference_score_mode(vl, oracle_mod, kats, metric):
+    """in reference score mode the returned score is the functor's u64 milli-unit distance
+    (hnsw.rs:113-174) / 1000 (hnsw.rs:478) through convert_distance_to_similarity (hnsw.rs:51-75), bit for bit."""
+    n, dim, k = 3000, 48, 10
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=16)
+    if metric in (2, 3):
+        rows = rows * np.float32(7.5)            # spread the milli-unit distances / leave the dot clamp's flat top
+    q = oracle_mod.synth_rows(43, 0, 6, dim, clusters=16)
+    h = vl.HNSWIndex(dim, vl.SimilarityMetric(metric), ef_construction=64)
+    h.add_batch(np.arange(n, dtype=np.uint64), rows)
+    h.set_score_mode("reference")
+    gi, gs, gc = h.search_batch(q, k, vl.SimilarityMetric(metric), 32)
+    assert np.all(gc == k) and np.all(np.diff(gs, axis=1) <= 0)
+    for qi in range(q.shape[0]):
+        for j in range(k):
+            d = oracle_mod.hnsw_distance(metric, rows[int(gi[qi, j])].astype(np.float64), q[qi].astype(np.float64))
+            want = oracle_mod.convert_distance_to_similarity(d / 1000.0, metric)
+            assert gs[qi, j] == want, (metric, qi, j, gs[qi, j], want)
+    h.set_score_mode("exact")
+    _, gs2, _ = h.search_batch(q[:1], k, vl.SimilarityMetric(metric), 32)
+    want = oracle_mod.metric(metric, rows[int(h.search_batch(q[:1], k, vl.SimilarityMetric(metric), 32)[0][0, 0])].astype(np.float64),
+                             q[0].astype(np.float64))
+    assert gs2[0, 0] == want
+    if metric == 1:   # the reference's own toy KAT (hnsw.rs:605-634): quantised distances 173/1424/1424/911
+        case = kats["hnsw"]["id_mapping"]
+        t = vl.HNSWIndex(3, vl.SimilarityMetric.Euclidean)
+        for r in case["rows"]:
+            t.add(vl.Vector(r["id"], r["values"]))
+        t.set_score_mode("reference")
+        res = t.search(case["query"], 4, vl.SimilarityMetric.Euclidean)
+        by_id = {r.id: r.score for r in res}
+        for r, want in zip(case["rows"], case["scores_by_row"]):
+            if r["id"] in by_id:
+                assert by_id[r["id"]] == want, (r["id"], by_id[r["id"]], want)
+        assert res[0].id == 100

@@ -128,6 +128,7 @@ def lib():
         "vl_index_build": (i32, [vp]),
         "vl_hnsw_set_builder": (i32, [vp, i32]),
         "vl_hnsw_build_info": (i32, [vp, u64p, u64p]),
+        "vl_hnsw_set_score_mode": (i32, [vp, i32]),
         "vl_hnsw_graph_check": (i32, [vp, u64p]),
         "vl_index_search": (i32, [vp, fp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
         "vl_index_search_f64": (i32, [vp, dp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
@@ -395,6 +396,12 @@ class HNSWIndex(_CudaIndex):
     def set_builder(self, builder: str) -> None:
         """Where bulk adds into an empty index build the graph: "auto" (device from 4096 rows), "host", "device"."""
         st = self._L.vl_hnsw_set_builder(self._h, self.BUILDERS[builder])
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+
+    def set_score_mode(self, mode: str) -> None:
+        """"exact" (default): Flat similarity of the returned ids; "reference": the reference's quantised HNSW score."""
+        st = self._L.vl_hnsw_set_score_mode(self._h, {"exact": 0, "reference": 1}[mode])
         if st != VL_OK:
             raise VectorLiteError(st, _err())
 

@@ -699,6 +699,13 @@ int vl_hnsw_set_builder(vl_index* h, int builder) {
     return VL_OK;
 }
 
+int vl_hnsw_set_score_mode(vl_index* h, int mode) {
+    if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
+    if (mode != 0 && mode != 1) return fail(VL_ERR_INVALID, "score mode must be 0 (exact) or 1 (reference-quantised)");
+    hnsw_set_score_mode(h->hnsw.get(), static_cast<uint32_t>(mode));
+    return VL_OK;
+}
+
 int vl_hnsw_build_info(const vl_index* h, uint64_t* out_builder, uint64_t* out_micros) {
     if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
     uint64_t info[2];

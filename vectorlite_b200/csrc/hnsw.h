@@ -28,6 +28,7 @@ enum { HNSW_BUILDER_AUTO = 0, HNSW_BUILDER_HOST = 1, HNSW_BUILDER_DEVICE = 2 };
 int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n, const float* d_rows,
                   uint32_t pitch, cudaStream_t stream, uint64_t* launches);
 void hnsw_set_builder(HnswState* s, int builder);
+void hnsw_set_score_mode(HnswState* s, uint32_t mode);
 // [0] builder used by the last bulk add (1 host, 2 device), [1] its wall time in microseconds
 void hnsw_build_info(const HnswState* s, uint64_t out[2]);
 bool hnsw_soft_delete(HnswState* s, uint64_t id);

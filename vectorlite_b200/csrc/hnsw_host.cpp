@@ -289,6 +289,7 @@ bool hnsw_max_id(const HnswState* s, uint64_t* out) {  // metadata.keys().max() 
 uint64_t hnsw_live(const HnswState* s) { return s->live; }
 
 void hnsw_set_builder(HnswState* s, int builder) { s->builder = builder; }
+void hnsw_set_score_mode(HnswState* s, uint32_t mode) { s->score_mode = mode; }
 void hnsw_build_info(const HnswState* s, uint64_t out[2]) {
     out[0] = static_cast<uint64_t>(s->last_builder);
     out[1] = s->last_build_us;
@@ -512,7 +513,7 @@ int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const fl
     double* d_scores = reinterpret_cast<double*>(s->d_out + on * 8);
     uint32_t* d_counts = reinterpret_cast<uint32_t*>(s->d_out + on * 16);
     int st = hnsw_launch_search(g, d_rows, pitch, s->dim, s->metric, s->d_q, nq, k, ef_search, d_ids, d_scores,
-                                d_counts, s->d_visited, stream);
+                                d_counts, s->d_visited, stream, s->score_mode);
     if (st) return st;
     unsigned long long vis = 0;
     cudaMemcpyAsync(s->h_out, s->d_out, need, cudaMemcpyDeviceToHost, stream);

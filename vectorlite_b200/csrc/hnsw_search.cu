@@ -40,6 +40,7 @@ struct HnswParams {
     const float* rows;
     const float* queries;
     uint32_t pitch, dim, k, ef, vis_mask, beam_cap;
+    uint32_t score_mode = 0;              // 0: exact flat similarity, 1: the reference's quantised score (hnsw.rs:478,51-75)
     uint64_t* out_ids;
     double* out_scores;
     uint32_t* out_counts;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     __shared__ int s_nc, s_size, s_done;
     __shared__ float s_invq;
     __shared__ double s_ex[HN_K_MAX];
+    __shared__ double s_qs[HN_K_MAX];   // reference score mode: quantised scores
     __shared__ uint32_t s_rid[HN_K_MAX];
     __shared__ int s_rcount;
 
@@ -412,16 +414,47 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
             sc = a0;
         }
         s_ex[t] = sc;
+        if (p.score_mode == 1) {
+            // reference score mode: the u64 milli-unit distance of the functors (hnsw.rs:113-174; `as u64`
+            // truncates toward zero, saturates, NaN -> 0), divided by 1000 (hnsw.rs:478) and pushed through
+            // convert_distance_to_similarity (hnsw.rs:51-75), which divides cosine / dot by 1000 AGAIN
+            unsigned long long d;
+            if (METRIC == COSINE) {
+                const double na = __dsqrt_rn(a1), nb = __dsqrt_rn(a2);
+                d = (na == 0.0 || nb == 0.0) ? 1000ull
+                                             : __double2ull_rz(__dmul_rn(__dsub_rn(1.0, __ddiv_rn(a0, __dmul_rn(na, nb))), 1000.0));
+            } else if (METRIC == EUCLIDEAN) {
+                d = __double2ull_rz(__dmul_rn(__dsqrt_rn(a0), 1000.0));
+            } else if (METRIC == MANHATTAN) {
+                d = __double2ull_rz(__dmul_rn(a0, 1000.0));
+            } else {
+                const double c = a0 != a0 ? a0 : fmin(fmax(a0, -1000.0), 1000.0);   // f64::clamp keeps NaN
+                d = c != c ? 0ull : __double2ull_rz(__dsub_rn(1000.0, c));
+            }
+            const double dist = __ddiv_rn(__ull2double_rn(d), 1000.0);
+            double q;
+            if (METRIC == COSINE) q = __dsub_rn(1.0, __ddiv_rn(dist, 1000.0));
+            else if (METRIC == DOT) q = fmin(fmax(__ddiv_rn(__dsub_rn(1000.0, dist), 1000.0), 0.0), 1.0);
+            else q = __ddiv_rn(1.0, __dadd_rn(1.0, dist));
+            s_qs[t] = q;
+        }
     }
     __syncthreads();
     for (int t = tid; t < rc; t += HN_THREADS) {  // final order: score desc, insertion order asc (hnsw.rs:493)
         const double me = s_ex[t];
         const uint32_t mn = s_rid[t];
         int rank = 0;
-        for (int j = 0; j < rc; ++j) rank += (s_ex[j] > me) || (s_ex[j] == me && s_rid[j] < mn);
+        if (p.score_mode == 1) {   // quantised score desc; ties (the reference keeps the crate's order) by exact score
+            const double mq = s_qs[t];
+            for (int j = 0; j < rc; ++j)
+                rank += (s_qs[j] > mq) ||
+                        (s_qs[j] == mq && ((s_ex[j] > me) || (s_ex[j] == me && s_rid[j] < mn)));
+        } else {
+            for (int j = 0; j < rc; ++j) rank += (s_ex[j] > me) || (s_ex[j] == me && s_rid[j] < mn);
+        }
         const size_t o = static_cast<size_t>(qi) * p.k + rank;
         p.out_ids[o] = p.g.ids[mn];
-        p.out_scores[o] = me;
+        p.out_scores[o] = p.score_mode == 1 ? s_qs[t] : me;
     }
     for (int i = rc + tid; i < static_cast<int>(p.k); i += HN_THREADS) {
         const size_t o = static_cast<size_t>(qi) * p.k + i;
@@ -493,7 +526,7 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, uint32_t score_mode) {
     if (k > HN_K_MAX) return 9;
     HnswParams p;
     p.g = g;
@@ -513,6 +546,7 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.out_scores = d_out_scores;
     p.out_counts = d_out_counts;
     p.visited = d_visited;
+    p.score_mode = score_mode;
     const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, pitch);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, false>(p, nq, smem, stream);

@@ -47,6 +47,7 @@ struct HnswState {
     size_t locks_cap = 0;
     std::mutex entry_mu;
     int builder = 0;                   // HNSW_BUILDER_*
+    uint32_t score_mode = 0;           // 0 exact flat similarity, 1 reference-quantised (hnsw.rs:478 + 51-75)
     int last_builder = 0;              // builder used by the last bulk add
     uint64_t last_build_us = 0;
     // ---- device copy ----
@@ -65,7 +66,7 @@ struct HnswState {
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
-                       cudaStream_t stream);
+                       cudaStream_t stream, uint32_t score_mode = 0);
 
 // hnsw_search.cu, construction mode: node d_order[i]'s row is query i; beam of `ef` on `level`
 int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
