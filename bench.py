@@ -362,7 +362,7 @@ def main():
 
     # ---- extras: other metrics, batched (B=1024) tensor-core / CUDA-core pipelines ---------------------
     extras = {}
-    if args.extras:
+    if args.extras or world == 1:   # N = 1: always (a second of GPU time); N > 1: only on request
         for name, mid in METRIC_NAMES.items():
             m2 = vl.SimilarityMetric(mid)
 
@@ -406,7 +406,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
         rows = synth_host_rows(oracle, 42, n_shard, DIM, threads)
-        nq_cpu = max(threads, 4)
+        nq_cpu = max(3 * threads, 4)   # ≈ 20-25 s of CPU work at 1M rows (0.5 s per query per thread)
         qps_cpu, dt_cpu, cpu_ids = cpu_flat_qps(oracle, rows, queries[:nq_cpu], k, int(metric), threads)
         assert np.array_equal(cpu_ids[:4].astype(np.int64), got_ids[:4]), "GPU ids differ from the oracle"
         qps_1t, dt_1t, _ = cpu_flat_qps(oracle, rows, queries[:2], k, int(metric), 1)

@@ -21,6 +21,9 @@
 //
 // Bound: random 1.5 KB row gathers → HBM/L2 latency and bandwidth; no single roofline.  Reported:
 // QPS, visited nodes per query (d_visited), recall@10 vs exact flat.
+#include <algorithm>
+#include <cstdlib>
+
 #include "hnsw_state.h"
 #include "kernels.h"
 
@@ -100,8 +103,9 @@ __device__ __forceinline__ unsigned long long beam_key(float d, uint32_t node) {
     return (static_cast<unsigned long long>(f32_orderable(d)) << 32) | (static_cast<unsigned long long>(node) << 1);
 }
 
-template <int METRIC, int NCH, bool BUILD>
-__global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
+template <int METRIC, int NCH, bool BUILD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
+    constexpr int THREADS = WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: q[pitch] f32 | beam[ef_cap] u64 | vis[vis_mask+1] u32
     float4* s_q = reinterpret_cast<float4*>(smem_raw);
@@ -111,9 +115,12 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     __shared__ uint32_t s_cid[HN_MAX_CAND];
     __shared__ int s_nc, s_size, s_done;
     __shared__ float s_invq;
-    __shared__ double s_ex[HN_K_MAX];
-    __shared__ double s_qs[HN_K_MAX];   // reference score mode: quantised scores
-    __shared__ uint32_t s_rid[HN_K_MAX];
+    // result staging reuses the traversal's scratch (dead by then): exact scores over the candidate keys,
+    // result nodes over the candidate ids, quantised scores (reference score mode) over the visited cache
+    static_assert(HN_K_MAX <= HN_MAX_CAND, "result arrays alias the candidate arrays");
+    double* s_ex = reinterpret_cast<double*>(s_ck);
+    uint32_t* s_rid = s_cid;
+    double* s_qs = reinterpret_cast<double*>(s_vis);   // >= 2048 tags x 2 B... needs HN_K_MAX x 8 B: see size_pool
     __shared__ int s_rcount;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -125,8 +132,8 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     const int top_level = BUILD ? (p.entry_only ? p.stop_level : p.g.max_level) : p.g.max_level;
     const int bottom_level = BUILD ? p.stop_level : 0;
 
-    for (uint32_t i = tid; i < pitch4; i += HN_THREADS) s_q[i] = q4[i];
-    for (uint32_t i = tid; i <= p.vis_mask; i += HN_THREADS) s_vis[i] = 0u;
+    for (uint32_t i = tid; i < pitch4; i += THREADS) s_q[i] = q4[i];
+    for (uint32_t i = tid; i <= p.vis_mask; i += THREADS) s_vis[i] = 0u;
     __syncthreads();
     float4 qreg[NCH > 0 ? NCH : 1];
     if (NCH > 0) {
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
             // ---- all warps: distances, 8 candidates per warp per round; candidates that cannot enter
             // the pool (not closer than its current worst entry) are dropped right here
             const unsigned long long worst_now = s_worst;
-            for (int g0 = warp * 8; g0 < nc; g0 += HN_WARPS * 8) {
+            for (int g0 = warp * 8; g0 < nc; g0 += WARPS * 8) {
                 const int cnt = min(8, nc - g0);
                 score8(s_cid + g0, cnt, s_ck + g0);
                 __syncwarp();
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
                 s_worst = next_ef == 1u ? (s_beam[0] >> 1) : ~0ull;
                 s_worst_idx = 0;
             }
-            for (uint32_t i = tid; i <= p.vis_mask; i += HN_THREADS) s_vis[i] = 0u;
+            for (uint32_t i = tid; i <= p.vis_mask; i += THREADS) s_vis[i] = 0u;
             __syncthreads();
             if (tid == 0) {
                 const uint32_t node = static_cast<uint32_t>(s_beam[0] >> 1) & 0x7FFFFFFFu;
@@ -340,11 +347,11 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
         const int size = s_size;
         int len = 2;
         while (len < size) len <<= 1;
-        for (int i = size + tid; i < len; i += HN_THREADS) s_beam[i] = ~0ull;
+        for (int i = size + tid; i < len; i += THREADS) s_beam[i] = ~0ull;
         __syncthreads();
         for (int k2 = 2; k2 <= len; k2 <<= 1)
             for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (len >> 1); t += HN_THREADS) {
+                for (int t = tid; t < (len >> 1); t += THREADS) {
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const int pp = i | j;
                     const bool asc = (i & k2) == 0;
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
 
     if (BUILD) {   // construction: hand the whole sorted beam (ascending distance) to the neighbour selection
         const int size = s_size;
-        for (int i = tid; i < size; i += HN_THREADS) p.out_keys[static_cast<size_t>(qi) * p.out_stride + i] = s_beam[i];
+        for (int i = tid; i < size; i += THREADS) p.out_keys[static_cast<size_t>(qi) * p.out_stride + i] = s_beam[i];
         if (tid == 0) p.out_counts[qi] = static_cast<uint32_t>(size);
         return;
     }
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     }
     __syncthreads();
     const int rc = s_rcount;
-    for (int t = tid; t < rc; t += HN_THREADS) {
+    for (int t = tid; t < rc; t += THREADS) {
         const uint32_t node = s_rid[t];
         const float* row = p.rows + static_cast<size_t>(node) * p.pitch;
         const float* q = reinterpret_cast<const float*>(s_q);
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
         }
     }
     __syncthreads();
-    for (int t = tid; t < rc; t += HN_THREADS) {  // final order: score desc, insertion order asc (hnsw.rs:493)
+    for (int t = tid; t < rc; t += THREADS) {  // final order: score desc, insertion order asc (hnsw.rs:493)
         const double me = s_ex[t];
         const uint32_t mn = s_rid[t];
         int rank = 0;
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
         p.out_ids[o] = p.g.ids[mn];
         p.out_scores[o] = p.score_mode == 1 ? s_qs[t] : me;
     }
-    for (int i = rc + tid; i < static_cast<int>(p.k); i += HN_THREADS) {
+    for (int i = rc + tid; i < static_cast<int>(p.k); i += THREADS) {
         const size_t o = static_cast<size_t>(qi) * p.k + i;
         p.out_ids[o] = ~0ull;
         p.out_scores[o] = 0.0;
@@ -467,18 +474,40 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswParams p) {
     }
 }
 
-template <int METRIC, bool BUILD>
-static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
+template <int METRIC, bool BUILD, int WARPS>
+static int launch_warps(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
     if (p.pitch == 384) {
-        auto k = hnsw_search_kernel<METRIC, 3, BUILD>;
+        auto k = hnsw_search_kernel<METRIC, 3, BUILD, WARPS>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        k<<<nq, HN_THREADS, smem, s>>>(p);
+        k<<<nq, WARPS * 32, smem, s>>>(p);
     } else {
-        auto k = hnsw_search_kernel<METRIC, 0, BUILD>;
+        auto k = hnsw_search_kernel<METRIC, 0, BUILD, WARPS>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        k<<<nq, HN_THREADS, smem, s>>>(p);
+        k<<<nq, WARPS * 32, smem, s>>>(p);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 6;
+}
+
+// CTA width: narrow CTAs (1–2 warps) keep more queries resident per SM and spend less time at CTA barriers
+// while warp 0 runs the serial pool maintenance; wide beams amortise better over 4 warps.
+static int hnsw_cta_warps(uint32_t beam, uint32_t nq) {
+    if (const char* e = std::getenv("VL_HNSW_WARPS")) {
+        const int w = atoi(e);
+        if (w == 1 || w == 2 || w == 4) return w;
+    }
+    // measured on 1M x 384 (scripts/hnsw_tune.py, profiles/r01_hnsw_tune.jsonl): with thousands of queries in
+    // flight one warp per query wins at every beam width (1.42M vs 0.85M q/s at beam 80)
+    (void)beam;
+    return nq < 1024 ? 4 : 1;          // few queries: latency matters, use a whole CTA per query
+}
+
+template <int METRIC, bool BUILD>
+static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
+    switch (hnsw_cta_warps(p.ef, nq)) {
+        case 1: return launch_warps<METRIC, BUILD, 1>(p, nq, smem, s);
+        case 2: return launch_warps<METRIC, BUILD, 2>(p, nq, smem, s);
+        default: return launch_warps<METRIC, BUILD, 4>(p, nq, smem, s);
+    }
 }
 
 // beam / visited-cache sizing shared by search and construction; returns the dynamic smem bytes
@@ -488,8 +517,12 @@ static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t pitch) 
     while (bcap < p.ef) bcap <<= 1;
     p.beam_cap = bcap;
     // visited tag cache (16-bit tags): ~2 slots per expected evaluation (~W·M0/2 fresh nodes), 2K..32K entries
-    const uint32_t want = p.ef * M0;
-    uint32_t cap = 2048;
+    // wide beams are occupancy-bound by the cache's shared memory: halve it there (a lost tag only costs a
+    // re-evaluation), keep it roomy for narrow beams where re-evaluations dominate
+    uint32_t vis_div = p.ef >= 256 ? 2 : 1;
+    if (const char* e = std::getenv("VL_HNSW_VIS_DIV")) vis_div = static_cast<uint32_t>(std::max(1, atoi(e)));
+    const uint32_t want = p.ef * M0 / vis_div;
+    uint32_t cap = 2048;   // >= HN_K_MAX·8 B: the quantised-score staging aliases the cache
     while (cap < want && cap < 32768) cap <<= 1;
     p.vis_mask = cap - 1;
     return static_cast<size_t>(pitch) * 4 + static_cast<size_t>(bcap) * 8 + static_cast<size_t>(cap) * 2;
