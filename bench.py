@@ -151,7 +151,7 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
     del rows
     sweep = {}
     for ef in (0, 16, 32, 64, 128, 256):
-        h.search_batch(queries[:512], k, metric, ef)
+        h.search_batch(queries, k, metric, ef)      # warm-up at the timed batch size (same kernel variant)
         t0 = time.perf_counter()
         reps = 3
         for _ in range(reps):
@@ -217,10 +217,30 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything that writes to fd 1 (NCCL's version / INFO banner, library chatter) to stderr; the
+    one JSON line goes to the real stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -454,7 +474,7 @@ def main():
             "extras": extras,
             "hnsw": hnsw,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -18,11 +18,15 @@ flat.close()
 h = vl.HNSWIndex(dim, metric, M=16, M0=32, ef_construction=efc)
 h.add_batch(ids, rows); h.build()
 print(json.dumps({"build": h.build_info()}), flush=True)
-for warps in os.environ.get("WARPS", "4,2,1").split(","):
-    for vdiv in os.environ.get("VDIVS", "1,2").split(","):
+import itertools
+for warps, vdiv, regpool in itertools.product(os.environ.get("WARPS", "4,2,1").split(","),
+                                              os.environ.get("VDIVS", "1,2").split(","),
+                                              os.environ.get("REGPOOLS", "1").split(",")):
+    if True:
         os.environ["VL_HNSW_WARPS"] = warps
         os.environ["VL_HNSW_VIS_DIV"] = vdiv
-        row = {"warps": int(warps), "vis_div": int(vdiv)}
+        os.environ["VL_HNSW_REGPOOL"] = regpool
+        row = {"warps": int(warps), "vis_div": int(vdiv), "regpool": int(regpool)}
         for ef in (0, 16, 32, 64, 128):
             h.search_batch(queries[:512], k, metric, ef)
             t = time.perf_counter()
@@ -33,3 +37,15 @@ for warps in os.environ.get("WARPS", "4,2,1").split(","):
             row[str(ef)] = {"qps": round(nq / dt), "recall": round(hit / (nq * k), 4),
                             "visited": round(h.stats()["hnsw_visited"] / nq)}
         print(json.dumps(row), flush=True)
+
+if os.environ.get("REBUILD"):
+    for regpool in os.environ["REBUILD"].split(","):
+        os.environ["VL_HNSW_REGPOOL"] = regpool
+        os.environ.pop("VL_HNSW_WARPS", None); os.environ.pop("VL_HNSW_VIS_DIV", None)
+        h2 = vl.HNSWIndex(dim, metric, M=16, M0=32, ef_construction=efc)
+        h2.add_batch(ids, rows)
+        print(json.dumps({"rebuild_regpool": int(regpool), "build": h2.build_info(), "graph": h2.graph_check()}), flush=True)
+        gi, gs, gc = h2.search_batch(queries, k, metric, 0)
+        hit = sum(len(set(map(int, gi[i, :gc[i]])) & set(map(int, truth[i]))) for i in range(nq))
+        print(json.dumps({"rebuild_regpool": int(regpool), "recall_ef0": hit / (nq * k)}), flush=True)
+        h2.close()
