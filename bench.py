@@ -138,7 +138,8 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
     flat.fill_synthetic(42, n, clusters=clusters)
     qsrc = vl.FlatIndex(DIM, device=device)
     qsrc.fill_synthetic(43, nq, clusters=clusters)
-    queries = qsrc.export()[1]
+    import torch
+    queries = torch.from_numpy(qsrc.export()[1]).pin_memory().numpy()   # e2e leg: inputs start in PINNED host memory
     truth, _, _ = flat.search_batch(queries, k, metric)          # exact, certified (tensor-core batched path)
     ids, rows = flat.export()
     flat.close()

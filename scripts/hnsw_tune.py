@@ -11,7 +11,8 @@ dim, k, nq, clusters = 384, 10, 4096, 1024
 metric = vl.SimilarityMetric.Cosine
 flat = vl.FlatIndex(dim); flat.fill_synthetic(42, n, clusters=clusters)
 qidx = vl.FlatIndex(dim); qidx.fill_synthetic(43, nq, clusters=clusters)
-queries = qidx.export()[1]
+import torch
+queries = torch.from_numpy(qidx.export()[1]).pin_memory().numpy() if os.environ.get('PINNED', '1') == '1' else qidx.export()[1]
 truth, _, _ = flat.search_batch(queries, k, metric)
 ids, rows = flat.export()
 flat.close()
@@ -28,7 +29,7 @@ for warps, vdiv, regpool in itertools.product(os.environ.get("WARPS", "4,2,1").s
         os.environ["VL_HNSW_REGPOOL"] = regpool
         row = {"warps": int(warps), "vis_div": int(vdiv), "regpool": int(regpool)}
         for ef in (0, 16, 32, 64, 128):
-            h.search_batch(queries[:512], k, metric, ef)
+            h.search_batch(queries, k, metric, ef)
             t = time.perf_counter()
             for _ in range(3):
                 gi, gs, gc = h.search_batch(queries, k, metric, ef)

@@ -389,6 +389,24 @@ def test_full_size_1m_properties_and_sampled_oracle(vl, oracle_mod):
     for metric in vl.SimilarityMetric:
         _check(vl, oracle_mod, idx, rows, None, q, k, metric)
     assert idx.stats()["exact_queries"] == 0, "certificate should hold on i.i.d. data"
+    # BASELINE config 2, B = 1024 at full size: the tcgen05 pipeline (all three threshold stages, coalesced
+    # stage-0 stores, convergent survivor flush, streaming rescore) against the oracle on sampled queries
+    # and against the independent single-query fp32 path
+    bq = oracle_mod.synth_rows(43, 1000, 1024, dim)
+    sample = [0, 1, 127, 128, 511, 1023]
+    for metric in (vl.SimilarityMetric.Cosine, vl.SimilarityMetric.Euclidean, vl.SimilarityMetric.DotProduct):
+        before = idx.stats()
+        bi, bs, bc = idx.search_batch(bq, k, metric)
+        after = idx.stats()
+        assert np.all(bc == k) and np.all(np.diff(bs, axis=1) <= 0)
+        assert after["exact_queries"] == before["exact_queries"], "every certificate must hold on the tensor path"
+        st, oi, os_ = oracle_mod.flat_search_batch(rows, None, bq[sample], k, int(metric), nthreads=8)
+        assert st == 0
+        assert np.array_equal(bi[sample], oi), metric
+        assert np.array_equal(bs[sample].view(np.uint64), os_.view(np.uint64)), metric
+        for j in (5, 700):
+            si, ss, _ = idx.search_batch(bq[j:j + 1], k, metric)
+            assert np.array_equal(si[0], bi[j]) and np.array_equal(ss[0].view(np.uint64), bs[j].view(np.uint64))
 
 
 @pytest.mark.parametrize("n,dim", [(5, 8), (3000, 96), (20000, 384), (70000, 100)])

@@ -262,15 +262,21 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         };
         if (active) {
             uint32_t buf = 0, tphase = 0;
+            float xn_pref = 0.f;
+            if (METRIC == EUCLIDEAN) {
+                const uint32_t r0 = p.row_lo + t0 * BN + etid;
+                xn_pref = r0 < p.row_hi ? __ldg(p.sq_norm + r0) : 0.f;
+            }
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
                 const uint32_t row0 = p.row_lo + t * BN;
                 if (METRIC == EUCLIDEAN) {
-                    // stage ‖x‖² of the tile's rows (all epilogue warps read all 256 of them)
-                    for (int i = etid; i < BN; i += EPI_THREADS) {
-                        const uint32_t r = row0 + i;
-                        s_xn[buf * BN + i] = r < p.row_hi ? __ldg(p.sq_norm + r) : 0.f;
-                    }
+                    // stage ‖x‖² of the tile's rows (one per epilogue thread; every warp reads its 128 columns).
+                    // The value was loaded one tile ahead, so its L2/HBM latency is off the critical path.
+                    static_assert(EPI_THREADS == BN, "one squared norm per epilogue thread");
+                    s_xn[buf * BN + etid] = xn_pref;
                     asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                    const uint32_t rn = row0 + tstride * BN + etid;
+                    xn_pref = (t + tstride < p.tiles && rn < p.row_hi) ? __ldg(p.sq_norm + rn) : 0.f;
                 }
                 mbar_wait(bar_tfull + 8 * buf, tphase);
                 tc_fence_after();

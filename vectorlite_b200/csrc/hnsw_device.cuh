@@ -19,7 +19,7 @@ struct HnswParams {
     HnswDeviceGraph g;
     const float* rows;
     const float* queries;
-    uint32_t pitch, dim, k, ef, vis_mask, beam_cap;
+    uint32_t pitch, dim, k, ef, vis_mask, beam_cap, cand_cap;
     uint32_t score_mode = 0;              // 0: exact flat similarity, 1: the reference's quantised score (hnsw.rs:478,51-75)
     uint64_t* out_ids;
     double* out_scores;
@@ -80,12 +80,29 @@ __device__ __forceinline__ unsigned long long beam_key(float d, uint32_t node) {
     return (static_cast<unsigned long long>(f32_orderable(d)) << 32) | (static_cast<unsigned long long>(node) << 1);
 }
 
+// Warp-wide argmax (MAX) / argmin of 63-bit pool values (orderable distance << 31 | node) with their indices, on
+// the hardware reduction unit (redux.sync, 32-bit): distance word first, node word among the ties, then one
+// ballot + shuffle for the index — ~8 instructions instead of a 5-round 64-bit shuffle butterfly (~40).
+// Lanes without a value pass 0 (MAX) / ~0 (min) and index -1.
+template <bool MAX>
+__device__ __forceinline__ void warp_arg63(unsigned long long& v, int& idx) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t hi = static_cast<uint32_t>(v >> 31), lo = static_cast<uint32_t>(v) & 0x7FFFFFFFu;
+    const uint32_t mh = MAX ? __reduce_max_sync(FULL, hi) : __reduce_min_sync(FULL, hi);
+    const bool c1 = hi == mh;
+    const uint32_t ml = MAX ? __reduce_max_sync(FULL, c1 ? lo : 0u) : __reduce_min_sync(FULL, c1 ? lo : 0xFFFFFFFFu);
+    const unsigned b = __ballot_sync(FULL, c1 && lo == ml);
+    const int src = __ffs(b) - 1;
+    v = (static_cast<unsigned long long>(mh) << 31) | ml;
+    idx = __shfl_sync(FULL, idx, src);
+}
+
 // Result phase shared by the search kernels: s_beam[0..size) holds the pool sorted ascending by (distance, node).
 // Construction mode hands the whole beam to the neighbour selection; search mode takes the first k non-deleted
 // entries (hnsw.rs:472-475), re-scores them in f64 with the reference's Flat formulae and orders them.
 template <int METRIC, bool BUILD, int THREADS>
 __device__ __forceinline__ void finish_query(const HnswParams& p, uint32_t qi, const unsigned long long* s_beam,
-                                             int size_in, const float4* s_q, double* s_ex, uint32_t* s_rid,
+                                             int size_in, const float* q, double* s_ex, uint32_t* s_rid,
                                              double* s_qs, unsigned long long n_eval) {
     __shared__ int s_rcount;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,7 +136,6 @@ __device__ __forceinline__ void finish_query(const HnswParams& p, uint32_t qi, c
     for (int t = tid; t < rc; t += THREADS) {
         const uint32_t node = s_rid[t];
         const float* row = p.rows + static_cast<size_t>(node) * p.pitch;
-        const float* q = reinterpret_cast<const float*>(s_q);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         for (uint32_t j = 0; j < p.dim; ++j) {
             const double x = static_cast<double>(row[j]), y = static_cast<double>(q[j]);

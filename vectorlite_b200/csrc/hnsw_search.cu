@@ -32,20 +32,23 @@ template <int METRIC, int NCH, bool BUILD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
     constexpr int THREADS = WARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: q[pitch] f32 | beam[ef_cap] u64 | vis[vis_mask+1] u32
+    // layout: [q[pitch] f32 — only when the query is not register-resident (NCH == 0)] | beam[beam_cap] u64 |
+    //         vis[vis_mask+1] u16 | candidate keys[cand_cap] u64 | candidate ids[cand_cap] u32
+    // Everything is sized by the host (size_pool): a narrow beam at M0 = 32 needs ~6.5–10.5 KB, so 21–32 one-warp
+    // CTAs are resident per SM.
     float4* s_q = reinterpret_cast<float4*>(smem_raw);
-    unsigned long long* s_beam = reinterpret_cast<unsigned long long*>(smem_raw + static_cast<size_t>(p.pitch) * 4);
+    unsigned long long* s_beam = reinterpret_cast<unsigned long long*>(smem_raw + (NCH == 0 ? static_cast<size_t>(p.pitch) * 4 : 0));
     uint16_t* s_vis = reinterpret_cast<uint16_t*>(s_beam + p.beam_cap);
-    __shared__ unsigned long long s_ck[HN_MAX_CAND];  // candidate keys of this step
-    __shared__ uint32_t s_cid[HN_MAX_CAND];
+    unsigned long long* s_ck = reinterpret_cast<unsigned long long*>(s_vis + p.vis_mask + 1);   // candidate keys of this step
+    uint32_t* s_cid = reinterpret_cast<uint32_t*>(s_ck + p.cand_cap);
     __shared__ int s_nc, s_size, s_done;
     __shared__ float s_invq;
     // result staging reuses the traversal's scratch (dead by then): exact scores over the candidate keys,
-    // result nodes over the candidate ids, quantised scores (reference score mode) over the visited cache
-    static_assert(HN_K_MAX <= HN_MAX_CAND, "result arrays alias the candidate arrays");
+    // result nodes over the candidate ids (cand_cap >= k), quantised scores (reference score mode) over the
+    // visited cache (>= 4 KB)
     double* s_ex = reinterpret_cast<double*>(s_ck);
     uint32_t* s_rid = s_cid;
-    double* s_qs = reinterpret_cast<double*>(s_vis);   // >= 2048 tags x 2 B... needs HN_K_MAX x 8 B: see size_pool
+    double* s_qs = reinterpret_cast<double*>(s_vis);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t qi = blockIdx.x;
@@ -56,20 +59,29 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
     const int top_level = BUILD ? (p.entry_only ? p.stop_level : p.g.max_level) : p.g.max_level;
     const int bottom_level = BUILD ? p.stop_level : 0;
 
-    for (uint32_t i = tid; i < pitch4; i += THREADS) s_q[i] = q4[i];
+    if (NCH == 0)
+        for (uint32_t i = tid; i < pitch4; i += THREADS) s_q[i] = q4[i];
     for (uint32_t i = tid; i <= p.vis_mask; i += THREADS) s_vis[i] = 0u;
-    __syncthreads();
     float4 qreg[NCH > 0 ? NCH : 1];
     if (NCH > 0) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) qreg[c] = s_q[c * 32 + lane];
+        for (int c = 0; c < NCH; ++c) qreg[c] = __ldg(q4 + c * 32 + lane);
     }
+    __syncthreads();
     const uint32_t nch = NCH > 0 ? NCH : (pitch4 + 31) / 32;
     if (METRIC == COSINE && warp == 0) {  // 1/‖q‖ (fp32 is enough for traversal)
         float a = 0.f;
-        for (uint32_t i = lane; i < pitch4; i += 32) {
-            const float4 v = s_q[i];
-            a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (NCH > 0) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float4 v = qreg[c];
+                a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+        } else {
+            for (uint32_t i = lane; i < pitch4; i += 32) {
+                const float4 v = s_q[i];
+                a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
@@ -131,12 +143,7 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             const unsigned long long kk = s_beam[i] >> 1;
             if (kk >= w) { w = kk; wi = i; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ow = __shfl_xor_sync(0xFFFFFFFFu, w, o);
-            const int oi = __shfl_xor_sync(0xFFFFFFFFu, wi, o);
-            if (ow > w || (ow == w && oi > wi)) { w = ow; wi = oi; }
-        }
+        warp_arg63<true>(w, wi);
         if (lane == 0) {
             s_worst = size == static_cast<int>(ef) ? w : ~0ull;
             s_worst_idx = wi;
@@ -175,12 +182,7 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
                         const unsigned long long kk = s_beam[i];
                         if (!(kk & 1ull) && (kk >> 1) < best) { best = kk >> 1; bi = i; }
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
-                        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-                        if (ob < best) { best = ob; bi = oi; }
-                    }
+                    warp_arg63<false>(best, bi);
                     if (bi < 0) break;
                     ++picked;
                     const uint32_t node = static_cast<uint32_t>(best) & 0x7FFFFFFFu;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             }
     }
 
-    finish_query<METRIC, BUILD, THREADS>(p, qi, s_beam, s_size, s_q, s_ex, s_rid, s_qs, n_eval);
+    finish_query<METRIC, BUILD, THREADS>(p, qi, s_beam, s_size, reinterpret_cast<const float*>(q4), s_ex, s_rid, s_qs, n_eval);
 }
 
 template <int METRIC, bool BUILD, int WARPS>
@@ -328,21 +330,30 @@ static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStre
 }
 
 // beam / visited-cache sizing shared by search and construction; returns the dynamic smem bytes
-static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t pitch) {
+static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg, uint32_t k, uint32_t pitch) {
+    const bool query_in_smem = pitch != 384;   // launch_warps: pitch 384 runs the register-resident (NCH = 3) kernels
     p.ef = W;
     uint32_t bcap = 64;
     while (bcap < p.ef) bcap <<= 1;
     p.beam_cap = bcap;
     // visited tag cache (16-bit tags): ~2 slots per expected evaluation (~W·M0/2 fresh nodes), 2K..32K entries
-    // wide beams are occupancy-bound by the cache's shared memory: halve it there (a lost tag only costs a
-    // re-evaluation), keep it roomy for narrow beams where re-evaluations dominate
-    uint32_t vis_div = p.ef >= 256 ? 2 : 1;
+    // The kernel is occupancy-bound by shared memory (one-warp CTAs, 32 per SM at <= 7 KB): a cache of ~ef·M0/2
+    // tags (/4 for wide beams) loses a few tags — each costs one re-evaluation — but keeps more queries resident
+    // (measured: profiles/r01_hnsw_tune.jsonl, vis_div rows)
+    uint32_t vis_div = p.ef >= 256 ? 4 : 2;
     if (const char* e = std::getenv("VL_HNSW_VIS_DIV")) vis_div = static_cast<uint32_t>(std::max(1, atoi(e)));
     const uint32_t want = p.ef * M0 / vis_div;
     uint32_t cap = 2048;   // >= HN_K_MAX·8 B: the quantised-score staging aliases the cache
     while (cap < want && cap < 32768) cap <<= 1;
     p.vis_mask = cap - 1;
-    return static_cast<size_t>(pitch) * 4 + static_cast<size_t>(bcap) * 8 + static_cast<size_t>(cap) * 2;
+    // candidates of one step: up to HN_MAX_EXPAND expanded entries x degree; the arrays also stage the results
+    const uint32_t expand = p.ef >= 64 ? HN_MAX_EXPAND : (p.ef >= 32 ? 2 : 1);
+    uint32_t cc = expand * max_deg;
+    if (cc < k) cc = k;
+    if (cc < 8) cc = 8;
+    p.cand_cap = (cc + 7u) & ~7u;
+    return (query_in_smem ? static_cast<size_t>(pitch) * 4 : 0) + static_cast<size_t>(bcap) * 8 +
+           static_cast<size_t>(cap) * 2 + static_cast<size_t>(p.cand_cap) * 12;
 }
 
 // construction-time search (hnsw_build.cu): node order[i]'s row is query i; greedy descent from the entry
@@ -363,7 +374,7 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
     p.out_ids = nullptr; p.out_scores = nullptr; p.out_counts = d_out_counts; p.visited = nullptr;
     p.order = d_order; p.stop_level = level; p.entry_only = entry_only ? 1u : 0u;
     p.out_keys = d_out_keys; p.out_stride = out_stride;
-    const size_t smem = size_pool(p, ef, level == 0 ? g.M0 : g.M, pitch);
+    const size_t smem = size_pool(p, ef, level == 0 ? g.M0 : g.M, std::max(g.M, g.M0), 0, pitch);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, true>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN, true>(p, nq, smem, stream);
@@ -397,7 +408,7 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.out_counts = d_out_counts;
     p.visited = d_visited;
     p.score_mode = score_mode;
-    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, pitch);
+    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, false>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN, false>(p, nq, smem, stream);
