@@ -310,25 +310,7 @@ int hnsw_build_device(HnswState* s, const float* d_rows, uint32_t pitch, cudaStr
     for (uint32_t i = 0; i < n; ++i)
         if (s->level[i] > max_level) { max_level = s->level[i]; entry = i; }
     // ---- device graph arrays (same buffers the search uses) ------------------------------------------
-    auto grow = [](auto*& p, size_t& cap, size_t need) {
-        using T = std::remove_reference_t<decltype(*p)>;
-        if (p && need <= cap) return true;
-        cudaFree(p);
-        p = nullptr;
-        const size_t nc = need + need / 4 + 64;
-        if (cudaMalloc(&p, nc * sizeof(T)) != cudaSuccess) return false;
-        cap = nc;
-        return true;
-    };
-    size_t cap;
-    cap = s->d_n_cap; if (!grow(s->d_adj0, cap, static_cast<size_t>(n) * s->M0)) return 7;
-    cap = s->d_n_cap; if (!grow(s->d_upper_off, cap, n)) return 7;
-    cap = s->d_n_cap; if (!grow(s->d_level, cap, n)) return 7;
-    cap = s->d_n_cap; if (!grow(s->d_deleted, cap, n)) return 7;
-    cap = s->d_n_cap; if (!grow(s->d_ids, cap, n)) return 7;
-    cap = s->d_n_cap; if (!grow(s->d_inv_norm, cap, n)) return 7;
-    s->d_n_cap = 0;
-    if (!grow(s->d_upper, s->d_upper_cap, std::max<size_t>(s->upper.size(), 1))) return 7;
+    if (int st = hnsw_reserve_device(s, n)) return st;
     cudaMemsetAsync(s->d_adj0, 0xFF, static_cast<size_t>(n) * s->M0 * 4, stream);
     if (!s->upper.empty()) cudaMemsetAsync(s->d_upper, 0xFF, s->upper.size() * 4, stream);
     cudaMemcpyAsync(s->d_upper_off, s->upper_off.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, stream);

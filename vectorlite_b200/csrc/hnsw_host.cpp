@@ -444,19 +444,29 @@ uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t*
     return written;
 }
 
+// device graph arrays for n nodes (capacity tracked in nodes / upper slots; grown geometrically)
+int hnsw_reserve_device(HnswState* s, size_t n) {
+    if (n > s->d_n_cap) {
+        const size_t nc = n + n / 4 + 64;
+        cudaFree(s->d_adj0); cudaFree(s->d_upper_off); cudaFree(s->d_level); cudaFree(s->d_deleted);
+        cudaFree(s->d_ids); cudaFree(s->d_inv_norm);
+        s->d_adj0 = s->d_upper_off = nullptr; s->d_level = s->d_deleted = nullptr; s->d_ids = nullptr; s->d_inv_norm = nullptr;
+        s->d_n_cap = 0;
+        if (cudaMalloc(&s->d_adj0, nc * s->M0 * 4) != cudaSuccess || cudaMalloc(&s->d_upper_off, nc * 4) != cudaSuccess ||
+            cudaMalloc(&s->d_level, nc) != cudaSuccess || cudaMalloc(&s->d_deleted, nc) != cudaSuccess ||
+            cudaMalloc(&s->d_ids, nc * 8) != cudaSuccess || cudaMalloc(&s->d_inv_norm, nc * 4) != cudaSuccess)
+            return 7;
+        s->d_n_cap = nc;
+    }
+    if (!dev_grow(s->d_upper, s->d_upper_cap, std::max<size_t>(s->upper.size(), 1))) return 7;
+    return 0;
+}
+
 int hnsw_upload(HnswState* s, cudaStream_t stream) {
     const size_t n = s->level.size();
     if (n == 0) return 0;
     if (s->dirty) {
-        size_t cap;
-        cap = s->d_n_cap; if (!dev_grow(s->d_adj0, cap, n * s->M0)) return 7;
-        cap = s->d_n_cap; if (!dev_grow(s->d_upper_off, cap, n)) return 7;
-        cap = s->d_n_cap; if (!dev_grow(s->d_level, cap, n)) return 7;
-        cap = s->d_n_cap; if (!dev_grow(s->d_deleted, cap, n)) return 7;
-        cap = s->d_n_cap; if (!dev_grow(s->d_ids, cap, n)) return 7;
-        cap = s->d_n_cap; if (!dev_grow(s->d_inv_norm, cap, n)) return 7;
-        s->d_n_cap = 0;  // always re-check: arrays have different element counts
-        if (!dev_grow(s->d_upper, s->d_upper_cap, std::max<size_t>(s->upper.size(), 1))) return 7;
+        if (int st = hnsw_reserve_device(s, n)) return st;
         cudaMemcpyAsync(s->d_adj0, s->adj0.data(), n * s->M0 * 4, cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(s->d_upper_off, s->upper_off.data(), n * 4, cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(s->d_level, s->level.data(), n, cudaMemcpyHostToDevice, stream);

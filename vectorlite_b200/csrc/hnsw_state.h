@@ -73,6 +73,8 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
                              const uint32_t* d_order, uint32_t nq, int level, bool entry_only, uint32_t ef,
                              unsigned long long* d_out_keys, uint32_t out_stride, uint32_t* d_out_counts,
                              cudaStream_t stream);
+// device graph arrays for n nodes (hnsw_host.cpp)
+int hnsw_reserve_device(HnswState* s, size_t n);
 // hnsw_build.cu: build the whole (empty) graph of `s` on the device; adjacency is copied back to the host
 int hnsw_build_device(HnswState* s, const float* d_rows, uint32_t pitch, cudaStream_t stream, uint64_t* launches);
 
