@@ -37,6 +37,7 @@ import numpy as np  # noqa: E402
 DIM = 384
 METRIC_NAMES = {"cosine": 0, "euclidean": 1, "manhattan": 2, "dot": 3}
 QUERIES_PER_STEP = 64
+E2E_CALLERS = 4          # concurrent host threads calling vl_index_search in the e2e leg (N = 1)
 
 
 def load_peaks():
@@ -161,6 +162,13 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
         hit = sum(len(set(map(int, gi[i, :gc[i]])) & set(map(int, truth[i]))) for i in range(nq))
         sweep[str(ef)] = {"recall_at_10": hit / (nq * k), "qps_e2e": nq / dt,
                           "visited_per_query": h.stats()["hnsw_visited"] / nq, "beam": 8 * (ef or k)}
+    # one query per call at the reference's own setting (ef = k): the lone-client latency of the host API
+    for i in range(20):
+        h.search_batch(queries[i:i + 1], k, metric, 0)
+    t0 = time.perf_counter()
+    for i in range(200):
+        h.search_batch(queries[i:i + 1], k, metric, 0)
+    single_us = (time.perf_counter() - t0) / 200 * 1e6
     ref = {}
     for name in ("hnsw_reference_recall_n20000_c1024_M16.json", "hnsw_reference_recall_n20000_c0_M16.json",
                  "hnsw_reference_recall_n50000_c1024_M16.json"):
@@ -172,7 +180,7 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
     return {"rows": n, "dim": DIM, "data": f"synthetic {clusters}-centre mixture, unit norm", "M": 16, "M0": 32,
             "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "builder": build_info,
             "host_threads": cpu_threads(),
-            "sweep": sweep,
+            "sweep": sweep, "single_query_latency_us_ef_k": single_us,
             "reference_restatement_recall": ref,
             "note": "reference recall = oracle restatement of crate hnsw 0.11 + u64-quantised functors at "
                     "efC=400 on smaller N (CPU build is single-threaded); parity at equal parameters is "
@@ -360,26 +368,49 @@ def main():
             traffic = None
 
     # ---- end to end through the host API (host buffers in, host results out) -----------------------
+    # One caller at a time (a lone client), and — on a single shard — E2E_CALLERS concurrent callers on the same
+    # handle, which is how the reference serves searches (tokio workers under a read lock, client.rs:398) and how
+    # the reference arm is timed (one query per host thread): the host-side part of one search overlaps the scan
+    # of another.  The sharded exchange is ordered per handle, so N > 1 keeps a single caller per rank.
+    def one_search(qi):
+        if world == 1:
+            idx.local.search_batch(queries[qi:qi + 1], k, metric)
+        else:
+            idx.search(queries[qi:qi + 1], k, metric)
+
     def step_e2e():
         for qi in range(QUERIES_PER_STEP):
-            if world == 1:
-                idx.local.search_batch(queries[qi:qi + 1], k, metric)
-            else:
-                idx.search(queries[qi:qi + 1], k, metric)
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
+            one_search(qi)
+
+    def time_e2e(step_fn):
+        for _ in range(2):
+            step_fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return e2e_steps * QUERIES_PER_STEP / dt * world
+
     e2e_steps = max(2, args.steps // 4)
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e_qps = e2e_steps * QUERIES_PER_STEP / e2e_dt * world
+    e2e_single = time_e2e(step_e2e)
+    e2e_qps, e2e_callers = e2e_single, 1
+    if world == 1:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=E2E_CALLERS)
+
+        def step_e2e_concurrent():
+            def work(c):
+                for qi in range(c, QUERIES_PER_STEP, E2E_CALLERS):
+                    one_search(qi)
+            list(pool.map(work, range(E2E_CALLERS)))
+        e2e_qps, e2e_callers = time_e2e(step_e2e_concurrent), E2E_CALLERS
+        pool.shutdown()
 
     # ---- extras: other metrics, batched (B=1024) tensor-core / CUDA-core pipelines ---------------------
     extras = {}
@@ -469,7 +500,9 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s x 1M-row shards",
                     "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
-                    "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8)},
+                    "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8),
+                    "callers": e2e_callers, "single_caller_value": e2e_single,
+                    "api": "vl_index_search (host buffers in, host results out), one query per call"},
             "gpu_launches": int(launches + (merges if (world > 1 and idx.exchange == "nccl") else 0)),
             "clocks": clocks,
             "extras": extras,

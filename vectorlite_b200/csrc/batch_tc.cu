@@ -135,7 +135,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* s_a = base;
     unsigned char* s_b = base + SMEM_A;
-    float* s_xn = reinterpret_cast<float*>(base + SMEM_A + SMEM_B);
+    // (SMEM_XN bytes after the B ring are reserved: the L2 epilogue keeps its squared norms in registers)
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SMEM_A + SMEM_B + SMEM_XN);
     // bars: [0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, then a_full, tmem_full[2], tmem_empty[2]
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE), bar_a = smem_u32(bars + 2 * NSTAGE);
@@ -262,29 +262,30 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         };
         if (active) {
             uint32_t buf = 0, tphase = 0;
-            float xn_pref = 0.f;
-            if (METRIC == EUCLIDEAN) {
-                const uint32_t r0 = p.row_lo + t0 * BN + etid;
-                xn_pref = r0 < p.row_hi ? __ldg(p.sq_norm + r0) : 0.f;
-            }
+            // L2: every warp keeps the ‖x‖² of its 128 columns in registers (lane l holds columns cbase + 32j + l,
+            // j = 0..3), loaded one tile ahead — no shared-memory staging and no barrier between epilogue warps
+            float xr[4] = {0.f, 0.f, 0.f, 0.f}, xp[4] = {0.f, 0.f, 0.f, 0.f};
+            auto load_xn = [&](uint32_t tile, float (&dst)[4]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t r = p.row_lo + tile * BN + cbase + 32 * j + lane;
+                    dst[j] = (tile < p.tiles && r < p.row_hi) ? __ldg(p.sq_norm + r) : 0.f;
+                }
+            };
+            if (METRIC == EUCLIDEAN) load_xn(t0, xp);
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
                 const uint32_t row0 = p.row_lo + t * BN;
                 if (METRIC == EUCLIDEAN) {
-                    // stage ‖x‖² of the tile's rows (one per epilogue thread; every warp reads its 128 columns).
-                    // The value was loaded one tile ahead, so its L2/HBM latency is off the critical path.
-                    static_assert(EPI_THREADS == BN, "one squared norm per epilogue thread");
-                    s_xn[buf * BN + etid] = xn_pref;
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                    const uint32_t rn = row0 + tstride * BN + etid;
-                    xn_pref = (t + tstride < p.tiles && rn < p.row_hi) ? __ldg(p.sq_norm + rn) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xr[j] = xp[j];
+                    load_xn(t + tstride, xp);
                 }
                 mbar_wait(bar_tfull + 8 * buf, tphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + buf * TMEM_BUF_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
-                const float* xn = s_xn + buf * BN;
                 // one 32-column chunk: branch-free survivor mask (2 instructions per score), then a
                 // compact loop over the (rare) set bits — keeps the hot loop inside the instruction cache
-                auto process = [&](const uint32_t (&v)[32], int c0) {
+                auto process = [&](const uint32_t (&v)[32], int c0, float xn_lane) {   // xn_lane: ‖x‖² of column c0 + lane
                     if (p.direct) {
                         // stage 0 keeps every score: transpose 32 queries × 16 columns through this warp's 2 KB of
                         // the (idle) survivor queue so that each half-warp stores 16 consecutive keys of ONE
@@ -295,7 +296,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 float s = __uint_as_float(v[half * 16 + i]);
-                                if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + half * 16 + i]) - qn;
+                                if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -__shfl_sync(0xFFFFFFFFu, xn_lane, half * 16 + i)) - qn;
                                 if (!isfinite(s)) nonfinite = true;
                                 st[lane * 16 + (i ^ (lane & 15))] = s;
                             }
@@ -314,13 +315,20 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         }
                         return;
                     }
+                    // L2: s = 2·acc − ‖x‖² >= τ' needs acc >= (τ' + ‖x‖²)/2; with the chunk's SMALLEST ‖x‖² (one
+                    // redux per 32 columns; ‖x‖² >= 0 so the uint order is the float order) that is a necessary
+                    // condition on acc alone — the hot loop is the same 2 instructions per score as cosine / dot and
+                    // the exact predicate is re-applied to the (rare) survivors.  The margin keeps the filter
+                    // conservative under rounding.
+                    float thr = tau;
+                    if (METRIC == EUCLIDEAN) {
+                        const float xm = __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, __float_as_uint(xn_lane)));
+                        thr = 0.5f * (tau + xm) - (4e-7f * (fabsf(tau) + xm) + 1e-30f);
+                    }
                     uint32_t m4[4] = {0u, 0u, 0u, 0u};   // independent partial masks: no 32-long dependent chain
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float s = __uint_as_float(v[i]);
-                        if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]);
-                        m4[i & 3] |= !(s < tau) ? (1u << i) : 0u;   // s >= tau, or NaN
-                    }
+                    for (int i = 0; i < 32; ++i)
+                        m4[i & 3] |= !(__uint_as_float(v[i]) < thr) ? (1u << i) : 0u;   // acc >= thr, or NaN
                     uint32_t mask = (m4[0] | m4[1]) | (m4[2] | m4[3]);
                     while (mask) {
                         const int i = __ffs(mask) - 1;
@@ -328,7 +336,11 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         const uint32_t r = row0 + c0 + i;
                         if (qvalid && r < p.row_hi) {
                             float s = __uint_as_float(select32(v, i));
-                            if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -xn[c0 + i]) - qn;   // −‖x−q‖²
+                            if (METRIC == EUCLIDEAN) {
+                                s = fmaf(2.f, s, -__ldg(p.sq_norm + r));   // rare path: L1/L2 hit
+                                if (s < tau) continue;              // passed the chunk-minimum filter only
+                                s -= qn;                            // −‖x−q‖²
+                            }
                             if (!isfinite(s)) nonfinite = true;
                             my_q[nloc * EPI_THREADS] = make_key(s, r);
                             if (++nloc == QCAP) flush();   // rare: a lane filled its queue inside one chunk
@@ -344,11 +356,12 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 tmem_ld_wait();
 #pragma unroll 1
                 for (int c0 = cbase; c0 < cbase + BN / 2; c0 += 64) {   // two chunks per iteration, loads double buffered
+                    const bool first = c0 == cbase;
                     tmem_ld32(tbase + c0 + 32, vb);
-                    process(va, c0);
+                    process(va, c0, first ? xr[0] : xr[2]);
                     tmem_ld_wait();
                     if (c0 + 64 < cbase + BN / 2) tmem_ld32(tbase + c0 + 64, va);
-                    process(vb, c0 + 32);
+                    process(vb, c0 + 32, first ? xr[1] : xr[3]);
                     tmem_ld_wait();
                 }
                 tc_fence_before();
