@@ -351,21 +351,36 @@ def main():
     value = qps_global * world
 
     # ---- dominant-kernel duration inside the same timed region (events around each scan launch) ---
-    idx.local.set_profiling(True)
-    ms_prof = timed(step_device, max(1, min(args.steps, 1024 // QUERIES_PER_STEP)))
-    scan_ms, scan_n = idx.local.profile_read()
-    idx.local.set_profiling(False)
-    scan_ms_avg = scan_ms / max(scan_n, 1)
-    algo_bytes = n_shard * DIM * 4 + (n_shard * 4 if metric == vl.SimilarityMetric.Cosine else 0) + DIM * 4
+    def scan_roofline(metric_):
+        """(kernel name, bytes/element, algorithmic bytes per launch, avg kernel ms, launches, traffic) of the
+        single-query scan as configured: events bracket every scan launch of a timed pass."""
+        b0 = idx.local.stats()["bf16_scans"]
+        idx.local.set_profiling(True)
+        timed(step_device if metric_ == metric else (lambda: [idx.search_device(d_queries[qi:qi + 1], k, metric_)
+                                                              for qi in range(QUERIES_PER_STEP)]),
+              max(1, min(args.steps, 1024 // QUERIES_PER_STEP)))
+        scan_ms, scan_n = idx.local.profile_read()
+        idx.local.set_profiling(False)
+        bf16 = idx.local.stats()["bf16_scans"] > b0
+        cos, l2 = metric_ == vl.SimilarityMetric.Cosine, metric_ == vl.SimilarityMetric.Euclidean
+        if bf16:   # bf16 mirror (cosine: pre-normalised rows, no norm array; L2: + fp32 ‖row‖²)
+            ab = n_shard * DIM * 2 + (n_shard * 4 if l2 else 0) + DIM * 4
+            name, tfile = "flat_scan_bf16_kernel", "r01_flat_scan_bf16_traffic.json"
+        else:
+            ab = n_shard * DIM * 4 + (n_shard * 4 if cos else 0) + DIM * 4
+            name, tfile = "flat_scan_kernel", "r01_flat_scan_traffic.json"
+        tr = None
+        tp = os.path.join(ROOT, "profiles", tfile)
+        if os.path.exists(tp):
+            try:
+                tr = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                tr = None
+        return name, (2 if bf16 else 4), ab, scan_ms / max(scan_n, 1), scan_n, tr
+
+    scan_kernel, scan_elem_bytes, algo_bytes, scan_ms_avg, scan_n, traffic = scan_roofline(metric)
     peak, peak_src = load_peaks()
     achieved = algo_bytes / (scan_ms_avg * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_flat_scan_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
 
     # ---- end to end through the host API (host buffers in, host results out) -----------------------
     # One caller at a time (a lone client), and — on a single shard — E2E_CALLERS concurrent callers on the same
@@ -424,6 +439,15 @@ def main():
             f()
             t_ms = timed(f, 5)
             extras[f"flat_b1_{name}_qps"] = 5 * QUERIES_PER_STEP / (t_ms * 1e-3)
+        # the same single-query search with scans pinned to the fp32 arena (VL_MODE_FP32): the 4 B/element headline
+        idx.local.set_mode(vl.Mode.Fp32)
+        f32_name, _, f32_bytes, f32_ms, f32_n, f32_tr = scan_roofline(metric)
+        t_ms = timed(step_device, 5)
+        extras["flat_b1_cosine_fp32_scan" if args.metric == "cosine" else f"flat_b1_{args.metric}_fp32_scan"] = {
+            "qps": 5 * QUERIES_PER_STEP / (t_ms * 1e-3) * world, "kernel": f32_name, "kernel_ms": f32_ms,
+            "achieved_gbs": f32_bytes / (f32_ms * 1e-3) / 1e9, "frac": f32_bytes / (f32_ms * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_launch": f32_bytes, "traffic": f32_tr}
+        idx.local.set_mode(vl.Mode.Auto)
         B = 1024
         bq = oracle.synth_rows(43, 1000, B, DIM)
         d_bq = torch.from_numpy(bq).to(dev)
@@ -480,7 +504,8 @@ def main():
         line = {
             "metric": "flat_1m_384d_k10_qps", "value": value, "unit": "queries/s x 1M-row shards",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": ("bf16 rows x f32 query, f32 accumulate; f64 rescore" if scan_elem_bytes == 2 else "f32; f64 rescore"),
             "data": "synthetic",
             "config": {"workload": f"flat {n_shard}x{DIM} f32 per GPU shard, {args.metric}, k={k}, B=1 "
                                    f"({QUERIES_PER_STEP} single-query searches per step)",
@@ -490,12 +515,16 @@ def main():
                                        else "NCCL all-gather + merge kernel")),
                        "l2": "inputs larger than L2 (1.536 GB store vs 126 MB)",
                        "pipelining": "programmatic dependent launch between consecutive searches", "exactness":
-                       "ids == oracle, f64 scores bit-identical (fp32 scan + fp64 rescore + certificate)"},
+                       "ids == oracle, f64 scores bit-identical (approximate scan over the "
+                       + ("bf16 mirror of the rows" if scan_elem_bytes == 2 else "fp32 arena")
+                       + " + f64 rescore of the over-selected candidates + optimality certificate)",
+                       "scanned_copy": ("bf16 mirror, 2 B/element (SURVEY §8d); the fp32-arena scan is reported in "
+                                        "extras.flat_b1_cosine_fp32_scan") if scan_elem_bytes == 2 else "fp32 arena"},
             "global_qps": qps_global,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "flat_scan_kernel", "kernel_ms": scan_ms_avg, "launches_timed": scan_n,
-                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel": scan_kernel, "kernel_ms": scan_ms_avg, "launches_timed": scan_n,
+                         "algorithmic_bytes_per_launch": algo_bytes, "scanned_copy_bytes_per_element": scan_elem_bytes,
                          "frac_of_nominal_8000": achieved / 8000.0},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s x 1M-row shards",

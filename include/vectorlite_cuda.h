@@ -63,6 +63,9 @@ typedef enum vl_index_type { VL_INDEX_FLAT = 0, VL_INDEX_HNSW = 1 } vl_index_typ
  *       summation order → optimality certificate; a query whose certificate fails is re-run on
  *       the EXACT path.  Both paths return identical, oracle-exact results.
  * EXACT: every row scored in f64 in reference order on the device, stable radix select. */
+/* AUTO: approximate scans may read the bf16 mirror of the rows (tensor-core batches; single-query scans at 384-d) —
+ * results stay bit-exact through the f64 rescore + certificate.  FP32: scans read the fp32 arena only.  EXACT: every
+ * row scored in f64. */
 typedef enum vl_mode { VL_MODE_AUTO = 0, VL_MODE_EXACT = 1, VL_MODE_FP32 = 2 } vl_mode;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
@@ -202,7 +205,8 @@ int vl_index_set_mode(vl_index* h, int mode);
 /* Row-sharded deployments: global storage position = base + local position. */
 int vl_index_set_pos_base(vl_index* h, uint64_t base);
 /* Counters since creation: [0] kernels launched, [1] searches served by the certified fast path,
- * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited. */
+ * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited,
+ * [6] single-query scans served from the bf16 mirror of the rows (AUTO mode, 384-d, cosine / dot / L2). */
 int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n);
 /* Pipelined device searches (flat, vl_index_search_device only).  When enabled, consecutive searches
  * enqueued on one stream overlap through programmatic dependent launch: the scan of search i+1

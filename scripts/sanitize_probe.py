@@ -1,4 +1,4 @@
-"""Small end-to-end pass over every kernel family, for compute-sanitizer (memcheck / racecheck / initcheck):
+"""Small end-to-end pass over every kernel family (a target for compute-sanitizer where that tool is available):
 flat single-query, batched CUDA-core and tensor-core pipelines (all metrics), exact path, HNSW device + host
 build, HNSW search (1-warp and 4-warp CTAs), reference score mode.  Checks results against the oracle."""
 import os, sys

@@ -476,6 +476,51 @@ def test_tensor_core_batched_path(vl, oracle_mod):
     assert np.array_equal(gi2, oi) and np.array_equal(gs2.view(np.uint64), os_.view(np.uint64))
 
 
+def test_bf16_mirror_single_query_scan(vl, oracle_mod):
+    """AUTO mode at 384-d: single-query cosine / dot / L2 scans read the bf16 mirror of the rows (half the HBM
+    bytes); the f64 rescore + bf16-bound certificate keep ids and scores bit-identical to the oracle.  A
+    certificate that cannot hold under the bf16 bound is retried on the fp32 scan, not on the exact path."""
+    n, dim, k = 30000, 384, 10
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    rows[777] = rows[5]                                   # an exact duplicate: positional tie-break
+    q = oracle_mod.synth_rows(43, 0, 6, dim)
+    q[2] = rows[5]
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    for metric in vl.SimilarityMetric:
+        before = idx.stats()
+        for j in range(q.shape[0]):
+            _check(vl, oracle_mod, idx, rows, None, q[j:j + 1], k, metric)
+        after = idx.stats()
+        used = after["bf16_scans"] - before["bf16_scans"]
+        assert (used == 0) if metric == vl.SimilarityMetric.Manhattan else (used >= q.shape[0]), (metric, used)
+        assert after["exact_queries"] == before["exact_queries"], metric
+    # FP32 mode: same answers, the mirror is not touched
+    idx.set_mode(vl.Mode.Fp32)
+    b = idx.stats()["bf16_scans"]
+    _check(vl, oracle_mod, idx, rows, None, q[:1], k, vl.SimilarityMetric.Cosine)
+    assert idx.stats()["bf16_scans"] == b
+    idx.set_mode(vl.Mode.Auto)
+    # delete shifts positions: the mirror is positional and must be rebuilt
+    idx.delete(3)
+    rows2 = np.delete(rows, 3, axis=0)
+    ids2 = np.delete(np.arange(n, dtype=np.uint64), 3)
+    _check(vl, oracle_mod, idx, rows2, ids2, q[:2], k, vl.SimilarityMetric.Cosine)
+    # near-ties below the bf16 bound (cosines within ~3e-3 of each other): bf16 certificate fails, fp32 retry certifies
+    base = oracle_mod.synth_rows(44, 0, 1, dim)[0]
+    rng = np.random.default_rng(5)
+    near = (base[None, :] + 1e-2 * rng.standard_normal((200, dim))).astype(np.float32)
+    far = oracle_mod.synth_rows(45, 0, 4000, dim)
+    rows3 = np.concatenate([far, near])
+    t = vl.FlatIndex(dim)
+    t.add_batch(np.arange(rows3.shape[0], dtype=np.uint64), rows3)
+    before = t.stats()
+    _check(vl, oracle_mod, t, rows3, None, base[None, :], k, vl.SimilarityMetric.Cosine)
+    after = t.stats()
+    assert after["bf16_scans"] > before["bf16_scans"]
+    assert after["exact_queries"] == before["exact_queries"], "the fp32 retry should certify these near-ties"
+
+
 def test_cpp_host_mirror(vl, tmp_path):
     """include/vectorlite.hpp (the C++ mirror of the reference interface) replays the reference's own
     flat / hnsw unit tests against the C ABI."""

@@ -40,7 +40,7 @@ static int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(_e));                                                \
     } while (0)
 
-enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_N = 8 };
+enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_N = 8 };
 
 namespace {
 
@@ -415,6 +415,53 @@ int run_exact_one(vl_index* h, Slot& s, const FlatView& v, const float* d_query,
     return VL_OK;
 }
 
+// Single-query scans read the bf16 mirror of the rows when one applies (AUTO mode, 384-d, cosine / dot / L2):
+// half the HBM bytes per query; the candidates are re-scored in f64 and certified with the bf16 bound exactly
+// as in the tensor-core batched path.  Brings the mirror up to date (lazily, like tc_prepare for batches) and
+// returns its pointers; `*mirror` stays null when the fp32 scan has to be used.
+static int single_query_mirror(vl_index* h, const FlatView& v, int metric, cudaStream_t stream, const void** mirror,
+                               const float** sq_norm) {
+    *mirror = nullptr;
+    *sq_norm = nullptr;
+    static const bool disabled = getenv("VL_DISABLE_BF16_SCAN") != nullptr;
+    if (disabled || h->mode != VL_MODE_AUTO || metric == VL_METRIC_MANHATTAN || v.pitch != 384) return VL_OK;
+    std::lock_guard<std::mutex> lk(h->tc_mu);
+    const bool cosine = metric == VL_METRIC_COSINE;
+    const uint64_t before = cosine ? h->tc.built_norm : h->tc.built_raw;
+    CU(tc_prepare(&h->tc, v, h->cap, metric, 1, stream));
+    if (!h->tc.usable || h->tc.KP != 384) return VL_OK;
+    const uint64_t after = cosine ? h->tc.built_norm : h->tc.built_raw;
+    if (after != before) CU(cudaStreamSynchronize(stream));   // other streams may scan the mirror next
+    *mirror = cosine ? h->tc.rows_norm : h->tc.rows_raw;
+    *sq_norm = h->tc.sq_norm;
+    return VL_OK;
+}
+
+// scan + finalize of up to NQ_CHUNK single queries (bf16 mirror when allowed and available, else the fp32 arena)
+static int launch_single_queries(vl_index* h, const FlatView& v, const float* dq, uint32_t m, uint32_t k, int metric,
+                                 const ScanWork& w, const SearchOut& out, bool pipelined, bool allow_bf16,
+                                 cudaStream_t stream, bool* used_bf16) {
+    const void* mirror = nullptr;
+    const float* sqn = nullptr;
+    if (allow_bf16) {
+        int st = single_query_mirror(h, v, metric, stream, &mirror, &sqn);
+        if (st) return st;
+    }
+    const bool prof = h->profiling && h->prof_n < h->prof_ev.size() / 2;
+    if (prof) CU(cudaEventRecord(h->prof_ev[2 * h->prof_n], stream));
+    if (mirror) CU(launch_flat_scan_bf16(v, mirror, sqn, dq, m, metric, w, pipelined, stream));
+    else CU(launch_flat_scan(v, dq, m, metric, w, pipelined, stream));
+    if (prof) {
+        CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
+        h->prof_n += 1;
+    }
+    CU(launch_flat_finalize(v, dq, m, k, metric, w, out, 1.0f, stream, mirror ? BatchTensor().tc_abs : 0.0));
+    h->stats[ST_LAUNCHES] += 2;
+    if (mirror) h->stats[ST_BF16_SCANS] += m;
+    if (used_bf16) *used_bf16 = mirror != nullptr;
+    return VL_OK;
+}
+
 int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
                 uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
     // flat.rs:99-104: the dimension is only checked when the index is non-empty
@@ -476,9 +523,19 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
                 zero_copy = true;
                 SearchOut hout{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
                 ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
-                CU(launch_flat_scan(v, s.d_q, m, metric, w, false, s.stream));
-                CU(launch_flat_finalize(v, s.d_q, m, k, metric, w, hout, 1.0f, s.stream));
-                h->stats[ST_LAUNCHES] += 2;
+                bool used_bf16 = false;
+                if ((st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, true, s.stream, &used_bf16)))
+                    return st;
+                if (used_bf16) {
+                    // a bf16 certificate that does not hold (top-k gaps below the bf16 bound) is retried on
+                    // the fp32 scan before anything falls back to the exact path
+                    CU(cudaStreamSynchronize(s.stream));
+                    bool retry = false;
+                    for (uint32_t q = 0; q < m; ++q) retry |= (s.h_flags[q] & FLAG_CERT_FAIL) != 0;
+                    if (retry && (st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, false, s.stream,
+                                                             nullptr)))
+                        return st;
+                }
             }
             if (!zero_copy) CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
@@ -823,15 +880,7 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         ScanWork w{s.cand, s.cand_count, s.cand_max, ctl, grid_x, Kp};
         const SearchOut out = out_at(q0);
         const float* dq = d_queries + static_cast<size_t>(q0) * h->pitch;
-        const bool prof = h->profiling && h->prof_n < h->prof_ev.size() / 2;
-        if (prof) CU(cudaEventRecord(h->prof_ev[2 * h->prof_n], stream));
-        CU(launch_flat_scan(v, dq, m, metric, w, h->pipelined, stream));
-        if (prof) {
-            CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
-            h->prof_n += 1;
-        }
-        CU(launch_flat_finalize(v, dq, m, k, metric, w, out, 1.0f, stream));
-        h->stats[ST_LAUNCHES] += 2;
+        if ((st = launch_single_queries(h, v, dq, m, k, metric, w, out, h->pipelined, true, stream, nullptr))) return st;
     }
     return VL_OK;
 }

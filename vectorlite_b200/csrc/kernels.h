@@ -69,10 +69,15 @@ struct SearchOut {         // device outputs, [nq][k]
 // publishing its candidates.  The caller guarantees the queries were not produced by that kernel.
 cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t nq, int metric,
                              const ScanWork& w, bool pipelined, cudaStream_t s);
+// the same scan over the index's bf16 mirror of the rows (384-d, cosine / dot / L2): half the HBM bytes per
+// query; scores in the tensor-core path's scan units, certified with its bf16 bound (finalize: tc_abs > 0)
+cudaError_t launch_flat_scan_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
+                                  uint32_t nq, int metric, const ScanWork& w, bool pipelined, cudaStream_t s);
 // merge per-CTA candidates, fp64 rescore in reference order, rank, certify (grid = nq)
+// tc_abs > 0: the candidates come from a bf16 scan, |approx − exact| <= tc_abs·‖x‖·‖q‖
 cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k,
                                  int metric, const ScanWork& w, const SearchOut& out, float eps_scale,
-                                 cudaStream_t s);
+                                 cudaStream_t s, double tc_abs = 0.0);
 size_t flat_scan_smem_bytes(uint32_t pitch);
 int flat_scan_max_grid_x(int device, uint32_t pitch);
 
