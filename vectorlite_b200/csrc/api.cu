@@ -58,6 +58,7 @@ struct Slot {  // one in-flight search: stream + scratch, all sized on demand
     uint32_t* cand_count = nullptr; size_t cc_cap = 0;
     uint64_t* cand_max = nullptr; size_t cm_cap = 0;
     QueryCtl* ctl = nullptr; size_t ctl_cap = 0;
+    uint64_t* early = nullptr; size_t early_cap = 0;   // [2][NQ_CHUNK][EARLY_STRIDE], zero between searches
     // outputs: ONE device block + ONE pinned mirror per call, carved as
     // [ids m*k u64][scores m*k f64][counts m u32][flags m u32] so a single D2H brings everything
     unsigned char* d_out = nullptr; unsigned char* h_out = nullptr; size_t out_bytes = 0;
@@ -104,6 +105,7 @@ struct vl_index {
     Slot dev_slot;               // used by vl_index_search_device (caller-ordered)
     cudaStream_t mut_stream = nullptr;
     int max_grid_x = 148 * 4;
+    int max_grid_x_bf16 = 148 * 2;
     std::atomic<uint64_t> stats[ST_N];
     // ---- profiling (roofline reports) ----
     bool pipelined = false;      // vl_index_set_pipelined: PDL overlap between consecutive device searches
@@ -144,6 +146,15 @@ int grow_dev(T*& p, size_t& cap, size_t need) {
     return VL_OK;
 }
 
+static int reserve_early(Slot& s, cudaStream_t stream) {
+    const size_t need = 2ull * NQ_CHUNK * EARLY_STRIDE;
+    if (s.early_cap >= need) return VL_OK;
+    int st = grow_dev(s.early, s.early_cap, need);
+    if (st) return st;
+    CU(cudaMemsetAsync(s.early, 0, s.early_cap * sizeof(uint64_t), stream));
+    return VL_OK;
+}
+
 int slot_reserve(vl_index* h, Slot& s, uint32_t nq, uint32_t k, int Kp, int grid_x) {
     int st;
     const size_t qf = static_cast<size_t>(nq) * h->pitch;
@@ -162,6 +173,7 @@ int slot_reserve(vl_index* h, Slot& s, uint32_t nq, uint32_t k, int Kp, int grid
         if ((st = grow_dev(s.ctl, s.ctl_cap, nq))) return st;
         CU(cudaMemsetAsync(s.ctl, 0, nq * sizeof(QueryCtl), s.stream));
     }
+    if ((st = reserve_early(s, s.stream))) return st;
     const size_t on = static_cast<size_t>(nq) * std::max<uint32_t>(k, 1);
     const size_t need = on * 16 + static_cast<size_t>(nq) * 8;
     if (need > s.out_bytes) {
@@ -195,7 +207,7 @@ int slot_reserve_batch(Slot& s, uint32_t nq, BatchWork* w) {
 }
 
 void slot_free(Slot& s) {
-    cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.cand_max); cudaFree(s.ctl);
+    cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.cand_max); cudaFree(s.ctl); cudaFree(s.early);
     cudaFree(s.d_out); cudaFreeHost(s.h_out);
     cudaFree(s.b_cand); cudaFree(s.b_count); cudaFree(s.b_tau); cudaFree(s.b_qflags);
     cudaFree(s.d_exact); cudaFree(s.d_exflags);
@@ -447,15 +459,22 @@ static int launch_single_queries(vl_index* h, const FlatView& v, const float* dq
         int st = single_query_mirror(h, v, metric, stream, &mirror, &sqn);
         if (st) return st;
     }
+    ScanWork ws = w;
+    if (mirror) {   // persistent grid of the bf16 kernel: one resident wave (scan and finalize must agree on it)
+        const uint32_t tiles = (v.n + 127) / 128;
+        ws.grid_x = static_cast<int>(std::min<uint32_t>(std::min<uint32_t>(tiles, static_cast<uint32_t>(h->max_grid_x_bf16)),
+                                                         static_cast<uint32_t>(w.grid_x)));
+        if (ws.grid_x < 1) ws.grid_x = 1;
+    }
     const bool prof = h->profiling && h->prof_n < h->prof_ev.size() / 2;
     if (prof) CU(cudaEventRecord(h->prof_ev[2 * h->prof_n], stream));
-    if (mirror) CU(launch_flat_scan_bf16(v, mirror, sqn, dq, m, metric, w, pipelined, stream));
-    else CU(launch_flat_scan(v, dq, m, metric, w, pipelined, stream));
+    if (mirror) CU(launch_flat_scan_bf16(v, mirror, sqn, dq, m, metric, ws, pipelined, stream));
+    else CU(launch_flat_scan(v, dq, m, metric, ws, pipelined, stream));
     if (prof) {
         CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
         h->prof_n += 1;
     }
-    CU(launch_flat_finalize(v, dq, m, k, metric, w, out, 1.0f, stream, mirror ? BatchTensor().tc_abs : 0.0));
+    CU(launch_flat_finalize(v, dq, m, k, metric, ws, out, 1.0f, stream, mirror ? BatchTensor().tc_abs : 0.0));
     h->stats[ST_LAUNCHES] += 2;
     if (mirror) h->stats[ST_BF16_SCANS] += m;
     if (used_bf16) *used_bf16 = mirror != nullptr;
@@ -523,6 +542,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
                 zero_copy = true;
                 SearchOut hout{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
                 ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
+                w.early = m <= NQ_CHUNK ? s.early : nullptr;
                 bool used_bf16 = false;
                 if ((st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, true, s.stream, &used_bf16)))
                     return st;
@@ -611,6 +631,7 @@ static int create_common(uint32_t dim, int device, vl_index** out, int type) {
         return fail(VL_ERR_CUDA, "device init failed: %s", msg);
     }
     h->max_grid_x = std::min(flat_scan_max_grid_x(device, h->pitch), SCAN_CAP);
+    h->max_grid_x_bf16 = std::min(flat_scan_bf16_max_grid_x(device), SCAN_CAP);
     *out = h;
     return VL_OK;
 }
@@ -875,9 +896,12 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         }
         // two control-block sets, alternated per launch: in pipelined mode the next scan starts
         // while the previous finalize (which re-arms its own set at the end) may still be running
-        QueryCtl* ctl = s.ctl + (h->dev_parity & 1) * NQ_CHUNK;
+        const uint32_t parity = h->dev_parity & 1;
+        QueryCtl* ctl = s.ctl + parity * NQ_CHUNK;
         h->dev_parity ^= 1;
+        if ((st = reserve_early(s, stream))) return st;
         ScanWork w{s.cand, s.cand_count, s.cand_max, ctl, grid_x, Kp};
+        w.early = s.early + static_cast<size_t>(parity) * NQ_CHUNK * EARLY_STRIDE;
         const SearchOut out = out_at(q0);
         const float* dq = d_queries + static_cast<size_t>(q0) * h->pitch;
         if ((st = launch_single_queries(h, v, dq, m, k, metric, w, out, h->pipelined, true, stream, nullptr))) return st;

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) flat_finalize_kernel(FinalizeP
     const uint32_t* ccount = p.cand_count + static_cast<size_t>(qi) * G;
     const uint64_t* cmax = p.cand_max + static_cast<size_t>(qi) * G;
     if (tid == 0) { s_overflow = 0; s_count = 0; s_tau1 = 0ull; s_nz = 0; }
+    if (p.early)   // the scan is complete: clear what it published so the slot is all-zero for its next user
+        for (int i = tid; i < G; i += FIN_THREADS) p.early[static_cast<size_t>(qi) * EARLY_STRIDE + i] = 0ull;
     __syncthreads();
     {
         int nz = 0;
@@ -172,6 +174,7 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
     p.n = v.n; p.dim = v.dim; p.pitch = v.pitch; p.k = k;
     p.metric = metric; p.Kp = w.Kp; p.grid_x = w.grid_x; p.CH = CH;
     p.cand = w.cand; p.cand_count = w.cand_count; p.cand_max = w.cand_max; p.ctl = w.ctl;
+    p.early = w.early;
     p.out_ids = out.ids; p.out_scores = out.scores; p.out_pos = out.pos;
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = eps_scale;

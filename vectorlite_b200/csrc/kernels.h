@@ -16,6 +16,7 @@ constexpr int SCAN_TILES_PER_CHECK = 4;   // CTA-wide barrier every 4 tiles
 constexpr int SCAN_LIMIT = SCAN_CAP - SCAN_TILES_PER_CHECK * SCAN_TILE_ROWS;  // 768
 constexpr int KP_MAX = 512;               // max over-selected candidates per query (K')
 constexpr int FIN_THREADS = 512;
+constexpr int EARLY_STRIDE = 1024;        // per-query slots of the scan's early grid-wide threshold exchange (>= grid_x)
 
 struct FlatView {          // device-resident flat store (one shard)
     const float* rows;     // [n][pitch] fp32, zero padded to pitch
@@ -36,6 +37,8 @@ struct ScanWork {          // per workspace slot
     QueryCtl* ctl;         // [nq]
     int grid_x;
     int Kp;
+    uint64_t* early = nullptr;  // [nq][EARLY_STRIDE] first-tile maxima, all zero between searches (the finalize
+                           // kernel clears what its scan published); nullptr disables the early threshold
 };
 
 // Peer-memory exchange of a row-sharded search (exchange.cu).  When G > 0 the kernel that writes a
@@ -80,6 +83,7 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
                                  cudaStream_t s, double tc_abs = 0.0);
 size_t flat_scan_smem_bytes(uint32_t pitch);
 int flat_scan_max_grid_x(int device, uint32_t pitch);
+int flat_scan_bf16_max_grid_x(int device);   // the bf16 kernel keeps 2 CTAs per SM resident (124 registers)
 
 // exact path: every row scored in f64 in reference order
 cudaError_t launch_exact_scores(const FlatView& v, const float* d_query, int metric, double* d_scores,

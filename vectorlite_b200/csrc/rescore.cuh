@@ -18,6 +18,7 @@ struct FinalizeParams {
     const uint32_t* cand_count;
     const uint64_t* cand_max;
     QueryCtl* ctl;
+    uint64_t* early = nullptr;   // [nq][EARLY_STRIDE] published by the scan; cleared by the finalize kernel
     uint64_t* out_ids;
     double* out_scores;
     uint64_t* out_pos;
