@@ -365,10 +365,10 @@ def main():
         cos, l2 = metric_ == vl.SimilarityMetric.Cosine, metric_ == vl.SimilarityMetric.Euclidean
         if bf16:   # bf16 mirror (cosine: pre-normalised rows, no norm array; L2: + fp32 ‖row‖²)
             ab = n_shard * DIM * 2 + (n_shard * 4 if l2 else 0) + DIM * 4
-            name, tfile = "flat_scan_bf16_kernel", "r01_flat_scan_bf16_traffic.json"
+            name, tfile = "flat_scan_kernel<METRIC,3,BF16=true> (bf16 mirror)", "r01_flat_scan_bf16_traffic.json"
         else:
             ab = n_shard * DIM * 4 + (n_shard * 4 if cos else 0) + DIM * 4
-            name, tfile = "flat_scan_kernel", "r01_flat_scan_traffic.json"
+            name, tfile = "flat_scan_kernel<METRIC,NCH,BF16=false> (fp32 arena)", "r01_flat_scan_traffic.json"
         tr = None
         tp = os.path.join(ROOT, "profiles", tfile)
         if os.path.exists(tp):

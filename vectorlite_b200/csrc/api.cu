@@ -45,6 +45,7 @@ enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HN
 namespace {
 
 constexpr uint32_t NQ_CHUNK = 32;  // queries per launch of the per-query scan
+constexpr uint32_t DEV_SETS = 4;   // control-block / early-threshold sets rotated by pipelined device searches
 constexpr uint32_t BATCH_MIN = 8;        // nq >= BATCH_MIN → batched tile pipeline
 constexpr uint32_t BATCH_CHUNK = 1024;   // queries per batched pass
 constexpr uint32_t BATCH_CAPQ = 4096;    // candidate slots per query
@@ -109,7 +110,7 @@ struct vl_index {
     std::atomic<uint64_t> stats[ST_N];
     // ---- profiling (roofline reports) ----
     bool pipelined = false;      // vl_index_set_pipelined: PDL overlap between consecutive device searches
-    uint32_t dev_parity = 0;     // ping-pong of the dev_slot control blocks
+    uint32_t dev_parity = 0;     // rotation of the dev_slot control-block sets (DEV_SETS)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // pairs
     size_t prof_n = 0;                  // pairs recorded since last read
@@ -147,7 +148,7 @@ int grow_dev(T*& p, size_t& cap, size_t need) {
 }
 
 static int reserve_early(Slot& s, cudaStream_t stream) {
-    const size_t need = 2ull * NQ_CHUNK * EARLY_STRIDE;
+    const size_t need = static_cast<size_t>(DEV_SETS) * NQ_CHUNK * EARLY_STRIDE;
     if (s.early_cap >= need) return VL_OK;
     int st = grow_dev(s.early, s.early_cap, need);
     if (st) return st;
@@ -890,15 +891,15 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         if ((st = grow_dev(s.cand, s.cand_cap, static_cast<size_t>(m) * grid_x * Kp))) return st;
         if ((st = grow_dev(s.cand_count, s.cc_cap, static_cast<size_t>(m) * grid_x))) return st;
         if ((st = grow_dev(s.cand_max, s.cm_cap, static_cast<size_t>(m) * grid_x))) return st;
-        if (s.ctl_cap < 2 * NQ_CHUNK) {
-            if ((st = grow_dev(s.ctl, s.ctl_cap, 2 * NQ_CHUNK))) return st;
-            CU(cudaMemsetAsync(s.ctl, 0, 2 * NQ_CHUNK * sizeof(QueryCtl), stream));
+        if (s.ctl_cap < DEV_SETS * NQ_CHUNK) {
+            if ((st = grow_dev(s.ctl, s.ctl_cap, DEV_SETS * NQ_CHUNK))) return st;
+            CU(cudaMemsetAsync(s.ctl, 0, DEV_SETS * NQ_CHUNK * sizeof(QueryCtl), stream));
         }
-        // two control-block sets, alternated per launch: in pipelined mode the next scan starts
+        // DEV_SETS control-block sets, rotated per launch: in pipelined mode the next scan starts
         // while the previous finalize (which re-arms its own set at the end) may still be running
-        const uint32_t parity = h->dev_parity & 1;
+        const uint32_t parity = h->dev_parity % DEV_SETS;
         QueryCtl* ctl = s.ctl + parity * NQ_CHUNK;
-        h->dev_parity ^= 1;
+        h->dev_parity += 1;
         if ((st = reserve_early(s, stream))) return st;
         ScanWork w{s.cand, s.cand_count, s.cand_max, ctl, grid_x, Kp};
         w.early = s.early + static_cast<size_t>(parity) * NQ_CHUNK * EARLY_STRIDE;
