@@ -13,6 +13,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -40,13 +41,20 @@ static int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(_e));                                                \
     } while (0)
 
-enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_N = 8 };
+enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_COMBINED = 7, ST_N = 8 };
 
 namespace {
 
 constexpr uint32_t NQ_CHUNK = 32;  // queries per launch of the per-query scan
 constexpr uint32_t DEV_SETS = 4;   // control-block / early-threshold sets rotated by pipelined device searches
-constexpr uint32_t BATCH_MIN = 8;        // nq >= BATCH_MIN → batched tile pipeline
+// nq >= batch_min → batched tile pipeline.  Measured at 1M x 384 (profiles/r01_small_batch.md): the tensor-core
+// pipeline serves 2..128 queries in 0.19 ms, less than two single-query scans, so it takes over from nq = 2; the
+// CUDA-core pipeline (manhattan, FP32 mode, wider rows) costs 3.7 ms per 128-query tile and only pays from 16.
+static uint32_t batch_min_for(bool tensor_path) {
+    static const int forced = [] { const char* e = getenv("VL_BATCH_MIN"); return e ? atoi(e) : 0; }();
+    if (forced >= 2) return static_cast<uint32_t>(forced);
+    return tensor_path ? 2u : 16u;
+}
 constexpr uint32_t BATCH_CHUNK = 1024;   // queries per batched pass
 constexpr uint32_t BATCH_CAPQ = 4096;    // candidate slots per query
 
@@ -117,6 +125,16 @@ struct vl_index {
     // ---- tensor-core batched path ----
     TcState tc;
     std::mutex tc_mu;
+    // ---- combiner: concurrent single-query callers are coalesced into one batched launch ----
+    struct Pending {
+        const float* q; uint32_t k; int metric;
+        uint64_t* ids; double* scores; uint32_t* count;
+        int rc = VL_OK; bool done = false; std::string err;
+    };
+    std::mutex comb_mu;
+    std::condition_variable comb_cv;
+    std::vector<Pending*> comb_queue;
+    bool comb_leader = false;
     // ---- hnsw ----
     HnswPtr hnsw;
     int hnsw_metric = -1;
@@ -482,8 +500,8 @@ static int launch_single_queries(vl_index* h, const FlatView& v, const float* dq
     return VL_OK;
 }
 
-int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
-                uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+static int flat_search_impl(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                            uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
     // flat.rs:99-104: the dimension is only checked when the index is non-empty
     if (h->n != 0 && qdim != h->dim)
         return fail(VL_ERR_DIM, "Dimension mismatch: expected %u, got %u", h->dim, qdim);
@@ -503,7 +521,8 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
     int rc = VL_OK;
-    const bool batched = fast && nq >= BATCH_MIN;
+    const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
+    const bool batched = fast && nq >= batch_min_for(tensor_path);
     const uint32_t chunk = batched ? BATCH_CHUNK : NQ_CHUNK;
     for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += chunk) {
         const uint32_t m = std::min(chunk, nq - q0);
@@ -603,6 +622,85 @@ extern "C" {
 
 const char* vl_last_error(void) { return g_err; }
 const char* vl_version(void) { return "vectorlite-b200 0.1.0 (sm_100a)"; }
+
+// Front door of the flat host search.  The reference serves searches from many worker threads under a read lock
+// (client.rs:398, server.rs:258-275): concurrent SINGLE-query callers on one handle are combined — the first one
+// in becomes the leader, runs whatever has queued up behind the running launch as ONE batched search (the
+// tensor-core pipeline serves up to 128 queries in the time of 1.6 single-query scans) and hands the results
+// back.  A lone caller runs its own query at once: no added latency, no timer.
+constexpr size_t COMBINE_MAX = 128;
+int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+    static const bool combine = getenv("VL_DISABLE_COMBINER") == nullptr;
+    if (!combine || nq != 1 || h->n == 0 || k == 0 || qdim != h->dim)
+        return flat_search_impl(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
+    vl_index::Pending me;
+    me.q = queries; me.k = k; me.metric = metric; me.ids = out_ids; me.scores = out_scores; me.count = out_counts;
+    std::unique_lock<std::mutex> lk(h->comb_mu);
+    h->comb_queue.push_back(&me);
+    while (!me.done) {
+        if (h->comb_leader) {
+            h->comb_cv.wait(lk);
+            continue;
+        }
+        // leader: take the head of the queue and everything behind it with the same (k, metric)
+        h->comb_leader = true;
+        std::vector<vl_index::Pending*> batch;
+        const uint32_t bk = h->comb_queue.front()->k;
+        const int bm = h->comb_queue.front()->metric;
+        for (auto it = h->comb_queue.begin(); it != h->comb_queue.end() && batch.size() < COMBINE_MAX;) {
+            if ((*it)->k == bk && (*it)->metric == bm) {
+                batch.push_back(*it);
+                it = h->comb_queue.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        const uint32_t m = static_cast<uint32_t>(batch.size());
+        int rc;
+        std::string err;
+        if (m == 1) {
+            vl_index::Pending* p = batch[0];
+            rc = flat_search_impl(h, p->q, 1, qdim, bk, bm, p->ids, p->scores, p->count);
+            if (rc != VL_OK) err = vl_last_error();
+        } else {
+            std::vector<float> qs(static_cast<size_t>(m) * qdim);
+            std::vector<uint64_t> ids(static_cast<size_t>(m) * bk);
+            std::vector<double> sc(static_cast<size_t>(m) * bk);
+            std::vector<uint32_t> cnt(m);
+            for (uint32_t i = 0; i < m; ++i) memcpy(qs.data() + static_cast<size_t>(i) * qdim, batch[i]->q, qdim * sizeof(float));
+            rc = flat_search_impl(h, qs.data(), m, qdim, bk, bm, ids.data(), sc.data(), cnt.data());
+            if (rc != VL_OK) err = vl_last_error();
+            for (uint32_t i = 0; i < m; ++i) {
+                memcpy(batch[i]->ids, ids.data() + static_cast<size_t>(i) * bk, bk * sizeof(uint64_t));
+                memcpy(batch[i]->scores, sc.data() + static_cast<size_t>(i) * bk, bk * sizeof(double));
+                *batch[i]->count = cnt[i];
+            }
+            h->stats[ST_COMBINED] += m;
+        }
+        std::vector<int> rcs(m, rc);
+        std::vector<std::string> errs(m, err);
+        if (rc != VL_OK && m > 1) {   // a batch-level failure (e.g. one NaN query) must not leak to the other callers
+            for (uint32_t i = 0; i < m; ++i) {
+                vl_index::Pending* p = batch[i];
+                rcs[i] = flat_search_impl(h, p->q, 1, qdim, bk, bm, p->ids, p->scores, p->count);
+                errs[i] = rcs[i] != VL_OK ? std::string(vl_last_error()) : std::string();
+            }
+        }
+        lk.lock();
+        for (uint32_t i = 0; i < m; ++i) {
+            batch[i]->rc = rcs[i];
+            batch[i]->err = errs[i];
+            batch[i]->done = true;
+        }
+        h->comb_leader = false;
+        h->comb_cv.notify_all();
+    }
+    lk.unlock();
+    if (me.rc != VL_OK) return fail(me.rc, "%s", me.err.c_str());   // re-raise in the caller's thread
+    return VL_OK;
+}
 
 static int create_common(uint32_t dim, int device, vl_index** out, int type) {
     if (!out) return fail(VL_ERR_INVALID, "out is null");
@@ -863,7 +961,8 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         out.peers.q_off = o.peers.q_off + q0;
         return out;
     };
-    if (nq >= BATCH_MIN) {
+    const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
+    if (nq >= batch_min_for(tensor_path)) {
         const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
         for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
             const uint32_t m = std::min(BATCH_CHUNK, nq - q0);
@@ -1074,7 +1173,7 @@ int vl_index_search_exchange(vl_index* h, vl_exchange* x, const float* d_queries
     m.out_flags = d_out_flags;
     // Pipelined handles: the merge joins the programmatic-dependent-launch chain scan → finalize → merge →
     // next scan, so the next search's scan streams rows while this (tiny) kernel waits for the peers.
-    CU(launch_exchange_merge(m, h->pipelined && nq < BATCH_MIN, stream));
+    CU(launch_exchange_merge(m, h->pipelined && nq == 1, stream));
     h->stats[ST_LAUNCHES] += 1;
     return VL_OK;
 }
