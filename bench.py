@@ -37,7 +37,9 @@ import numpy as np  # noqa: E402
 DIM = 384
 METRIC_NAMES = {"cosine": 0, "euclidean": 1, "manhattan": 2, "dot": 3}
 QUERIES_PER_STEP = 64
-E2E_CALLERS = 4          # concurrent host threads calling vl_index_search in the e2e leg (N = 1)
+E2E_CALLERS = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4))
+# ^ concurrent host threads calling vl_index_search in the e2e leg (N = 1): as many as the reference arm uses
+#   (one query per host thread)
 
 
 def load_peaks():
@@ -416,15 +418,30 @@ def main():
     e2e_single = time_e2e(step_e2e)
     e2e_qps, e2e_callers = e2e_single, 1
     if world == 1:
+        # E2E_CALLERS threads issue the steps' single-query searches back to back (a shared cursor, no barrier
+        # between steps); every call is still one query in host memory → one result in host memory
+        import itertools
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=E2E_CALLERS)
 
-        def step_e2e_concurrent():
-            def work(c):
-                for qi in range(c, QUERIES_PER_STEP, E2E_CALLERS):
-                    one_search(qi)
+        def run_concurrent(n_steps):
+            total = n_steps * QUERIES_PER_STEP
+            cursor = itertools.count()
+
+            def work(_):
+                while True:
+                    i = next(cursor)
+                    if i >= total:
+                        return
+                    one_search(i % QUERIES_PER_STEP)
             list(pool.map(work, range(E2E_CALLERS)))
-        e2e_qps, e2e_callers = time_e2e(step_e2e_concurrent), E2E_CALLERS
+        run_concurrent(2)
+        conc_steps = max(e2e_steps, args.steps)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_concurrent(conc_steps)
+        e2e_qps = conc_steps * QUERIES_PER_STEP / (time.perf_counter() - t0)
+        e2e_callers = E2E_CALLERS
         pool.shutdown()
 
     # ---- extras: other metrics, batched (B=1024) tensor-core / CUDA-core pipelines ---------------------
@@ -531,7 +548,8 @@ def main():
                     "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
                     "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8),
                     "callers": e2e_callers, "single_caller_value": e2e_single,
-                    "api": "vl_index_search (host buffers in, host results out), one query per call"},
+                    "api": "vl_index_search (host buffers in, host results out), one query per call; concurrent callers on a "
+                           "handle are combined into batched launches by the handle (csrc/api.cu flat_search)"},
             "gpu_launches": int(launches + (merges if (world > 1 and idx.exchange == "nccl") else 0)),
             "clocks": clocks,
             "extras": extras,

@@ -521,6 +521,53 @@ def test_bf16_mirror_single_query_scan(vl, oracle_mod):
     assert after["exact_queries"] == before["exact_queries"], "the fp32 retry should certify these near-ties"
 
 
+def test_concurrent_single_query_callers_are_combined(vl, oracle_mod):
+    """Many host threads calling search() with ONE query each on the same handle (the reference's serving pattern,
+    client.rs:398 under a read lock): the handle combines what queues up behind a running launch into one batched
+    search.  Every caller must still get exactly its own oracle answer; errors stay with their caller."""
+    import threading
+    n, dim, k, T, per = 20000, 384, 10, 8, 12
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    q = oracle_mod.synth_rows(43, 0, T * per, dim)
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    idx.search_batch(q[:1], k, vl.SimilarityMetric.Cosine)            # build the mirrors outside the race
+    idx.search_batch(q[:4], k, vl.SimilarityMetric.Cosine)
+    st, oi, os_ = oracle_mod.flat_search_batch(rows, None, q, k, 0, nthreads=8)
+    assert st == 0
+    got = {}
+    errors = []
+
+    def worker(t):
+        try:
+            for j in range(per):
+                i = t * per + j
+                metric = vl.SimilarityMetric.Cosine
+                gi, gs, gc = idx.search_batch(q[i:i + 1], k, metric)
+                got[i] = (gi[0].copy(), gs[0].copy(), int(gc[0]))
+            if t == 0:                                                 # a bad query fails alone
+                bad = q[0].copy(); bad[3] = np.nan
+                try:
+                    idx.search_batch(bad[None, :], k, vl.SimilarityMetric.Cosine)
+                    errors.append("NaN query did not raise")
+                except Exception:
+                    pass
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    before = idx.stats()
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(T * per):
+        gi, gs, gc = got[i]
+        assert gc == k and np.array_equal(gi, oi[i]) and np.array_equal(gs.view(np.uint64), os_[i].view(np.uint64)), i
+    after = idx.stats()
+    print("combined:", after["combined_queries"] - before["combined_queries"], "of", T * per)
+    assert after["combined_queries"] > before["combined_queries"], "8 concurrent callers should have been combined"
+
+
 def test_cpp_host_mirror(vl, tmp_path):
     """include/vectorlite.hpp (the C++ mirror of the reference interface) replays the reference's own
     flat / hnsw unit tests against the C ABI."""
