@@ -171,6 +171,26 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
     for i in range(200):
         h.search_batch(queries[i:i + 1], k, metric, 0)
     single_us = (time.perf_counter() - t0) / 200 * 1e6
+    # the same one-query calls from E2E_CALLERS concurrent threads (combined into shared launches by the handle)
+    import itertools
+    from concurrent.futures import ThreadPoolExecutor
+    total_conc = 4096
+
+    def conc_run(total):
+        cursor = itertools.count()
+
+        def work(_):
+            while True:
+                i = next(cursor)
+                if i >= total:
+                    return
+                h.search_batch(queries[i % nq:i % nq + 1], k, metric, 0)
+        with ThreadPoolExecutor(max_workers=E2E_CALLERS) as pool:
+            list(pool.map(work, range(E2E_CALLERS)))
+    conc_run(256)
+    t0 = time.perf_counter()
+    conc_run(total_conc)
+    conc_qps = total_conc / (time.perf_counter() - t0)
     ref = {}
     for name in ("hnsw_reference_recall_n20000_c1024_M16.json", "hnsw_reference_recall_n20000_c0_M16.json",
                  "hnsw_reference_recall_n50000_c1024_M16.json"):
@@ -183,6 +203,7 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
             "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "builder": build_info,
             "host_threads": cpu_threads(),
             "sweep": sweep, "single_query_latency_us_ef_k": single_us,
+            "concurrent_single_query_callers": {"callers": E2E_CALLERS, "qps_e2e_ef_k": conc_qps},
             "reference_restatement_recall": ref,
             "note": "reference recall = oracle restatement of crate hnsw 0.11 + u64-quantised functors at "
                     "efC=400 on smaller N (CPU build is single-threaded); parity at equal parameters is "

@@ -237,3 +237,33 @@ def test_reference_score_mode(vl, oracle_mod, kats, metric):
             if r["id"] in by_id:
                 assert by_id[r["id"]] == want, (r["id"], by_id[r["id"]], want)
         assert res[0].id == 100
+
+
+def test_concurrent_single_query_callers_are_combined(vl, oracle_mod):
+    """Concurrent one-query search() calls on one HNSW handle are combined into one launch; every caller gets the
+    answer a lone call gives (the traversal of a query does not depend on its batch)."""
+    import threading
+    n, dim, k, T, per = 8000, 64, 10, 8, 10
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=32)
+    q = oracle_mod.synth_rows(43, 0, T * per, dim, clusters=32)
+    h = vl.HNSWIndex(dim, vl.SimilarityMetric.Cosine, ef_construction=64)
+    h.add_batch(np.arange(n, dtype=np.uint64), rows)
+    alone = [h.search_batch(q[i:i + 1], k, vl.SimilarityMetric.Cosine, 16) for i in range(T * per)]
+    got, errors = {}, []
+
+    def worker(t):
+        try:
+            for j in range(per):
+                i = t * per + j
+                got[i] = h.search_batch(q[i:i + 1], k, vl.SimilarityMetric.Cosine, 16)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    before = h.stats()["combined_queries"]
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(T * per):
+        assert np.array_equal(got[i][0], alone[i][0]) and np.array_equal(got[i][1], alone[i][1]), i
+    assert h.stats()["combined_queries"] > before

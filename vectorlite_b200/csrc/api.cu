@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -127,7 +128,7 @@ struct vl_index {
     std::mutex tc_mu;
     // ---- combiner: concurrent single-query callers are coalesced into one batched launch ----
     struct Pending {
-        const float* q; uint32_t k; int metric;
+        const float* q; uint32_t k; int metric; uint32_t ef;
         uint64_t* ids; double* scores; uint32_t* count;
         int rc = VL_OK; bool done = false; std::string err;
     };
@@ -623,19 +624,18 @@ extern "C" {
 const char* vl_last_error(void) { return g_err; }
 const char* vl_version(void) { return "vectorlite-b200 0.1.0 (sm_100a)"; }
 
-// Front door of the flat host search.  The reference serves searches from many worker threads under a read lock
-// (client.rs:398, server.rs:258-275): concurrent SINGLE-query callers on one handle are combined — the first one
-// in becomes the leader, runs whatever has queued up behind the running launch as ONE batched search (the
-// tensor-core pipeline serves up to 128 queries in the time of 1.6 single-query scans) and hands the results
-// back.  A lone caller runs its own query at once: no added latency, no timer.
+// Combiner shared by the flat and HNSW host searches.  The reference serves searches from many worker threads
+// under a read lock (client.rs:398, server.rs:258-275): concurrent SINGLE-query callers on one handle are combined
+// — the first one in becomes the leader, runs whatever has queued up behind the running launch as ONE batched
+// search (flat: the tensor-core pipeline serves up to 128 queries in the time of 1.6 single-query scans; HNSW: one
+// CTA per query, all in flight together) and hands the results back.  A lone caller runs its own query at once: no
+// added latency, no timer.  `impl(queries, m, ids, scores, counts)` is the uncombined search of m queries.
 constexpr size_t COMBINE_MAX = 128;
-int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
-                uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
-    static const bool combine = getenv("VL_DISABLE_COMBINER") == nullptr;
-    if (!combine || nq != 1 || h->n == 0 || k == 0 || qdim != h->dim)
-        return flat_search_impl(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
+using SearchImpl = std::function<int(const float*, uint32_t, uint32_t, int, uint32_t, uint64_t*, double*, uint32_t*)>;
+static int combined_search(vl_index* h, const float* query, uint32_t qdim, uint32_t k, int metric, uint32_t ef,
+                           uint64_t* out_ids, double* out_scores, uint32_t* out_counts, const SearchImpl& impl) {
     vl_index::Pending me;
-    me.q = queries; me.k = k; me.metric = metric; me.ids = out_ids; me.scores = out_scores; me.count = out_counts;
+    me.q = query; me.k = k; me.metric = metric; me.ef = ef; me.ids = out_ids; me.scores = out_scores; me.count = out_counts;
     std::unique_lock<std::mutex> lk(h->comb_mu);
     h->comb_queue.push_back(&me);
     while (!me.done) {
@@ -643,13 +643,13 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
             h->comb_cv.wait(lk);
             continue;
         }
-        // leader: take the head of the queue and everything behind it with the same (k, metric)
+        // leader: take the head of the queue and everything behind it with the same (k, metric, ef)
         h->comb_leader = true;
         std::vector<vl_index::Pending*> batch;
-        const uint32_t bk = h->comb_queue.front()->k;
+        const uint32_t bk = h->comb_queue.front()->k, bef = h->comb_queue.front()->ef;
         const int bm = h->comb_queue.front()->metric;
         for (auto it = h->comb_queue.begin(); it != h->comb_queue.end() && batch.size() < COMBINE_MAX;) {
-            if ((*it)->k == bk && (*it)->metric == bm) {
+            if ((*it)->k == bk && (*it)->metric == bm && (*it)->ef == bef) {
                 batch.push_back(*it);
                 it = h->comb_queue.erase(it);
             } else {
@@ -662,7 +662,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
         std::string err;
         if (m == 1) {
             vl_index::Pending* p = batch[0];
-            rc = flat_search_impl(h, p->q, 1, qdim, bk, bm, p->ids, p->scores, p->count);
+            rc = impl(p->q, 1u, bk, bm, bef, p->ids, p->scores, p->count);
             if (rc != VL_OK) err = vl_last_error();
         } else {
             std::vector<float> qs(static_cast<size_t>(m) * qdim);
@@ -670,7 +670,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
             std::vector<double> sc(static_cast<size_t>(m) * bk);
             std::vector<uint32_t> cnt(m);
             for (uint32_t i = 0; i < m; ++i) memcpy(qs.data() + static_cast<size_t>(i) * qdim, batch[i]->q, qdim * sizeof(float));
-            rc = flat_search_impl(h, qs.data(), m, qdim, bk, bm, ids.data(), sc.data(), cnt.data());
+            rc = impl(qs.data(), m, bk, bm, bef, ids.data(), sc.data(), cnt.data());
             if (rc != VL_OK) err = vl_last_error();
             for (uint32_t i = 0; i < m; ++i) {
                 memcpy(batch[i]->ids, ids.data() + static_cast<size_t>(i) * bk, bk * sizeof(uint64_t));
@@ -684,7 +684,7 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
         if (rc != VL_OK && m > 1) {   // a batch-level failure (e.g. one NaN query) must not leak to the other callers
             for (uint32_t i = 0; i < m; ++i) {
                 vl_index::Pending* p = batch[i];
-                rcs[i] = flat_search_impl(h, p->q, 1, qdim, bk, bm, p->ids, p->scores, p->count);
+                rcs[i] = impl(p->q, 1u, bk, bm, bef, p->ids, p->scores, p->count);
                 errs[i] = rcs[i] != VL_OK ? std::string(vl_last_error()) : std::string();
             }
         }
@@ -700,6 +700,20 @@ int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, u
     lk.unlock();
     if (me.rc != VL_OK) return fail(me.rc, "%s", me.err.c_str());   // re-raise in the caller's thread
     return VL_OK;
+}
+
+static bool combiner_enabled() {
+    static const bool on = getenv("VL_DISABLE_COMBINER") == nullptr;
+    return on;
+}
+
+int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+    if (!combiner_enabled() || nq != 1 || h->n == 0 || k == 0 || qdim != h->dim)
+        return flat_search_impl(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
+    return combined_search(h, queries, qdim, k, metric, 0u, out_ids, out_scores, out_counts,
+                           [&](const float* q, uint32_t m, uint32_t bk, int bm, uint32_t, uint64_t* ids, double* sc,
+                               uint32_t* cnt) { return flat_search_impl(h, q, m, qdim, bk, bm, ids, sc, cnt); });
 }
 
 static int create_common(uint32_t dim, int device, vl_index** out, int type) {
@@ -920,16 +934,22 @@ int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdi
         for (size_t i = 0; i < static_cast<size_t>(nq) * k; ++i) { out_ids[i] = ~0ull; out_scores[i] = 0.0; }
         for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
         if (hnsw_live(h->hnsw.get()) == 0 || k == 0 || nq == 0) return VL_OK;
-        DeviceGuard dg(h->device);
-        int st = hnsw_upload(h->hnsw.get(), h->mut_stream);
-        if (st) return fail(st, "hnsw graph upload failed");
-        uint64_t visited = 0, launches = 0;
-        st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, queries, nq, k, ef, out_ids, out_scores,
-                              out_counts, h->mut_stream, &visited, &launches);
-        h->stats[ST_HNSW_VISITED] = visited;
-        h->stats[ST_LAUNCHES] += launches;
-        if (st) return fail(st, "hnsw search failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return VL_OK;
+        auto impl = [&](const float* q, uint32_t m, uint32_t bk, int, uint32_t bef, uint64_t* ids, double* sc,
+                        uint32_t* cnt) -> int {
+            DeviceGuard dg(h->device);
+            int st = hnsw_upload(h->hnsw.get(), h->mut_stream);
+            if (st) return fail(st, "hnsw graph upload failed");
+            uint64_t visited = 0, launches = 0;
+            st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, q, m, bk, bef, ids, sc, cnt, h->mut_stream,
+                                  &visited, &launches);
+            h->stats[ST_HNSW_VISITED] = visited;
+            h->stats[ST_LAUNCHES] += launches;
+            if (st) return fail(st, "hnsw search failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return VL_OK;
+        };
+        if (combiner_enabled() && nq == 1)   // concurrent single-query callers share one launch
+            return combined_search(h, queries, qdim, k, metric, ef, out_ids, out_scores, out_counts, impl);
+        return impl(queries, nq, k, metric, ef, out_ids, out_scores, out_counts);
     }
     return flat_search(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
 }
