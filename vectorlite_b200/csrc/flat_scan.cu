@@ -130,7 +130,8 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
     // Stand-alone (non-pipelined) launches let their finalize be launched right away: it parks in
     // griddepcontrol.wait until this grid has completed, which takes its launch latency off a lone caller's
     // critical path.  In a pipelined stream the same trigger would also release the NEXT query's scan into SMs
-    // that are still streaming (measured 5 % slower, 7711 vs 8089 q/s), so it is not used there.
+    // that are still streaming (measured 5 % slower, 7711 vs 8089 q/s; a trigger after the last tile: 7950), so it is
+    // not used there.
     if (early_trigger) pdl_launch_dependents();
     CtaTopK<SCAN_CAP, SCAN_THREADS> topk{s_keys, &s_count};
     for (uint32_t i = tid; i < pitch4; i += SCAN_THREADS) s_q[i] = q4[i];
@@ -162,7 +163,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
                            static_cast<uint32_t>(Kp) <= G;
 
     unsigned long long tau = 0ull, tau_local = 0ull, g_next = 0ull;
-    bool nonfinite = false;
+    bool nonfinite = false, got_early = false;
     for (uint32_t it = 0; it < my_tiles; ++it) {
         if (it == 1 && use_early) {
             // ---- publish the best key of the first tile -------------------------------------------------------
@@ -178,7 +179,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
             if (lane == 0 && m) atomicMax(&s_red, m);
             __syncthreads();
             if (tid == 0 && s_red) *reinterpret_cast<volatile unsigned long long*>(early + b) = s_red;
-        } else if (it == 3 && use_early) {
+        } else if ((it == 3 || it == 5 || it == 7) && use_early && !got_early) {
             // ---- early grid-wide threshold: min over Kp disjoint groups of the published maxima ------------------
             __syncthreads();
             if (tid == 0) s_red = ~0ull;
@@ -211,6 +212,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
                 tau = t1;
                 tau_local = t1 > tau_local ? t1 : tau_local;
             }
+            got_early = t1 != 0ull;   // 0: some CTAs had not published yet (staggered start) — try again two tiles on
         } else if ((it & (SCAN_TILES_PER_CHECK - 1)) == 0) {
             __syncthreads();
             if (s_count > LIMIT) {  // uniform: read after the barrier, no pushes in flight
