@@ -521,6 +521,21 @@ def test_bf16_mirror_single_query_scan(vl, oracle_mod):
     assert after["exact_queries"] == before["exact_queries"], "the fp32 retry should certify these near-ties"
 
 
+@pytest.mark.parametrize("dim", [128, 256])
+def test_bf16_mirror_scan_other_widths(vl, oracle_mod, dim):
+    """The bf16-mirror single-query scan also serves 128- and 256-element rows (NCH = 1, 2)."""
+    n, k = 12000, 10
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    q = oracle_mod.synth_rows(43, 0, 3, dim)
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    for metric in (vl.SimilarityMetric.Cosine, vl.SimilarityMetric.Euclidean, vl.SimilarityMetric.DotProduct):
+        b = idx.stats()["bf16_scans"]
+        for j in range(q.shape[0]):
+            _check(vl, oracle_mod, idx, rows, None, q[j:j + 1], k, metric)
+        assert idx.stats()["bf16_scans"] - b >= q.shape[0], (dim, metric)
+
+
 def test_concurrent_single_query_callers_are_combined(vl, oracle_mod):
     """Many host threads calling search() with ONE query each on the same handle (the reference's serving pattern,
     client.rs:398 under a read lock): the handle combines what queues up behind a running launch into one batched

@@ -456,12 +456,14 @@ static int single_query_mirror(vl_index* h, const FlatView& v, int metric, cudaS
     *mirror = nullptr;
     *sq_norm = nullptr;
     static const bool disabled = getenv("VL_DISABLE_BF16_SCAN") != nullptr;
-    if (disabled || h->mode != VL_MODE_AUTO || metric == VL_METRIC_MANHATTAN || v.pitch != 384) return VL_OK;
+    if (disabled || h->mode != VL_MODE_AUTO || metric == VL_METRIC_MANHATTAN || !flat_scan_bf16_supports(v.pitch) ||
+        v.pitch != v.dim)
+        return VL_OK;
     std::lock_guard<std::mutex> lk(h->tc_mu);
     const bool cosine = metric == VL_METRIC_COSINE;
     const uint64_t before = cosine ? h->tc.built_norm : h->tc.built_raw;
     CU(tc_prepare(&h->tc, v, h->cap, metric, 1, stream));
-    if (!h->tc.usable || h->tc.KP != 384) return VL_OK;
+    if (!h->tc.usable || h->tc.KP != v.pitch) return VL_OK;
     const uint64_t after = cosine ? h->tc.built_norm : h->tc.built_raw;
     if (after != before) CU(cudaStreamSynchronize(stream));   // other streams may scan the mirror next
     *mirror = cosine ? h->tc.rows_norm : h->tc.rows_raw;

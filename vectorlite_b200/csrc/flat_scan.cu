@@ -115,7 +115,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
     constexpr int TILE = (SCAN_THREADS / 32) * R;
     constexpr int LIMIT = SCAN_CAP - SCAN_TILES_PER_CHECK * TILE;
     constexpr int OWN_SHIFT = BF16 ? 1 : 2;              // owner lanes: every 2nd (16 rows) / 4th (8 rows)
-    static_assert(!BF16 || NCH == 3, "the bf16 mirror variant is specialised for 384-d rows");
+    static_assert(!BF16 || (NCH >= 1 && NCH <= 3), "the bf16 mirror variant serves rows of 128 / 256 / 384 elements");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
     float4* s_q = reinterpret_cast<float4*>(smem_raw + SCAN_CAP * sizeof(uint64_t));
@@ -402,16 +402,29 @@ cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t
     }
 }
 
-// single-query scan over the bf16 mirror; requires pitch == 384 and metric != manhattan
+// single-query scan over the bf16 mirror; requires pitch (== the mirror's padded width) of 128 / 256 / 384 elements
+// and metric != manhattan
+template <int METRIC>
+static cudaError_t launch_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
+                               uint32_t nq, const ScanWork& w, bool pipelined, cudaStream_t s) {
+    switch (v.pitch) {
+        case 128: return launch_one<METRIC, 1, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        case 256: return launch_one<METRIC, 2, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        case 384: return launch_one<METRIC, 3, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+bool flat_scan_bf16_supports(uint32_t pitch) { return pitch == 128 || pitch == 256 || pitch == 384; }
+
 cudaError_t launch_flat_scan_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
                                   uint32_t nq, int metric, const ScanWork& w, bool pipelined, cudaStream_t s) {
-    if (v.pitch != 384 || !mirror) return cudaErrorNotSupported;
+    if (!flat_scan_bf16_supports(v.pitch) || !mirror) return cudaErrorNotSupported;
     switch (metric) {
-        case COSINE: return launch_one<COSINE, 3, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
-        case EUCLIDEAN:
-            return sq_norm ? launch_one<EUCLIDEAN, 3, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s)
-                           : cudaErrorNotSupported;
-        case DOT: return launch_one<DOT, 3, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        case COSINE: return launch_bf16<COSINE>(v, mirror, sq_norm, d_queries, nq, w, pipelined, s);
+        case EUCLIDEAN: return sq_norm ? launch_bf16<EUCLIDEAN>(v, mirror, sq_norm, d_queries, nq, w, pipelined, s)
+                                       : cudaErrorNotSupported;
+        case DOT: return launch_bf16<DOT>(v, mirror, sq_norm, d_queries, nq, w, pipelined, s);
         default: return cudaErrorNotSupported;
     }
 }
