@@ -198,6 +198,10 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
         if os.path.exists(pth):
             d = json.load(open(pth))
             ref[name] = {e: round(v["recall_at_10"], 4) for e, v in d["sweep"].items()}
+            if "qps_4threads" in next(iter(d["sweep"].values())):
+                # timed when the golden file was generated (build container's host cores, 4 threads) — not this box
+                ref[name]["qps_4threads_when_generated"] = {e: round(v["qps_4threads"]) for e, v in d["sweep"].items()}
+                ref[name]["visited_per_query"] = {e: round(v["visited_per_query"]) for e, v in d["sweep"].items()}
     h.close()
     return {"rows": n, "dim": DIM, "data": f"synthetic {clusters}-centre mixture, unit norm", "M": 16, "M0": 32,
             "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "builder": build_info,
@@ -569,6 +573,7 @@ def main():
                     "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
                     "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8),
                     "callers": e2e_callers, "single_caller_value": e2e_single,
+                    "bf16_retries": idx.local.stats()["bf16_retries"],
                     "api": "vl_index_search (host buffers in, host results out), one query per call; concurrent callers on a "
                            "handle are combined into batched launches by the handle (csrc/api.cu flat_search)"},
             "gpu_launches": int(launches + (merges if (world > 1 and idx.exchange == "nccl") else 0)),

@@ -206,8 +206,9 @@ int vl_index_set_mode(vl_index* h, int mode);
 int vl_index_set_pos_base(vl_index* h, uint64_t base);
 /* Counters since creation: [0] kernels launched, [1] searches served by the certified fast path,
  * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited,
- * [6] single-query scans served from the bf16 mirror of the rows (AUTO mode, 384-d, cosine / dot / L2),
- * [7] single-query host searches that were combined with concurrent callers into a batched launch. */
+ * [6] single-query scans served from the bf16 mirror of the rows (AUTO mode, 128/256/384-d, all four metrics),
+ * [7] single-query host searches that were combined with concurrent callers into a batched launch,
+ * [8] mirror scans whose certificate did not hold under the bf16 bound and were re-run on the fp32 arena. */
 int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n);
 /* Pipelined device searches (flat, vl_index_search_device only).  When enabled, consecutive searches
  * enqueued on one stream overlap through programmatic dependent launch: the scan of search i+1

@@ -306,9 +306,10 @@ class _CudaIndex:
         return ids[:got.value], rows[:got.value]
 
     def stats(self) -> dict:
-        out = np.zeros(8, dtype=np.uint64)
-        self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 8)
-        keys = ["launches", "fast_queries", "exact_queries", "h2d_bytes", "d2h_bytes", "hnsw_visited", "bf16_scans", "combined_queries"]
+        out = np.zeros(9, dtype=np.uint64)
+        self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 9)
+        keys = ["launches", "fast_queries", "exact_queries", "h2d_bytes", "d2h_bytes", "hnsw_visited", "bf16_scans",
+                "combined_queries", "bf16_retries"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def set_mode(self, mode: Mode) -> None:

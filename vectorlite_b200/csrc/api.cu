@@ -42,7 +42,7 @@ static int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(_e));                                                \
     } while (0)
 
-enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_COMBINED = 7, ST_N = 8 };
+enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_COMBINED = 7, ST_BF16_RETRY = 8, ST_N = 9 };
 
 namespace {
 
@@ -447,7 +447,7 @@ int run_exact_one(vl_index* h, Slot& s, const FlatView& v, const float* d_query,
     return VL_OK;
 }
 
-// Single-query scans read the bf16 mirror of the rows when one applies (AUTO mode, 384-d, cosine / dot / L2):
+// Single-query scans read the bf16 mirror of the rows when one applies (AUTO mode, 128/256/384-d, all four metrics):
 // half the HBM bytes per query; the candidates are re-scored in f64 and certified with the bf16 bound exactly
 // as in the tensor-core batched path.  Brings the mirror up to date (lazily, like tc_prepare for batches) and
 // returns its pointers; `*mirror` stays null when the fp32 scan has to be used.
@@ -456,9 +456,7 @@ static int single_query_mirror(vl_index* h, const FlatView& v, int metric, cudaS
     *mirror = nullptr;
     *sq_norm = nullptr;
     static const bool disabled = getenv("VL_DISABLE_BF16_SCAN") != nullptr;
-    if (disabled || h->mode != VL_MODE_AUTO || metric == VL_METRIC_MANHATTAN || !flat_scan_bf16_supports(v.pitch) ||
-        v.pitch != v.dim)
-        return VL_OK;
+    if (disabled || h->mode != VL_MODE_AUTO || !flat_scan_bf16_supports(v.pitch) || v.pitch != v.dim) return VL_OK;
     std::lock_guard<std::mutex> lk(h->tc_mu);
     const bool cosine = metric == VL_METRIC_COSINE;
     const uint64_t before = cosine ? h->tc.built_norm : h->tc.built_raw;
@@ -575,9 +573,11 @@ static int flat_search_impl(vl_index* h, const float* queries, uint32_t nq, uint
                     CU(cudaStreamSynchronize(s.stream));
                     bool retry = false;
                     for (uint32_t q = 0; q < m; ++q) retry |= (s.h_flags[q] & FLAG_CERT_FAIL) != 0;
-                    if (retry && (st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, false, s.stream,
-                                                             nullptr)))
-                        return st;
+                    if (retry) {
+                        h->stats[ST_BF16_RETRY] += m;
+                        if ((st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, false, s.stream, nullptr)))
+                            return st;
+                    }
                 }
             }
             if (!zero_copy) CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));

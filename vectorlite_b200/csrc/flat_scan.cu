@@ -7,12 +7,13 @@
 //   * fp32 arena  [n][pitch] fp32 — algorithmic bytes per query = n·pitch·4 (+ n·4 inv-norms for cosine);
 //     one warp reads 8 whole rows per iteration as 128-bit ld.global.nc.L1::no_allocate (3 per lane per
 //     384-d row, 512 B coalesced per instruction);
-//   * bf16 mirror [n][384] bf16 (cosine: rows pre-scaled by 1/‖row‖; dot / L2: raw rows + fp32 ‖row‖²) —
+//   * bf16 mirror [n][384] bf16 (cosine: rows pre-scaled by 1/‖row‖; dot / L2 / L1: raw rows, L2 + fp32 ‖row‖²) —
 //     HALF the bytes per query (s = 2 B/element, stated in bench.py's roofline); one warp reads
 //     16 whole 768-B rows per iteration as 64-bit streaming loads (lane l gets elements 4·(32c + l) … +3 of
 //     chunk c, the same elements as the fp32 layout, so the query registers are identical); bf16 → fp32 is a
 //     shift / mask, accumulation is fp32 against the fp32 query.  Scores are in the tensor-core path's scan
-//     units (cos·‖q‖, x·q, −‖x−q‖² via 2x·q − ‖x‖² − ‖q‖²) and are certified with the same bf16 bound.
+//     units (cos·‖q‖, x·q, −‖x−q‖² via 2x·q − ‖x‖² − ‖q‖²) and are certified with the same bf16 bound; L1 is
+//     −Σ|x̃−q| directly, certified with Σ|x̃−x| <= 2^-9·‖x‖₁ <= 2^-9·√dim·max‖row‖.
 // The query lives in registers; per-lane partial sums are reduced with a transposed butterfly; each row's
 // fp32 score becomes a 64-bit key (score, ~position) and is appended to a CTA candidate buffer only if it
 // beats the running threshold.  The exact f64 score and the final order are produced by flat_finalize.cu.
@@ -58,11 +59,22 @@ __device__ __forceinline__ uint2 ldg_stream64(const uint2* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float dot4_bf16(float acc, const uint2& v, const float4& q) {
-    acc = fmaf(__uint_as_float(v.x << 16), q.x, acc);
-    acc = fmaf(__uint_as_float(v.x & 0xFFFF0000u), q.y, acc);
-    acc = fmaf(__uint_as_float(v.y << 16), q.z, acc);
-    acc = fmaf(__uint_as_float(v.y & 0xFFFF0000u), q.w, acc);
+// cosine / dot / L2: Σ x̃·q (L2 finishes as 2x̃·q − ‖x‖² − ‖q‖²); manhattan: Σ |x̃ − q|
+template <int METRIC>
+__device__ __forceinline__ float accum4_bf16(float acc, const uint2& v, const float4& q) {
+    const float x0 = __uint_as_float(v.x << 16), x1 = __uint_as_float(v.x & 0xFFFF0000u);
+    const float x2 = __uint_as_float(v.y << 16), x3 = __uint_as_float(v.y & 0xFFFF0000u);
+    if (METRIC == MANHATTAN) {
+        acc += fabsf(x0 - q.x);
+        acc += fabsf(x1 - q.y);
+        acc += fabsf(x2 - q.z);
+        acc += fabsf(x3 - q.w);
+    } else {
+        acc = fmaf(x0, q.x, acc);
+        acc = fmaf(x1, q.y, acc);
+        acc = fmaf(x2, q.z, acc);
+        acc = fmaf(x3, q.w, acc);
+    }
     return acc;
 }
 
@@ -253,7 +265,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
 #pragma unroll
                     for (int r = 0; r < R; ++r) v[r] = ldg_stream64(base + static_cast<size_t>(r) * pitch4 + c * 32);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = dot4_bf16(acc[r], v[r], qreg[c]);
+                    for (int r = 0; r < R; ++r) acc[r] = accum4_bf16<METRIC>(acc[r], v[r], qreg[c]);
                 }
             } else {
 #pragma unroll
@@ -262,7 +274,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
                     for (int r = 0; r < R; ++r) {
                         if (row0 + r < hi) {
                             const uint2 v = ldg_stream64(base + static_cast<size_t>(r) * pitch4 + c * 32);
-                            acc[r] = dot4_bf16(acc[r], v, qreg[c]);
+                            acc[r] = accum4_bf16<METRIC>(acc[r], v, qreg[c]);
                         }
                     }
                 }
@@ -312,6 +324,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
         if (owner) {
             if (BF16) {
                 if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -a1) - qn2;   // −‖x−q‖²
+                if (METRIC == MANHATTAN) s = -s;                        // −Σ|x̃−q|
             } else {
                 if (METRIC == COSINE) s *= a1;
                 if (METRIC == EUCLIDEAN || METRIC == MANHATTAN) s = -s;
@@ -403,7 +416,6 @@ cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t
 }
 
 // single-query scan over the bf16 mirror; requires pitch (== the mirror's padded width) of 128 / 256 / 384 elements
-// and metric != manhattan
 template <int METRIC>
 static cudaError_t launch_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
                                uint32_t nq, const ScanWork& w, bool pipelined, cudaStream_t s) {
@@ -425,6 +437,7 @@ cudaError_t launch_flat_scan_bf16(const FlatView& v, const void* mirror, const f
         case EUCLIDEAN: return sq_norm ? launch_bf16<EUCLIDEAN>(v, mirror, sq_norm, d_queries, nq, w, pipelined, s)
                                        : cudaErrorNotSupported;
         case DOT: return launch_bf16<DOT>(v, mirror, sq_norm, d_queries, nq, w, pipelined, s);
+        case MANHATTAN: return launch_bf16<MANHATTAN>(v, mirror, sq_norm, d_queries, nq, w, pipelined, s);
         default: return cudaErrorNotSupported;
     }
 }

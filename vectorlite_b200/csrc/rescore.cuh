@@ -111,6 +111,14 @@ __device__ __forceinline__ void rank_and_certify(const FinalizeParams& p, uint32
                     ok = qn >= 1e-15 && kth > worst / qn + p.tc_abs;
                 } else if (p.metric == DOT) {
                     ok = kth > worst + p.tc_abs * maxn * qn + 1e-30;
+                } else if (p.metric == MANHATTAN) {
+                    // −Σ|x̃−q| with fp32 query: rounding the rows moves the sum by at most Σ|x̃−x| <= 2^-9·‖x‖₁
+                    // <= 2^-9·√dim·‖x‖ (Cauchy–Schwarz); the fp32 sum of non-negative terms adds a RELATIVE
+                    // (nn+2)·u on top.  Every excluded row therefore has exact Σ|x−q| >= L.
+                    double L = (-worst) * (1.0 - (nn + 2.0) * u * 1.01) -
+                               0.001953125 * 1.01 * sqrt(static_cast<double>(p.dim)) * maxn - 1e-30;
+                    L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
+                    ok = kth > sim_from_l1(L);
                 } else {                        // −‖x−q‖² from ‖x‖² + ‖q‖² − 2x·q
                     double L = (-worst) - 2.0 * p.tc_abs * maxn * qn - 2e-6 * (maxn * maxn + qn * qn) - 1e-36;
                     L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
