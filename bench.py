@@ -42,6 +42,32 @@ E2E_CALLERS = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffi
 #   (one query per host thread)
 
 
+def native_callers(index, queries, k, metric, ef, n_threads, total):
+    """`total` single-query vl_index_search calls (host buffers in, host results out) issued by `n_threads` plain
+    host threads sharing one cursor (scripts/native_callers.cpp) — the reference's serving pattern without the
+    Python interpreter lock between calls.  Returns (queries/s, ids[nq,k], scores[nq,k]) or None when the helper
+    is not built."""
+    import ctypes as C
+    so = os.path.join(ROOT, "scripts", "libvl_native_callers.so")
+    if not os.path.exists(so):
+        return None
+    N = C.CDLL(so)
+    N.vl_native_callers.restype = C.c_double
+    N.vl_native_callers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                    C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    nq, dim = q.shape
+    ids = np.zeros((nq, k), dtype=np.uint64)
+    sc = np.zeros((nq, k), dtype=np.float64)
+    cnt = np.zeros(nq, dtype=np.uint32)
+    fn = C.cast(index._L.vl_index_search, C.c_void_p)
+    dt = N.vl_native_callers(fn, index._h, q.ctypes.data, nq, dim, k, int(metric), ef, n_threads, total,
+                             ids.ctypes.data, sc.ctypes.data, cnt.ctypes.data)
+    if dt <= 0:
+        raise RuntimeError(f"native callers: vl_index_search failed with status {int(-dt)}")
+    return total / dt, ids, sc
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -191,6 +217,12 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
     t0 = time.perf_counter()
     conc_run(total_conc)
     conc_qps = total_conc / (time.perf_counter() - t0)
+    conc_impl = "python threads (ctypes)"
+    nat = native_callers(h, queries[:1024], k, metric, 0, E2E_CALLERS, 2 * total_conc)
+    if nat is not None:
+        conc_py, conc_qps, conc_impl = conc_qps, nat[0], "native host threads (scripts/native_callers.cpp)"
+    else:
+        conc_py = None
     ref = {}
     for name in ("hnsw_reference_recall_n20000_c1024_M16.json", "hnsw_reference_recall_n20000_c0_M16.json",
                  "hnsw_reference_recall_n50000_c1024_M16.json"):
@@ -207,7 +239,8 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
             "ef_construction": efc, "k": k, "batch": nq, "build_seconds": build_s, "builder": build_info,
             "host_threads": cpu_threads(),
             "sweep": sweep, "single_query_latency_us_ef_k": single_us,
-            "concurrent_single_query_callers": {"callers": E2E_CALLERS, "qps_e2e_ef_k": conc_qps},
+            "concurrent_single_query_callers": {"callers": E2E_CALLERS, "qps_e2e_ef_k": conc_qps, "callers_impl": conc_impl,
+                                                "python_callers_qps": conc_py},
             "reference_restatement_recall": ref,
             "note": "reference recall = oracle restatement of crate hnsw 0.11 + u64-quantised functors at "
                     "efC=400 on smaller N (CPU build is single-threaded); parity at equal parameters is "
@@ -442,6 +475,7 @@ def main():
     e2e_steps = max(2, args.steps // 4)
     e2e_single = time_e2e(step_e2e)
     e2e_qps, e2e_callers = e2e_single, 1
+    e2e_python_callers, e2e_impl = None, "python threads (ctypes)"
     if world == 1:
         # E2E_CALLERS threads issue the steps' single-query searches back to back (a shared cursor, no barrier
         # between steps); every call is still one query in host memory → one result in host memory
@@ -468,6 +502,15 @@ def main():
         e2e_qps = conc_steps * QUERIES_PER_STEP / (time.perf_counter() - t0)
         e2e_callers = E2E_CALLERS
         pool.shutdown()
+        # the same calls from plain host threads (no interpreter lock between them): the headline e2e figure
+        e2e_python_callers = e2e_qps
+        want_ids, want_sc, _ = idx.local.search_batch(queries[:QUERIES_PER_STEP], k, metric)
+        native_callers(idx.local, queries[:QUERIES_PER_STEP], k, metric, 0, E2E_CALLERS, 4 * QUERIES_PER_STEP)
+        nat = native_callers(idx.local, queries[:QUERIES_PER_STEP], k, metric, 0, E2E_CALLERS,
+                             conc_steps * QUERIES_PER_STEP)
+        if nat is not None:
+            assert np.array_equal(nat[1], want_ids) and np.array_equal(nat[2].view(np.uint64), want_sc.view(np.uint64))
+            e2e_qps, e2e_impl = nat[0], "native host threads (scripts/native_callers.cpp)"
 
     # ---- extras: other metrics, batched (B=1024) tensor-core / CUDA-core pipelines ---------------------
     extras = {}
@@ -572,7 +615,8 @@ def main():
             "e2e": {"value": e2e_qps, "unit": "queries/s x 1M-row shards",
                     "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
                     "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8),
-                    "callers": e2e_callers, "single_caller_value": e2e_single,
+                    "callers": e2e_callers, "callers_impl": e2e_impl, "python_callers_value": e2e_python_callers,
+                    "single_caller_value": e2e_single,
                     "bf16_retries": idx.local.stats()["bf16_retries"],
                     "api": "vl_index_search (host buffers in, host results out), one query per call; concurrent callers on a "
                            "handle are combined into batched launches by the handle (csrc/api.cu flat_search)"},

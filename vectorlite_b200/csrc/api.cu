@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -51,10 +53,11 @@ constexpr uint32_t DEV_SETS = 4;   // control-block / early-threshold sets rotat
 // nq >= batch_min → batched tile pipeline.  Measured at 1M x 384 (profiles/r01_small_batch.md): the tensor-core
 // pipeline serves 2..128 queries in 0.19 ms, less than two single-query scans, so it takes over from nq = 2; the
 // CUDA-core pipeline (manhattan, FP32 mode, wider rows) costs 3.7 ms per 128-query tile and only pays from 16.
-static uint32_t batch_min_for(bool tensor_path) {
+// Where single-query scans read the bf16 mirror (0.12 ms each, manhattan included) the CUDA-core pipeline pays from 32.
+static uint32_t batch_min_for(bool tensor_path, bool mirror_scans = false) {
     static const int forced = [] { const char* e = getenv("VL_BATCH_MIN"); return e ? atoi(e) : 0; }();
     if (forced >= 2) return static_cast<uint32_t>(forced);
-    return tensor_path ? 2u : 16u;
+    return tensor_path ? 2u : (mirror_scans ? 32u : 16u);
 }
 constexpr uint32_t BATCH_CHUNK = 1024;   // queries per batched pass
 constexpr uint32_t BATCH_CAPQ = 4096;    // candidate slots per query
@@ -136,6 +139,7 @@ struct vl_index {
     std::condition_variable comb_cv;
     std::vector<Pending*> comb_queue;
     bool comb_leader = false;
+    size_t comb_expect = 1;   // size of the batch that just completed: how many callers the next leader may wait for
     // ---- hnsw ----
     HnswPtr hnsw;
     int hnsw_metric = -1;
@@ -451,12 +455,16 @@ int run_exact_one(vl_index* h, Slot& s, const FlatView& v, const float* d_query,
 // half the HBM bytes per query; the candidates are re-scored in f64 and certified with the bf16 bound exactly
 // as in the tensor-core batched path.  Brings the mirror up to date (lazily, like tc_prepare for batches) and
 // returns its pointers; `*mirror` stays null when the fp32 scan has to be used.
+static bool mirror_scans_apply(const vl_index* h) {
+    static const bool disabled = getenv("VL_DISABLE_BF16_SCAN") != nullptr;
+    return !disabled && h->mode == VL_MODE_AUTO && flat_scan_bf16_supports(h->pitch) && h->pitch == h->dim;
+}
+
 static int single_query_mirror(vl_index* h, const FlatView& v, int metric, cudaStream_t stream, const void** mirror,
                                const float** sq_norm) {
     *mirror = nullptr;
     *sq_norm = nullptr;
-    static const bool disabled = getenv("VL_DISABLE_BF16_SCAN") != nullptr;
-    if (disabled || h->mode != VL_MODE_AUTO || !flat_scan_bf16_supports(v.pitch) || v.pitch != v.dim) return VL_OK;
+    if (!mirror_scans_apply(h)) return VL_OK;
     std::lock_guard<std::mutex> lk(h->tc_mu);
     const bool cosine = metric == VL_METRIC_COSINE;
     const uint64_t before = cosine ? h->tc.built_norm : h->tc.built_raw;
@@ -523,7 +531,7 @@ static int flat_search_impl(vl_index* h, const float* queries, uint32_t nq, uint
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
     int rc = VL_OK;
     const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
-    const bool batched = fast && nq >= batch_min_for(tensor_path);
+    const bool batched = fast && nq >= batch_min_for(tensor_path, mirror_scans_apply(h));
     const uint32_t chunk = batched ? BATCH_CHUNK : NQ_CHUNK;
     for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += chunk) {
         const uint32_t m = std::min(chunk, nq - q0);
@@ -633,6 +641,10 @@ const char* vl_version(void) { return "vectorlite-b200 0.1.0 (sm_100a)"; }
 // CTA per query, all in flight together) and hands the results back.  A lone caller runs its own query at once: no
 // added latency, no timer.  `impl(queries, m, ids, scores, counts)` is the uncombined search of m queries.
 constexpr size_t COMBINE_MAX = 128;
+static int combine_wait_us() {
+    static const int us = [] { const char* e = getenv("VL_COMBINE_WAIT_US"); return e ? std::max(0, atoi(e)) : 100; }();
+    return us;
+}
 using SearchImpl = std::function<int(const float*, uint32_t, uint32_t, int, uint32_t, uint64_t*, double*, uint32_t*)>;
 static int combined_search(vl_index* h, const float* query, uint32_t qdim, uint32_t k, int metric, uint32_t ef,
                            uint64_t* out_ids, double* out_scores, uint32_t* out_counts, const SearchImpl& impl) {
@@ -647,6 +659,19 @@ static int combined_search(vl_index* h, const float* query, uint32_t qdim, uint3
         }
         // leader: take the head of the queue and everything behind it with the same (k, metric, ef)
         h->comb_leader = true;
+        if (h->comb_expect > 1 && h->comb_queue.size() < h->comb_expect) {
+            // Re-forming cohort: the callers of the batch that just completed are waking up and coming back with
+            // their next query.  Without this the first one back (usually the old leader) runs a batch of ONE while
+            // the other callers queue behind it — measured at 16 callers: batches alternate 1, 15, 1, 15 …
+            // Bounded (combine_wait_us, default 100 µs), and only after a batch that DID combine callers: a lone
+            // caller (comb_expect == 1) never waits.
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(combine_wait_us());
+            while (h->comb_queue.size() < h->comb_expect && std::chrono::steady_clock::now() < deadline) {
+                lk.unlock();
+                std::this_thread::yield();
+                lk.lock();
+            }
+        }
         std::vector<vl_index::Pending*> batch;
         const uint32_t bk = h->comb_queue.front()->k, bef = h->comb_queue.front()->ef;
         const int bm = h->comb_queue.front()->metric;
@@ -697,6 +722,7 @@ static int combined_search(vl_index* h, const float* query, uint32_t qdim, uint3
             batch[i]->done = true;
         }
         h->comb_leader = false;
+        h->comb_expect = m;
         h->comb_cv.notify_all();
     }
     lk.unlock();
@@ -984,7 +1010,7 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         return out;
     };
     const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
-    if (nq >= batch_min_for(tensor_path)) {
+    if (nq >= batch_min_for(tensor_path, mirror_scans_apply(h))) {
         const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
         for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
             const uint32_t m = std::min(BATCH_CHUNK, nq - q0);
