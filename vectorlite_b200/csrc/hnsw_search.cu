@@ -99,6 +99,12 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             acc[r] = 0.f;
             nid[r] = r < cnt ? ids[r] : HNSW_NONE;
         }
+        // the owner lane's 1/‖row‖ is requested together with the rows (it used to be a second, dependent round
+        // trip after the reduction)
+        const int own_r = lane >> 2;
+        const bool own = (lane & 3) == 0 && own_r < cnt;
+        const uint32_t own_id = own ? ids[own_r] : 0u;
+        const float invn = (METRIC == COSINE && own) ? __ldg(p.g.inv_norm + own_id) : 1.f;
         if (NCH > 0) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -123,11 +129,7 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             }
         }
         const float s = red8(acc, lane);
-        const int r = lane >> 2;
-        if ((lane & 3) == 0 && r < cnt) {
-            const float invn = METRIC == COSINE ? __ldg(p.g.inv_norm + ids[r]) : 1.f;
-            out[r] = beam_key(to_dist<METRIC>(s, invn, invq), ids[r]);
-        }
+        if (own) out[own_r] = beam_key(to_dist<METRIC>(s, invn, invq), own_id);
     };
 
     // ---- entry point ---------------------------------------------------------------------
@@ -175,7 +177,13 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
                 const int size = s_size;
                 const int expand = ef >= 64u ? HN_MAX_EXPAND : (ef >= 32u ? 2 : 1);
                 int nc = 0, picked = 0;
-                for (int e = 0; e < expand; ++e) {
+                // pick first (shared memory only), then fetch: the adjacency rows of all picked entries are
+                // requested together, so a step waits for ONE global-memory round trip instead of `expand`
+                uint32_t node_e[HN_MAX_EXPAND];
+#pragma unroll
+                for (int e = 0; e < HN_MAX_EXPAND; ++e) {
+                    node_e[e] = HNSW_NONE;
+                    if (e >= expand || picked < e) continue;      // uniform
                     unsigned long long best = ~0ull;
                     int bi = -1;
                     for (int i = lane; i < size; i += 32) {
@@ -183,16 +191,34 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
                         if (!(kk & 1ull) && (kk >> 1) < best) { best = kk >> 1; bi = i; }
                     }
                     warp_arg63<false>(best, bi);
-                    if (bi < 0) break;
+                    if (bi < 0) continue;
                     ++picked;
-                    const uint32_t node = static_cast<uint32_t>(best) & 0x7FFFFFFFu;
+                    node_e[e] = static_cast<uint32_t>(best) & 0x7FFFFFFFu;
                     if (lane == 0) s_beam[bi] |= 1ull;
                     __syncwarp();
-                    const uint32_t* adj = lvl == 0 ? p.g.adj0 + static_cast<size_t>(node) * p.g.M0
-                                                   : p.g.upper + (static_cast<size_t>(__ldg(p.g.upper_off + node)) + lvl - 1) * p.g.M;
-                    for (uint32_t j0 = 0; j0 < deg; j0 += 32) {
-                        const uint32_t j = j0 + lane;
-                        uint32_t v = j < deg ? __ldg(adj + j) : HNSW_NONE;
+                }
+                const uint32_t* adj_e[HN_MAX_EXPAND];
+                if (lvl == 0) {
+#pragma unroll
+                    for (int e = 0; e < HN_MAX_EXPAND; ++e)
+                        adj_e[e] = p.g.adj0 + static_cast<size_t>(node_e[e] != HNSW_NONE ? node_e[e] : 0u) * p.g.M0;
+                } else {
+                    uint32_t off_e[HN_MAX_EXPAND];
+#pragma unroll
+                    for (int e = 0; e < HN_MAX_EXPAND; ++e) off_e[e] = node_e[e] != HNSW_NONE ? __ldg(p.g.upper_off + node_e[e]) : 0u;
+#pragma unroll
+                    for (int e = 0; e < HN_MAX_EXPAND; ++e) adj_e[e] = p.g.upper + (static_cast<size_t>(off_e[e]) + lvl - 1) * p.g.M;
+                }
+                for (uint32_t j0 = 0; j0 < deg; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    uint32_t v_e[HN_MAX_EXPAND];
+#pragma unroll
+                    for (int e = 0; e < HN_MAX_EXPAND; ++e)
+                        v_e[e] = (node_e[e] != HNSW_NONE && j < deg) ? __ldg(adj_e[e] + j) : HNSW_NONE;
+#pragma unroll
+                    for (int e = 0; e < HN_MAX_EXPAND; ++e) {
+                        if (node_e[e] == HNSW_NONE) continue;     // uniform
+                        const uint32_t v = v_e[e];
                         bool fresh = false;
                         if (v != HNSW_NONE) {
                             const uint32_t slot = vis_hash(v) & p.vis_mask;
@@ -200,6 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
                             fresh = s_vis[slot] != tag;      // only warp 0 touches the cache
                             s_vis[slot] = tag;
                         }
+                        __syncwarp();                         // entry e's tags are visible to entry e+1's checks
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, fresh);
                         if (fresh) s_cid[nc + __popc(m & ((1u << lane) - 1))] = v;
                         nc += __popc(m);
@@ -227,21 +254,29 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             // ---- warp 0: insert the survivors (append while the pool is filling, else replace the worst)
             if (warp == 0) {
                 int size = s_size;
-                for (int j = 0; j < nc; ++j) {
-                    const unsigned long long key = s_ck[j];
-                    if (key == ~0ull || (key >> 1) >= s_worst) continue;
-                    bool dup = false;                       // the visited cache is lossy: exact de-duplication here
-                    for (int i = lane; i < size; i += 32) dup |= (s_beam[i] >> 1) == (key >> 1);
-                    if (__any_sync(0xFFFFFFFFu, dup)) continue;
-                    if (size < static_cast<int>(ef)) {
-                        if (lane == 0) s_beam[size] = key;
-                        ++size;
-                        __syncwarp();
-                        if (size == static_cast<int>(ef)) pool_recompute_worst(size, ef);
-                    } else {
-                        if (lane == 0) s_beam[s_worst_idx] = key;
-                        __syncwarp();
-                        pool_recompute_worst(size, ef);
+                // 32 candidates per ballot: the scoring phase already dropped what could not beat the pool's worst
+                // entry, so only the set bits (a handful per step once the pool is full) are walked, in order
+                for (int j0 = 0; j0 < nc; j0 += 32) {
+                    const unsigned long long key_l = j0 + lane < nc ? s_ck[j0 + lane] : ~0ull;
+                    unsigned live = __ballot_sync(0xFFFFFFFFu, key_l != ~0ull);
+                    while (live) {
+                        const int src = __ffs(live) - 1;
+                        live &= live - 1;
+                        const unsigned long long key = __shfl_sync(0xFFFFFFFFu, key_l, src);
+                        if ((key >> 1) >= s_worst) continue;
+                        bool dup = false;                   // the visited cache is lossy: exact de-duplication here
+                        for (int i = lane; i < size; i += 32) dup |= (s_beam[i] >> 1) == (key >> 1);
+                        if (__any_sync(0xFFFFFFFFu, dup)) continue;
+                        if (size < static_cast<int>(ef)) {
+                            if (lane == 0) s_beam[size] = key;
+                            ++size;
+                            __syncwarp();
+                            if (size == static_cast<int>(ef)) pool_recompute_worst(size, ef);
+                        } else {
+                            if (lane == 0) s_beam[s_worst_idx] = key;
+                            __syncwarp();
+                            pool_recompute_worst(size, ef);
+                        }
                     }
                 }
                 if (lane == 0) s_size = size;
@@ -310,12 +345,15 @@ static int launch_warps(const HnswParams& p, uint32_t nq, size_t smem, cudaStrea
 static int hnsw_cta_warps(uint32_t beam, uint32_t nq) {
     if (const char* e = std::getenv("VL_HNSW_WARPS")) {
         const int w = atoi(e);
-        if (w == 1 || w == 2 || w == 4) return w;
+        if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16) return w;
     }
     // measured on 1M x 384 (scripts/hnsw_tune.py, profiles/r01_hnsw_tune.jsonl): with thousands of queries in
     // flight one warp per query wins at every beam width (1.42M vs 0.85M q/s at beam 80)
+    // few queries: latency matters, use a whole CTA per query — 16 warps score the up-to-128 candidates of a step in
+    // one round of gathers (scripts/hnsw_latency.py, 1M x 384, beam 80: 370 / 701 / 955 µs per call at nq = 1 / 16 /
+    // 128 vs 439 / 847 / 1299 µs with 4 warps)
     (void)beam;
-    return nq < 1024 ? 4 : 1;          // few queries: latency matters, use a whole CTA per query
+    return nq <= 296 ? 16 : (nq < 1024 ? 4 : 1);
 }
 
 template <int METRIC, bool BUILD>
@@ -325,6 +363,8 @@ static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStre
     switch (hnsw_cta_warps(p.ef, nq)) {
         case 1: return launch_warps<METRIC, BUILD, 1>(p, nq, smem, s);
         case 2: return launch_warps<METRIC, BUILD, 2>(p, nq, smem, s);
+        case 8: return launch_warps<METRIC, BUILD, 8>(p, nq, smem, s);
+        case 16: return launch_warps<METRIC, BUILD, 16>(p, nq, smem, s);
         default: return launch_warps<METRIC, BUILD, 4>(p, nq, smem, s);
     }
 }
