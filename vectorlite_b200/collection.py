@@ -240,8 +240,8 @@ class Collection:
         save_collection_to_file(self, path)
 
     @staticmethod
-    def load_from_file(path: str, device: int = 0) -> "Collection":
-        return load_collection_from_file(path, device)
+    def load_from_file(path: str, device: int = 0, devices: Optional[Sequence[int]] = None) -> "Collection":
+        return load_collection_from_file(path, device, devices)
 
 
 class MicroBatcher:
@@ -295,11 +295,29 @@ class MicroBatcher:
 
 
 # ---- VectorLiteClient (client.rs:65-192) ----------------------------------------------------------------
+def make_index(dim: int, index_type: IndexType, metric: Optional[SimilarityMetric], device: int = 0,
+               devices: Optional[Sequence[int]] = None, shard_rows: int = 1 << 20):
+    """Shard-aware index construction: with `devices` (more than one entry) a Flat collection is row-sharded over
+    them and an HNSW collection keeps one replica per device (multi_gpu.py); otherwise one index on `device`."""
+    if devices is not None and len(devices) > 1:
+        from .multi_gpu import MultiGpuFlatIndex, MultiGpuHnswIndex
+        if index_type == IndexType.Flat:
+            return MultiGpuFlatIndex(dim, devices, shard_rows=shard_rows)
+        return MultiGpuHnswIndex(dim, metric, devices)
+    dev = devices[0] if devices else device
+    if index_type == IndexType.Flat:
+        return FlatIndex(dim, device=dev)
+    return HNSWIndex(dim, metric, device=dev)
+
+
 class VectorLiteClient:
-    def __init__(self, embedding_function: EmbeddingFunction, device: int = 0):
+    def __init__(self, embedding_function: EmbeddingFunction, device: int = 0,
+                 devices: Optional[Sequence[int]] = None, shard_rows: int = 1 << 20):
         self._collections: Dict[str, Collection] = {}
         self._ef = embedding_function
         self._device = device
+        self._devices = list(devices) if devices else None
+        self._shard_rows = shard_rows
         self._lock = threading.Lock()
 
     def create_collection(self, name: str, index_type: IndexType, metric: Optional[SimilarityMetric] = None) -> None:
@@ -307,12 +325,9 @@ class VectorLiteClient:
             if name in self._collections:
                 raise CollectionAlreadyExists(name)                      # client.rs:84-86
             dim = self._ef.dimension()
-            if index_type == IndexType.Flat:
-                index = FlatIndex(dim, device=self._device)
-            else:
-                if metric is None:                                       # client.rs:92-97
-                    raise InvalidRequest("HNSW index requires a similarity metric")
-                index = HNSWIndex(dim, metric, device=self._device)
+            if index_type != IndexType.Flat and metric is None:          # client.rs:92-97
+                raise InvalidRequest("HNSW index requires a similarity metric")
+            index = make_index(dim, index_type, metric, self._device, self._devices, self._shard_rows)
             self._collections[name] = Collection(name, index)
 
     def get_collection(self, name: str) -> Optional[Collection]:
@@ -370,7 +385,7 @@ def _now() -> str:
 def collection_to_document(collection: Collection) -> dict:
     """CollectionData::from_collection (persistence.rs:101-123) in serde's JSON shape."""
     idx = collection.index_read()
-    if isinstance(idx, HNSWIndex):
+    if idx.index_type() == IndexType.HNSW:
         eids, rows = idx.export()
         ids = [int(i) for i in eids]
         vals, meta = {}, {}
@@ -407,7 +422,8 @@ def save_collection_to_file(collection: Collection, path: str) -> None:
     os.replace(tmp, path)                                                # atomic rename
 
 
-def load_collection_from_file(path: str, device: int = 0) -> Collection:
+def load_collection_from_file(path: str, device: int = 0, devices: Optional[Sequence[int]] = None,
+                              shard_rows: int = 1 << 20) -> Collection:
     try:
         with open(path) as f:
             doc = json.load(f)
@@ -424,7 +440,7 @@ def load_collection_from_file(path: str, device: int = 0) -> Collection:
     (kind, body), = doc["index"].items()
     if kind == "Flat":
         data = body["data"]
-        index = FlatIndex(int(body["dim"]), device=device)
+        index = make_index(int(body["dim"]), IndexType.Flat, None, device, devices, shard_rows)
         if data:                                                         # ONE bulk upload into the device arena
             ids = np.array([d["id"] for d in data], dtype=np.uint64)
             rows = np.array([d["values"] for d in data], dtype=np.float32)
@@ -432,7 +448,7 @@ def load_collection_from_file(path: str, device: int = 0) -> Collection:
     elif kind == "HNSW":
         if int(body["dim"]) == 0:
             raise PersistenceError("Invalid dimension: cannot be 0")      # hnsw.rs:288-290
-        index = HNSWIndex(int(body["dim"]), SimilarityMetric[body["metric"]], device=device)
+        index = make_index(int(body["dim"]), IndexType.HNSW, SimilarityMetric[body["metric"]], device, devices)
         vv = body["vector_values"]
         if vv:                                                           # hnsw.rs:322-348 re-inserts every vector
             keys = sorted(vv, key=int)                                   # (deterministic order here; HashMap order there)
