@@ -185,6 +185,21 @@ int vl_index_search_exchange(vl_index* h, vl_exchange* x, const float* d_queries
                              int metric, uint64_t* d_out_ids, double* d_out_scores, uint64_t* d_out_pos,
                              uint32_t* d_out_counts, uint32_t* d_out_flags, void* cuda_stream);
 
+/* ---- shard group: a flat store row-sharded over several handles of ONE process ----------------------
+ * The reference's server is a single process whose Collection owns one index (src/client.rs:243-247); on a
+ * multi-GPU box it owns a group of flat handles, one per device.  Shard g holds the contiguous storage-order
+ * range [base_g, base_g + n_g) (the caller routes inserts: bulk loads split evenly, appends to the shard that
+ * owns the tail), so merging the per-shard top-k lists by a STABLE sort in shard order reproduces the stable
+ * sort of flat.rs:116 over the whole store (score desc, insertion order asc).  vl_group_search runs
+ * vl_index_search on every non-empty shard concurrently (host buffers in, host results out, same outputs and
+ * errors as vl_index_search) and is re-entrant like it.  The group borrows the handles: destroy it first. */
+typedef struct vl_group vl_group;
+int vl_group_create(vl_index* const* shards, uint32_t n, vl_group** out);
+void vl_group_destroy(vl_group* g);
+uint32_t vl_group_size(const vl_group* g);
+int vl_group_search(vl_group* g, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                    uint64_t* out_ids, double* out_scores, uint32_t* out_counts);
+
 /* ---- accessors ------------------------------------------------------------------------ */
 uint64_t vl_index_len(const vl_index* h);          /* VectorIndex::len */
 uint32_t vl_index_dim(const vl_index* h);          /* VectorIndex::dimension */

@@ -142,6 +142,10 @@ def lib():
         "vl_exchange_connect": (i32, [vp, vp]),
         "vl_exchange_connect_local": (i32, [C.POINTER(vp), u32]),
         "vl_index_search_exchange": (i32, [vp, vp, vp, u32, u32, i32, vp, vp, vp, vp, vp, vp]),
+        "vl_group_create": (i32, [C.POINTER(vp), u32, C.POINTER(vp)]),
+        "vl_group_destroy": (None, [vp]),
+        "vl_group_size": (u32, [vp]),
+        "vl_group_search": (i32, [vp, fp, u32, u32, u32, i32, u64p, dp, u32p]),
         "vl_index_len": (u64, [vp]),
         "vl_index_dim": (u32, [vp]),
         "vl_index_type_of": (i32, [vp]),

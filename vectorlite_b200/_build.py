@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libvectorlite_cuda.so")
 SOURCES = ["api.cu", "flat_scan.cu", "flat_finalize.cu", "exact.cu", "arena.cu", "batch_scan.cu",
-           "batch_tc.cu", "hnsw_host.cpp", "hnsw_search.cu", "hnsw_build.cu", "exchange.cu"]
+           "batch_tc.cu", "hnsw_host.cpp", "hnsw_search.cu", "hnsw_build.cu", "exchange.cu", "group.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-pthread", "--expt-relaxed-constexpr"]
 

@@ -628,6 +628,11 @@ static int flat_search_impl(vl_index* h, const float* queries, uint32_t nq, uint
 
 }  // namespace
 
+namespace vl {
+// for the host-only translation units of the library (group.cpp): sets the calling thread's vl_last_error()
+void set_last_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
+}  // namespace vl
+
 // =========================================================================================
 extern "C" {
 

@@ -1,0 +1,181 @@
+// group.cpp — a flat store ROW-SHARDED over several handles of one process (one per GPU) searched as ONE index.
+//
+// The reference is a single-process server: `Collection` owns one index behind an RwLock and calls
+// VectorIndex::search from its worker threads (src/client.rs:243-247,398).  On a multi-GPU box the CUDA-backed
+// collection owns a shard group instead: shard g holds the contiguous storage-order range [base_g, base_g + n_g)
+// (SURVEY §8e), every shard answers the query exactly (certified, f64 scores), and the per-shard top-k lists are
+// merged by a STABLE sort in shard order — score descending, global insertion order ascending, the tie-break of
+// flat.rs:116.  Routing of inserts / deletes to shards is host bookkeeping above the ABI (multi_gpu.py; the Rust
+// shim in INTEGRATION.md).
+//
+// Fan-out: the calling thread runs shard 0 itself and posts the other shards to a small pool of helper threads, so
+// all GPUs scan at the same time; several callers may be inside vl_group_search at once (their per-shard calls meet
+// in each handle's combiner exactly like direct callers).  Host-only code: everything on the device happens
+// inside vl_index_search.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/vectorlite_cuda.h"
+
+namespace vl {
+void set_last_error(const char* msg);   // api.cu: the thread-local string behind vl_last_error()
+}
+
+namespace {
+
+struct Call {
+    const float* queries;
+    uint32_t nq, qdim, k;
+    int metric;
+    std::vector<std::vector<uint64_t>> ids;      // [shard][nq*k]
+    std::vector<std::vector<double>> scores;
+    std::vector<std::vector<uint32_t>> counts;   // [shard][nq]
+    std::vector<int> rc;
+    std::vector<std::string> err;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint32_t remaining = 0;
+};
+
+struct Task {
+    Call* call;
+    uint32_t shard;
+};
+
+}  // namespace
+
+struct vl_group {
+    std::vector<vl_index*> shards;
+    uint32_t dim = 0;
+    std::vector<std::thread> helpers;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Task> queue;
+    bool stop = false;
+
+    void run_shard(Call* c, uint32_t s) {
+        c->ids[s].resize(static_cast<size_t>(c->nq) * c->k);
+        c->scores[s].resize(static_cast<size_t>(c->nq) * c->k);
+        c->counts[s].assign(c->nq, 0u);
+        c->rc[s] = vl_index_search(shards[s], c->queries, c->nq, c->qdim, c->k, c->metric, 0u, c->ids[s].data(),
+                                   c->scores[s].data(), c->counts[s].data());
+        if (c->rc[s] != VL_OK) c->err[s] = vl_last_error();
+    }
+
+    void helper_loop() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !queue.empty(); });
+                if (queue.empty()) return;   // stop
+                t = queue.front();
+                queue.pop_front();
+            }
+            run_shard(t.call, t.shard);
+            std::lock_guard<std::mutex> lk(t.call->mu);
+            if (--t.call->remaining == 0) t.call->cv.notify_one();
+        }
+    }
+};
+
+extern "C" {
+
+int vl_group_create(vl_index* const* shards, uint32_t n, vl_group** out) {
+    if (!out) { vl::set_last_error("out is null"); return VL_ERR_INVALID; }
+    *out = nullptr;
+    if (!shards || n == 0) { vl::set_last_error("a shard group needs at least one index"); return VL_ERR_INVALID; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!shards[i] || vl_index_type_of(shards[i]) != VL_INDEX_FLAT || vl_index_dim(shards[i]) != vl_index_dim(shards[0])) {
+            vl::set_last_error("every shard must be a flat index of the same dimension");
+            return VL_ERR_INVALID;
+        }
+    }
+    vl_group* g = new (std::nothrow) vl_group();
+    if (!g) { vl::set_last_error("host allocation failed"); return VL_ERR_OOM; }
+    g->shards.assign(shards, shards + n);
+    g->dim = vl_index_dim(shards[0]);
+    // helpers: enough for a few concurrent callers to have all their shards in flight
+    const uint32_t n_helpers = n > 1 ? std::min<uint32_t>(64u, (n - 1) * 8u) : 0u;
+    for (uint32_t i = 0; i < n_helpers; ++i) g->helpers.emplace_back([g] { g->helper_loop(); });
+    *out = g;
+    return VL_OK;
+}
+
+void vl_group_destroy(vl_group* g) {   // the shards stay alive: they belong to the caller
+    if (!g) return;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->stop = true;
+    }
+    g->cv.notify_all();
+    for (auto& t : g->helpers) t.join();
+    delete g;
+}
+
+uint32_t vl_group_size(const vl_group* g) { return g ? static_cast<uint32_t>(g->shards.size()) : 0u; }
+
+int vl_group_search(vl_group* g, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                    uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
+    if (!g || !out_ids || !out_scores || !out_counts || (!queries && nq)) {
+        vl::set_last_error("null argument");
+        return VL_ERR_INVALID;
+    }
+    for (size_t i = 0; i < static_cast<size_t>(nq) * k; ++i) { out_ids[i] = ~0ull; out_scores[i] = 0.0; }
+    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0u;
+    // shards that hold rows; flat.rs:99-104: the dimension is only checked when the store is non-empty
+    std::vector<uint32_t> live;
+    for (uint32_t s = 0; s < g->shards.size(); ++s)
+        if (vl_index_len(g->shards[s]) > 0) live.push_back(s);
+    if (live.empty() || nq == 0 || k == 0) return VL_OK;
+    if (live.size() == 1)
+        return vl_index_search(g->shards[live[0]], queries, nq, qdim, k, metric, 0u, out_ids, out_scores, out_counts);
+
+    const uint32_t S = static_cast<uint32_t>(g->shards.size());
+    Call c;
+    c.queries = queries; c.nq = nq; c.qdim = qdim; c.k = k; c.metric = metric;
+    c.ids.resize(S); c.scores.resize(S); c.counts.resize(S); c.rc.assign(S, VL_OK); c.err.resize(S);
+    c.remaining = static_cast<uint32_t>(live.size()) - 1;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        for (size_t i = 1; i < live.size(); ++i) g->queue.push_back(Task{&c, live[i]});
+    }
+    g->cv.notify_all();
+    g->run_shard(&c, live[0]);
+    {
+        std::unique_lock<std::mutex> lk(c.mu);
+        c.cv.wait(lk, [&] { return c.remaining == 0; });
+    }
+    for (uint32_t s : live)
+        if (c.rc[s] != VL_OK) {   // every shard sees the same query: report the first failure (dimension, NaN, …)
+            vl::set_last_error(c.err[s].c_str());
+            return c.rc[s];
+        }
+    // stable merge in shard order == (score desc, global storage position asc)
+    struct Hit { double score; uint64_t id; };
+    std::vector<Hit> hits;
+    for (uint32_t q = 0; q < nq; ++q) {
+        hits.clear();
+        for (uint32_t s : live) {
+            const uint32_t cnt = c.counts[s][q];
+            for (uint32_t r = 0; r < cnt; ++r)
+                hits.push_back(Hit{c.scores[s][static_cast<size_t>(q) * k + r], c.ids[s][static_cast<size_t>(q) * k + r]});
+        }
+        std::stable_sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) { return a.score > b.score; });
+        const uint32_t cnt = static_cast<uint32_t>(std::min<size_t>(hits.size(), k));
+        for (uint32_t r = 0; r < cnt; ++r) {
+            out_ids[static_cast<size_t>(q) * k + r] = hits[r].id;
+            out_scores[static_cast<size_t>(q) * k + r] = hits[r].score;
+        }
+        out_counts[q] = cnt;
+    }
+    return VL_OK;
+}
+
+}  // extern "C"

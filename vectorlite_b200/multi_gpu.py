@@ -10,8 +10,8 @@ collection on an 8-GPU box owns one of these instead, and nothing above the inde
   the shard that owns the tail (the last non-empty shard, moving on when it reaches `shard_rows`); when the last
   shard is full the store is re-split evenly with 25 % headroom per shard (`rebalance`).  Deletes are
   order-preserving inside their shard (`flat.rs:93-96`, missing id = Ok).  A search runs on every shard
-  concurrently (one host thread per device; each shard's answer is already exact and certified) and the per-shard
-  top-k lists are merged on the host by a stable sort in shard order.  The multi-PROCESS deployment of the same
+  concurrently (`vl_group_search`, csrc/group.cpp; each shard's answer is already exact and certified) and the
+  per-shard top-k lists are merged on the host by a stable sort in shard order.  The multi-PROCESS deployment of the same
   layout, with the exchange fused into the kernels over NVLink peer memory, is `sharded.ShardedFlatIndex`.
 * `MultiGpuHnswIndex` — HNSW does not shard (a graph traversal is sequential per query and partitioning the graph
   changes recall): one full REPLICA per device, mutations applied to all, queries split across the replicas.
@@ -26,7 +26,10 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from . import (DimensionMismatch, FlatIndex, HNSWIndex, IndexType, SearchResult, SimilarityMetric, Vector)
+import ctypes as C
+
+from . import (VL_ERR_DIM, VL_OK, DimensionMismatch, FlatIndex, HNSWIndex, IndexType, SearchResult, SimilarityMetric,
+               Vector, VectorLiteError, _err, _ptr, lib)
 
 _NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
 
@@ -49,7 +52,8 @@ class MultiGpuFlatIndex:
         self._meta: Dict[int, tuple] = {}         # id -> (text, metadata): gathered for the hits only
         self._tail = 0                            # shard that owns the tail of the storage order
         self._pool = ThreadPoolExecutor(max_workers=len(self._shards))
-        self._rr = 0
+        self._L = lib()
+        self._grp = None
         if data:
             self.add_batch(np.array([v.id for v in data], dtype=np.uint64),
                            np.array([np.asarray(v.values, dtype=np.float32) for v in data], dtype=np.float32),
@@ -57,9 +61,26 @@ class MultiGpuFlatIndex:
 
     # -- lifecycle / shape -------------------------------------------------------------------------------------
     def close(self) -> None:
+        self._drop_group()
         for s in self._shards:
             s.close()
         self._pool.shutdown(wait=False)
+
+    def _group(self):
+        """The vl_group over the current shard handles (re-created after a re-split replaces them)."""
+        if self._grp is None:
+            arr = (C.c_void_p * len(self._shards))(*[s.handle for s in self._shards])
+            g = C.c_void_p()
+            st = self._L.vl_group_create(arr, len(self._shards), C.byref(g))
+            if st != VL_OK:
+                raise VectorLiteError(st, _err())
+            self._grp = g
+        return self._grp
+
+    def _drop_group(self) -> None:
+        if self._grp is not None:
+            self._L.vl_group_destroy(self._grp)
+            self._grp = None
 
     def num_shards(self) -> int:
         return len(self._shards)
@@ -185,6 +206,7 @@ class MultiGpuFlatIndex:
         ids, rows = self.export()
         per = -(-ids.shape[0] // len(self._devices))
         self._shard_rows = max(self._shard_rows, int(per * (1.0 + headroom)) + 1)
+        self._drop_group()                       # it borrows the handles that are about to be replaced
         for s in self._shards:
             s.close()
         self._shards = [FlatIndex(self._dim, device=d) for d in self._devices]
@@ -209,22 +231,16 @@ class MultiGpuFlatIndex:
         out_ids = np.full((nq, k), _NONE, dtype=np.uint64)
         out_sc = np.zeros((nq, k), dtype=np.float64)
         out_cnt = np.zeros(nq, dtype=np.uint32)
-        live = [s for s in self._shards if s.len() > 0]
-        if not live or k == 0 or nq == 0:
+        if self.is_empty() or k == 0 or nq == 0:
             return out_ids, out_sc, out_cnt
-        if len(live) == 1:
-            return live[0].search_batch(q, k, similarity_metric, ef)
-        parts = [f.result() for f in [self._pool.submit(s.search_batch, q, k, similarity_metric, ef) for s in live]]
-        ids_all = np.concatenate([p[0] for p in parts], axis=1)               # [nq, S*k], shard order
-        sc_all = np.concatenate([p[1] for p in parts], axis=1)
-        valid = np.concatenate([np.arange(k)[None, :] < p[2][:, None] for p in parts], axis=1)
-        key = np.where(valid, -sc_all, np.inf)                                 # invalid slots sort last
-        order = np.argsort(key, axis=1, kind="stable")[:, :k]
-        cnt = np.minimum(valid.sum(axis=1), k).astype(np.uint32)
-        take = np.arange(k)[None, :] < cnt[:, None]
-        out_ids[take] = np.take_along_axis(ids_all, order, axis=1)[take]
-        out_sc[take] = np.take_along_axis(sc_all, order, axis=1)[take]
-        return out_ids, out_sc, cnt
+        # vl_group_search: every non-empty shard searched concurrently, stable merge in shard order (csrc/group.cpp)
+        st = self._L.vl_group_search(self._group(), _ptr(q, C.c_float), nq, qdim, k, int(similarity_metric),
+                                     _ptr(out_ids, C.c_uint64), _ptr(out_sc, C.c_double), _ptr(out_cnt, C.c_uint32))
+        if st == VL_ERR_DIM:
+            raise DimensionMismatch(self._dim, qdim, _err())
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        return out_ids, out_sc, out_cnt
 
     def search(self, query, k: int, similarity_metric: SimilarityMetric, ef: int = 0) -> List[SearchResult]:
         ids, scores, counts = self.search_batch(np.asarray(query, dtype=np.float32)[None, :], k, similarity_metric, ef)
