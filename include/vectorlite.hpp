@@ -152,6 +152,88 @@ public:
     IndexType index_type() const { return IndexType::HNSW; }
 };
 
+// A flat store row-sharded over several devices of ONE process behind the same trait: shard g holds
+// the contiguous storage-order range [base_g, base_g + n_g); appends go to the shard that owns the tail and move
+// on when it holds `shard_rows` rows (the last shard keeps growing; vectorlite_b200/multi_gpu.py adds the even
+// re-split); searches run on every shard at once through vl_group_search, whose stable merge in shard order is
+// the stable sort of flat.rs:116 over the whole store.
+class ShardedFlatIndex : public VectorIndex {
+    std::vector<std::unique_ptr<FlatIndex>> shards_;
+    std::unordered_map<uint64_t, size_t> where_;   // id -> shard
+    vl_group* group_ = nullptr;
+    size_t dim_, shard_rows_, tail_ = 0;
+
+public:
+    ShardedFlatIndex(size_t dim, const std::vector<int>& devices, size_t shard_rows = size_t(1) << 20)
+        : dim_(dim), shard_rows_(shard_rows ? shard_rows : 1) {
+        if (devices.empty()) throw std::invalid_argument("at least one device is required");
+        std::vector<vl_index*> hs;
+        for (int d : devices) {
+            shards_.push_back(std::make_unique<FlatIndex>(dim, std::vector<Vector>{}, d));
+            hs.push_back(shards_.back()->handle());
+        }
+        if (vl_group_create(hs.data(), static_cast<uint32_t>(hs.size()), &group_) != VL_OK)
+            throw VectorLiteError(VL_ERR_INVALID, vl_last_error());
+    }
+    ShardedFlatIndex(const ShardedFlatIndex&) = delete;
+    ShardedFlatIndex& operator=(const ShardedFlatIndex&) = delete;
+    ~ShardedFlatIndex() override { vl_group_destroy(group_); }   // before the shards it borrows
+
+    void add(const Vector& v) override {
+        if (v.values.size() != dim_) throw std::runtime_error("Vector dimension mismatch");          // flat.rs:84
+        if (where_.count(v.id)) throw std::runtime_error("Vector ID " + std::to_string(v.id) + " already exists");  // flat.rs:87
+        while (tail_ + 1 < shards_.size() && shards_[tail_]->len() >= shard_rows_) ++tail_;
+        shards_[tail_]->add(v);
+        where_[v.id] = tail_;
+    }
+    void remove(uint64_t id) override {                          // flat.rs:93-96: missing id is Ok
+        auto it = where_.find(id);
+        if (it == where_.end()) return;
+        shards_[it->second]->remove(id);
+        where_.erase(it);
+    }
+    std::vector<SearchResult> search(const std::vector<double>& q, size_t k, SimilarityMetric m) const override {
+        std::vector<float> qf(q.begin(), q.end());
+        std::vector<uint64_t> ids(k);
+        std::vector<double> scores(k);
+        uint32_t count = 0;
+        const int st = vl_group_search(group_, qf.data(), 1, static_cast<uint32_t>(qf.size()), static_cast<uint32_t>(k),
+                                       static_cast<int>(m), ids.data(), scores.data(), &count);
+        if (st == VL_ERR_DIM) throw DimensionMismatch(dim_, q.size());
+        if (st != VL_OK) throw VectorLiteError(st, vl_last_error());
+        std::vector<SearchResult> out(count);
+        for (uint32_t i = 0; i < count; ++i) {
+            auto v = shards_[where_.at(ids[i])]->get_vector(ids[i]);   // text / metadata live with the owning shard
+            out[i].id = ids[i];
+            out[i].score = scores[i];
+            if (v) { out[i].text = v->text; out[i].metadata = v->metadata; }
+        }
+        return out;
+    }
+    size_t len() const override { return where_.size(); }
+    std::optional<Vector> get_vector(uint64_t id) const override {
+        auto it = where_.find(id);
+        if (it == where_.end()) return std::nullopt;
+        return shards_[it->second]->get_vector(id);
+    }
+    size_t dimension() const override { return dim_; }
+    std::optional<uint64_t> max_id() const {
+        std::optional<uint64_t> best;
+        for (const auto& s : shards_) {
+            auto m = s->max_id();
+            if (m && (!best || *m > *best)) best = m;
+        }
+        return best;
+    }
+    std::vector<size_t> shard_sizes() const {
+        std::vector<size_t> out;
+        for (const auto& s : shards_) out.push_back(s->len());
+        return out;
+    }
+    std::optional<SimilarityMetric> metric() const { return std::nullopt; }
+    IndexType index_type() const { return IndexType::Flat; }
+};
+
 class VectorIndexWrapper {  // src/lib.rs:270-346
     std::unique_ptr<CudaIndex> idx_;
     IndexType type_;

@@ -38,6 +38,24 @@ int main() {
         r = d.search({1, 2}, 2, SimilarityMetric::DotProduct);
         CHECK(r[0].id == 1 && r[0].score == 5.0 && r[1].score == 4.0);
     }
+    {   // the same trait over a store row-sharded across devices of one process (three shards on device 0 here)
+        ShardedFlatIndex sh(3, {0, 0, 0}, 2);
+        const double rows[7][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 0}, {1, 1, 0}, {0, 0, 1}, {0, 1, 0}};
+        for (uint64_t i = 0; i < 7; ++i) sh.add({i + 10, {rows[i][0], rows[i][1], rows[i][2]}, "t" + std::to_string(i), {}});
+        auto sizes = sh.shard_sizes();
+        CHECK(sizes[0] == 2 && sizes[1] == 2 && sizes[2] == 3 && sh.len() == 7 && *sh.max_id() == 16);
+        auto r = sh.search({0.0, 1.0, 0.0}, 4, SimilarityMetric::Cosine);   // ids 11, 13, 16 tie at 1.0 across all three shards
+        CHECK(r.size() == 4 && r[0].id == 11 && r[1].id == 13 && r[2].id == 16 && r[3].id == 14 && r[0].score == 1.0 && r[1].text == "t3");
+        bool threw = false;
+        try { sh.add({13, {1, 2, 3}, "", {}}); } catch (const std::runtime_error& e) { threw = std::strstr(e.what(), "already exists") != nullptr; }
+        CHECK(threw);
+        sh.remove(13); sh.remove(999);
+        r = sh.search({0.0, 1.0, 0.0}, 2, SimilarityMetric::Cosine);
+        CHECK(r.size() == 2 && r[0].id == 11 && r[1].id == 16 && !sh.get_vector(13) && sh.get_vector(16)->values[1] == 1.0);
+        threw = false;
+        try { sh.search({1.0, 0.0}, 1, SimilarityMetric::Cosine); } catch (const DimensionMismatch& e) { threw = e.expected == 3 && e.actual == 2; }
+        CHECK(threw);
+    }
     {   // hnsw.rs:605-662
         HNSWIndex h(3, SimilarityMetric::Euclidean);
         CHECK(h.is_empty() && h.dimension() == 3);
