@@ -475,7 +475,7 @@ def main():
     e2e_steps = max(2, args.steps // 4)
     e2e_single = time_e2e(step_e2e)
     e2e_qps, e2e_callers = e2e_single, 1
-    e2e_python_callers, e2e_impl = None, "python threads (ctypes)"
+    e2e_python_callers, e2e_impl, e2e_single_python = None, "python threads (ctypes)", None
     if world == 1:
         # E2E_CALLERS threads issue the steps' single-query searches back to back (a shared cursor, no barrier
         # between steps); every call is still one query in host memory → one result in host memory
@@ -511,6 +511,9 @@ def main():
         if nat is not None:
             assert np.array_equal(nat[1], want_ids) and np.array_equal(nat[2].view(np.uint64), want_sc.view(np.uint64))
             e2e_qps, e2e_impl = nat[0], "native host threads (scripts/native_callers.cpp)"
+            # a lone native caller: the C-ABI latency without the Python wrapper's allocations
+            e2e_single_python = e2e_single
+            e2e_single = native_callers(idx.local, queries[:QUERIES_PER_STEP], k, metric, 0, 1, 8 * QUERIES_PER_STEP)[0]
 
     # ---- extras: other metrics, batched (B=1024) tensor-core / CUDA-core pipelines ---------------------
     extras = {}
@@ -616,7 +619,7 @@ def main():
                     "h2d_bytes_per_step": QUERIES_PER_STEP * DIM * 4,
                     "d2h_bytes_per_step": QUERIES_PER_STEP * (k * 16 + 8),
                     "callers": e2e_callers, "callers_impl": e2e_impl, "python_callers_value": e2e_python_callers,
-                    "single_caller_value": e2e_single,
+                    "single_caller_value": e2e_single, "python_single_caller_value": e2e_single_python,
                     "bf16_retries": idx.local.stats()["bf16_retries"],
                     "api": "vl_index_search (host buffers in, host results out), one query per call; concurrent callers on a "
                            "handle are combined into batched launches by the handle (csrc/api.cu flat_search)"},

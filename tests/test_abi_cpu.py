@@ -69,3 +69,16 @@ def test_invalid_arguments(vl):
     assert L.vl_flat_create(3, 0, None) == vl.VL_ERR_INVALID
     assert L.vl_index_len(None) == 0
     L.vl_index_destroy(None)                                             # no-op, must not crash
+
+
+def test_shard_group_argument_checks(vl):
+    """vl_group_* (the single-process shard group) rejects null / empty input without touching a device."""
+    L = vl.lib()
+    g = C.c_void_p()
+    assert L.vl_group_create(None, 0, C.byref(g)) == vl.VL_ERR_INVALID and not g.value
+    assert b"at least one" in L.vl_last_error()
+    arr = (C.c_void_p * 1)(None)
+    assert L.vl_group_create(arr, 1, C.byref(g)) == vl.VL_ERR_INVALID
+    assert L.vl_group_create(arr, 1, None) == vl.VL_ERR_INVALID
+    assert L.vl_group_size(None) == 0
+    L.vl_group_destroy(None)                                             # no-op, must not crash
