@@ -778,6 +778,17 @@ static int create_common(uint32_t dim, int device, vl_index** out, int type) {
     }
     h->max_grid_x = std::min(flat_scan_max_grid_x(device, h->pitch), SCAN_CAP);
     h->max_grid_x_bf16 = std::min(flat_scan_bf16_max_grid_x(device), SCAN_CAP);
+    {
+        // The persistent scan grid leaves a few CTA slots FREE: a full wave (2 x 124 registers x 256 threads per SM)
+        // fills the register file, so the finalize CTA of query i (and a sharded search's merge CTA, which waits
+        // for its peers) would otherwise hold back one scan CTA of query i+1 — and with equal shares per CTA the
+        // whole scan.  Measured in a pipelined stream at 1M x 384 (profiles/r01_grid_trim.txt): trim 0 / 1 / 2 / 4 / 8
+        // = 7937 / 8302 / 8583 / 8721 / 8655 q/s (bf16 mirror), 4224 / 4447 / 4495 / 4556 / 4509 (fp32 arena).
+        const char* e = getenv("VL_SCAN_GRID_TRIM");
+        const int t = e ? std::max(0, atoi(e)) : 4;
+        h->max_grid_x = std::max(1, h->max_grid_x - t);
+        h->max_grid_x_bf16 = std::max(1, h->max_grid_x_bf16 - t);
+    }
     *out = h;
     return VL_OK;
 }
