@@ -41,18 +41,21 @@ class MultiGpuFlatIndex:
     MIN_SPLIT_ROWS = 4096     # a bulk load is not split below this many rows per shard
 
     def __init__(self, dim: int, devices: Sequence[int], shard_rows: int = 1 << 20,
-                 data: Optional[Sequence[Vector]] = None):
+                 data: Optional[Sequence[Vector]] = None, shard_factory=None):
+        """`shard_factory(dim, device)` builds one shard (default: a `FlatIndex` on that device); the CPU tests of
+        the routing bookkeeping pass a stand-in, searches always go through the real handles."""
         if not devices:
             raise ValueError("at least one device is required")
         self._dim = int(dim)
         self._devices = [int(d) for d in devices]
-        self._shards: List[FlatIndex] = [FlatIndex(dim, device=d) for d in self._devices]
+        self._make = shard_factory or (lambda dim_, dev: FlatIndex(dim_, device=dev))
+        self._shards: List[FlatIndex] = [self._make(self._dim, d) for d in self._devices]
         self._shard_rows = max(1, int(shard_rows))
         self._where: Dict[int, int] = {}          # id -> shard
         self._meta: Dict[int, tuple] = {}         # id -> (text, metadata): gathered for the hits only
         self._tail = 0                            # shard that owns the tail of the storage order
         self._pool = ThreadPoolExecutor(max_workers=len(self._shards))
-        self._L = lib()
+        self._L = None                            # the C ABI, loaded with the first search
         self._grp = None
         if data:
             self.add_batch(np.array([v.id for v in data], dtype=np.uint64),
@@ -68,6 +71,8 @@ class MultiGpuFlatIndex:
 
     def _group(self):
         """The vl_group over the current shard handles (re-created after a re-split replaces them)."""
+        if self._L is None:
+            self._L = lib()
         if self._grp is None:
             arr = (C.c_void_p * len(self._shards))(*[s.handle for s in self._shards])
             g = C.c_void_p()
@@ -209,7 +214,7 @@ class MultiGpuFlatIndex:
         self._drop_group()                       # it borrows the handles that are about to be replaced
         for s in self._shards:
             s.close()
-        self._shards = [FlatIndex(self._dim, device=d) for d in self._devices]
+        self._shards = [self._make(self._dim, d) for d in self._devices]
         self._where.clear()
         self._tail = 0
         meta, self._meta = self._meta, {}
@@ -234,7 +239,8 @@ class MultiGpuFlatIndex:
         if self.is_empty() or k == 0 or nq == 0:
             return out_ids, out_sc, out_cnt
         # vl_group_search: every non-empty shard searched concurrently, stable merge in shard order (csrc/group.cpp)
-        st = self._L.vl_group_search(self._group(), _ptr(q, C.c_float), nq, qdim, k, int(similarity_metric),
+        grp = self._group()
+        st = self._L.vl_group_search(grp, _ptr(q, C.c_float), nq, qdim, k, int(similarity_metric),
                                      _ptr(out_ids, C.c_uint64), _ptr(out_sc, C.c_double), _ptr(out_cnt, C.c_uint32))
         if st == VL_ERR_DIM:
             raise DimensionMismatch(self._dim, qdim, _err())
