@@ -269,6 +269,10 @@ def run_reference(args):
         cpu_flat_qps(oracle, rows, queries[off:off + nq], args.k, metric, threads)
     dt = time.perf_counter() - t0
     qps = nq * args.steps / dt
+    # outside the timed steps: the same search with the reference's per-row String clone (flat.rs:111-112, a 16-byte
+    # text per row) and on ONE thread (the reference's own per-query behaviour) — SURVEY §8d brackets
+    qps_clone, _, _ = cpu_flat_qps(oracle, rows, queries[:nq], args.k, metric, threads, clone_bytes=16)
+    qps_1t, _, _ = cpu_flat_qps(oracle, rows, queries[:1], args.k, metric, 1)
     line = {
         "impl": "reference", "metric": "flat_1m_384d_k10_qps", "value": qps,
         "unit": "queries/s x 1M-row shards", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -281,7 +285,8 @@ def run_reference(args):
                    "note": "reference is Rust (no toolchain here): C++ oracle restatement of "
                            "flat.rs:98-119 + lib.rs:425-572, -O2 -ffp-contract=off"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": f"{nq * args.steps} queries over the full {n}-row store"},
+                         "sample": f"{nq * args.steps} queries over the full {n}-row store",
+                         "with_16B_text_clone_per_row_qps": qps_clone, "single_thread_qps": qps_1t},
         "e2e": {"value": qps, "unit": "queries/s x 1M-row shards", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
