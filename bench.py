@@ -135,6 +135,20 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def device_synth_rows(vl, seed, first_row, n, device):
+    """[n, DIM] f32 synthetic rows `first_row …` of stream `seed` from the PRODUCT's own counter-based generator
+    (vl_index_fill_synthetic; bit-identical to the oracle's synth_rows, tests/test_flat_gpu.py
+    test_device_generator_matches_oracle), so the measured arm does not need oracle/ for its inputs."""
+    src = vl.FlatIndex(DIM, device=device)
+    try:
+        src.fill_synthetic(seed, n, first_row=first_row)
+        rows = np.ascontiguousarray(src.export()[1], dtype=np.float32)
+    finally:
+        src.close()
+    assert rows.shape == (n, DIM)
+    return rows
+
+
 def cpu_flat_qps(oracle, rows, queries, k, metric, threads, clone_bytes=0):
     t0 = time.perf_counter()
     st, ids, _ = oracle.flat_search_batch(rows, None, queries, k, metric, nthreads=threads, clone_bytes=clone_bytes)
@@ -358,10 +372,8 @@ def main():
     assert idx.local.len() == n_shard
     idx.local.set_pipelined(True)   # PDL: scan of query i+1 overlaps the rescore/certify kernel of query i
 
-    import oracle  # checker + cpu_baseline leg only (never on the measured GPU path)
-    oracle.build()
     nq_pool = QUERIES_PER_STEP
-    queries = oracle.synth_rows(43, 0, nq_pool, DIM)
+    queries = device_synth_rows(vl, 43, 0, nq_pool, local_rank)   # the measured arm never touches oracle/
     d_queries = torch.from_numpy(queries).to(dev)
 
     def barrier():
@@ -542,7 +554,7 @@ def main():
             "algorithmic_bytes_per_launch": f32_bytes, "traffic": f32_tr}
         idx.local.set_mode(vl.Mode.Auto)
         B = 1024
-        bq = oracle.synth_rows(43, 1000, B, DIM)
+        bq = device_synth_rows(vl, 43, 1000, B, local_rank)
         d_bq = torch.from_numpy(bq).to(dev)
         tc_peak = None
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -573,6 +585,8 @@ def main():
     # ---- CPU baseline + sampled oracle check (rank 0, N = 1 only) ----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle  # the checker / CPU baseline: the only leg of this arm that executes anything under oracle/
+        oracle.build()
         threads = cpu_threads()
         rows = synth_host_rows(oracle, 42, n_shard, DIM, threads)
         nq_cpu = max(3 * threads, 4)   # ≈ 20-25 s of CPU work at 1M rows (0.5 s per query per thread)
