@@ -82,3 +82,18 @@ def test_shard_group_argument_checks(vl):
     assert L.vl_group_create(arr, 1, None) == vl.VL_ERR_INVALID
     assert L.vl_group_size(None) == 0
     L.vl_group_destroy(None)                                             # no-op, must not crash
+
+
+def test_bench_measured_arm_uses_oracle_only_as_checker():
+    """bench.py: the only code of the measured arm (`main`) that names `oracle` is the cpu_baseline leg — the
+    inputs come from the product's generator, the reference arm lives in run_reference()."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    main = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "main")
+    leg = next(n for n in ast.walk(main) if isinstance(n, ast.If) and "no_cpu_baseline" in ast.unparse(n.test))
+    inside = {id(n) for n in ast.walk(leg)}
+    stray = [n.lineno for n in ast.walk(main)
+             if ((isinstance(n, ast.Name) and n.id == "oracle") or
+                 (isinstance(n, ast.Import) and any(a.name == "oracle" for a in n.names))) and id(n) not in inside]
+    assert not stray, f"bench.py main() touches oracle outside the cpu_baseline leg at lines {stray}"
