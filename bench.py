@@ -261,6 +261,35 @@ def hnsw_section(vl, n, efc, device, nq=4096, k=10, clusters=1024):
                     "asserted in tests/test_hnsw_gpu.py"}
 
 
+def hnsw_reference_cpu(oracle, threads, n=10_000, efc=400, clusters=1024, nq=512, k=10):
+    """The reference's HNSW search on the host cores: the oracle restatement of crate hnsw 0.11 + the u64
+    milli-unit functors (hnsw.rs:113-174,415-496) on the bench's mixture data.  Bounded: the restated insert is
+    single-threaded like the reference's (≈ 40 s for 10K rows at ef_construction = 400), so the graph is small;
+    the 1M-row figures of the CUDA index are in the other arm's `hnsw` block."""
+    rows = oracle.synth_rows(42, 0, n, DIM, clusters)
+    q = oracle.synth_rows(43, 0, nq, DIM, clusters)
+    st, truth, _ = oracle.flat_search_batch(rows, None, q, k, 0, nthreads=threads)
+    assert st == 0
+    h = oracle.HNSW(DIM, 0, 16, 32, efc)
+    t0 = time.perf_counter()
+    h.add_batch(None, rows)
+    build_s = time.perf_counter() - t0
+    sweep = {}
+    for ef in (0, 64):
+        rec = {}
+        for th in (1, threads):
+            t0 = time.perf_counter()
+            st, ri, _, rc, vis = h.search_batch(q, k, ef, nthreads=th)
+            dt = time.perf_counter() - t0
+            rec[f"qps_{th}_threads" if th > 1 else "qps_1_thread"] = nq / dt
+        hit = sum(len(set(map(int, ri[i, :rc[i]])) & set(map(int, truth[i]))) for i in range(nq))
+        rec.update({"recall_at_10": hit / (nq * k), "visited_per_query": vis / nq})
+        sweep[str(ef)] = rec
+    return {"rows": n, "dim": DIM, "data": f"synthetic {clusters}-centre mixture, unit norm", "M": 16, "M0": 32,
+            "ef_construction": efc, "k": k, "queries": nq, "build_seconds_1_thread": build_s, "host_threads": threads,
+            "sweep": sweep, "kind": "port (restatement of the crate's published algorithm; graph parity unpinned)"}
+
+
 def run_reference(args):
     """The reference arm: CPU only, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -287,6 +316,9 @@ def run_reference(args):
     # text per row) and on ONE thread (the reference's own per-query behaviour) — SURVEY §8d brackets
     qps_clone, _, _ = cpu_flat_qps(oracle, rows, queries[:nq], args.k, metric, threads, clone_bytes=16)
     qps_1t, _, _ = cpu_flat_qps(oracle, rows, queries[:1], args.k, metric, 1)
+    hnsw_ref = None
+    if args.hnsw_rows > 0:
+        hnsw_ref = hnsw_reference_cpu(oracle, threads)
     line = {
         "impl": "reference", "metric": "flat_1m_384d_k10_qps", "value": qps,
         "unit": "queries/s x 1M-row shards", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -304,6 +336,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s x 1M-row shards", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "hnsw": hnsw_ref,
     }
     emit(line)
 
@@ -606,6 +639,14 @@ def main():
             hnsw = hnsw_section(vl, args.hnsw_rows, args.hnsw_efc, local_rank)
         except Exception as e:  # noqa: BLE001 — the headline line must still be printed
             hnsw = {"error": repr(e)}
+        try:   # the size the reference arm's CPU restatement is timed on (hnsw_reference_cpu): same data, same ef
+            hnsw_small = hnsw_section(vl, 10_000, args.hnsw_efc, local_rank, nq=512)
+            hnsw_small.pop("reference_restatement_recall", None)
+            if isinstance(hnsw, dict):
+                hnsw["same_size_as_reference_arm"] = hnsw_small
+        except Exception as e:  # noqa: BLE001
+            if isinstance(hnsw, dict):
+                hnsw["same_size_as_reference_arm"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
