@@ -97,3 +97,29 @@ def test_bench_measured_arm_uses_oracle_only_as_checker():
              if ((isinstance(n, ast.Name) and n.id == "oracle") or
                  (isinstance(n, ast.Import) and any(a.name == "oracle" for a in n.names))) and id(n) not in inside]
     assert not stray, f"bench.py main() touches oracle outside the cpu_baseline leg at lines {stray}"
+
+
+def test_rust_bindings_name_only_exported_symbols(vl):
+    """rust/vectorlite-cuda-sys/src/lib.rs (the extern "C" crate of INTEGRATION.md; cannot be compiled here) binds
+    only functions the header declares and the library exports, with the declared number of arguments."""
+    L = vl.lib()
+    hdr = open(os.path.join(ROOT, "include", "vectorlite_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = {m.group(1): m.group(2) for m in re.finditer(r"\b(vl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
+    rs = open(os.path.join(ROOT, "rust", "vectorlite-cuda-sys", "src", "lib.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    bound = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (vl_[a-z0-9_]+)\s*\(([^)]*)\)", rs, flags=re.S)}
+    assert len(bound) >= 18
+
+    def nargs(a):
+        a = a.strip()
+        return 0 if a in ("", "void") else a.count(",") + 1
+
+    for name, args in bound.items():
+        assert name in declared, f"{name} is bound in Rust but not declared in the header"
+        assert hasattr(L, name), f"{name} is bound in Rust but not exported"
+        assert nargs(args) == nargs(declared[name]), (name, args, declared[name])
+    # the shim in INTEGRATION.md / rust/vectorlite-src-index/cuda.rs calls only what the sys crate binds
+    shim = open(os.path.join(ROOT, "rust", "vectorlite-src-index", "cuda.rs")).read()
+    for name in set(re.findall(r"sys::(vl_[a-z0-9_]+)\s*\(", shim)):
+        assert name in bound, f"cuda.rs calls sys::{name}, which the sys crate does not bind"
