@@ -17,7 +17,7 @@ struct BatchTensor {      // bf16 mirror of the arena for the tcgen05 path (batc
     const void* rows_bf16 = nullptr;   // [n][pitch] bf16 (cosine: rows pre-scaled by 1/‖row‖)
     const void* rows_bf16_raw = nullptr;  // [n][pitch] bf16, unscaled (dot, L2)
     const float* sq_norm = nullptr;    // [n] ‖row‖² fp32 (L2 via ‖x‖²+‖q‖²−2x·q)
-    double tc_abs = 0.0040;            // certificate: |approx − exact| <= tc_abs·‖x‖·‖q‖
+    double tc_abs = 0.0040;            // certificate: |approx − exact| <= tc_abs·‖x‖·‖q‖ (see rescore.cuh for what it covers)
     void* scratch = nullptr;           // TcState*
 };
 

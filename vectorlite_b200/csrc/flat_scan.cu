@@ -13,7 +13,7 @@
 //     chunk c, the same elements as the fp32 layout, so the query registers are identical); bf16 → fp32 is a
 //     shift / mask, accumulation is fp32 against the fp32 query.  Scores are in the tensor-core path's scan
 //     units (cos·‖q‖, x·q, −‖x−q‖² via 2x·q − ‖x‖² − ‖q‖²) and are certified with the same bf16 bound; L1 is
-//     −Σ|x̃−q| directly, certified with Σ|x̃−x| <= 2^-9·‖x‖₁ <= 2^-9·√dim·max‖row‖.
+//     −Σ|x̃−q| directly, certified with Σ|x̃−x| <= 2^-8·‖x‖₁ <= 2^-8·√dim·max‖row‖.
 // The query lives in registers; per-lane partial sums are reduced with a transposed butterfly; each row's
 // fp32 score becomes a 64-bit key (score, ~position) and is appended to a CTA candidate buffer only if it
 // beats the running threshold.  The exact f64 score and the final order are produced by flat_finalize.cu.

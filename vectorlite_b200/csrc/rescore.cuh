@@ -103,8 +103,14 @@ __device__ __forceinline__ void rank_and_certify(const FinalizeParams& p, uint32
             const double kth = s_kth;
             bool ok;
             if (p.tc_abs > 0.0) {
-                // bf16 inputs: x̃ = x(1+δ), |δ| <= 2^-9 each side → |Σx̃q̃ − Σxq| <= (2^-8+2^-18)·‖x‖‖q‖,
-                // plus fp32 accumulation in the tensor core; tc_abs covers both with margin.
+                // bf16 round-to-nearest: x̃ = x(1+δ), |δ| <= 2^-8 in the worst case (an element just above a power
+                // of two), ~2^-9.5 RMS.  Single-query mirror scans round ONE operand (fp32 query):
+                // |Σx̃q − Σxq| <= 2^-8·‖x‖‖q‖ = 0.00391, + fp32 accumulation (pitch·2^-24) < tc_abs = 0.0040: rigorous.
+                // The tensor-core batches round BOTH operands: tc_abs then covers 2× the RMS-level error
+                // ((E_x + E_q)·‖x‖‖q‖ with E = ‖x̃−x‖/‖x‖ ≈ 0.0011 on real-valued data) but not the adversarial
+                // 2^-7 worst case of every element sitting on a rounding boundary with aligned signs; the
+                // measured-norm form of the bound (E_x from the mirror build, E_q per query) is the next step
+                // (DESIGN.md §3, §10).
                 const double qn = *s_qnorm;
                 const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
                 if (p.metric == COSINE) {       // rows pre-normalised: scan units are cos·‖q‖
@@ -112,11 +118,11 @@ __device__ __forceinline__ void rank_and_certify(const FinalizeParams& p, uint32
                 } else if (p.metric == DOT) {
                     ok = kth > worst + p.tc_abs * maxn * qn + 1e-30;
                 } else if (p.metric == MANHATTAN) {
-                    // −Σ|x̃−q| with fp32 query: rounding the rows moves the sum by at most Σ|x̃−x| <= 2^-9·‖x‖₁
-                    // <= 2^-9·√dim·‖x‖ (Cauchy–Schwarz); the fp32 sum of non-negative terms adds a RELATIVE
-                    // (nn+2)·u on top.  Every excluded row therefore has exact Σ|x−q| >= L.
+                    // −Σ|x̃−q| with fp32 query: rounding the rows moves the sum by at most Σ|x̃−x| <= 2^-8·‖x‖₁
+                    // <= 2^-8·√dim·‖x‖ (worst-case bf16 rounding, Cauchy–Schwarz); the fp32 sum of non-negative
+                    // terms adds a RELATIVE (nn+2)·u on top.  Every excluded row therefore has exact Σ|x−q| >= L.
                     double L = (-worst) * (1.0 - (nn + 2.0) * u * 1.01) -
-                               0.001953125 * 1.01 * sqrt(static_cast<double>(p.dim)) * maxn - 1e-30;
+                               0.00390625 * 1.01 * sqrt(static_cast<double>(p.dim)) * maxn - 1e-30;
                     L = L > 0.0 ? L * (1.0 - 1e-12) : 0.0;
                     ok = kth > sim_from_l1(L);
                 } else {                        // −‖x−q‖² from ‖x‖² + ‖q‖² − 2x·q
