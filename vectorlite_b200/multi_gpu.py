@@ -57,6 +57,7 @@ class MultiGpuFlatIndex:
         self._pool = ThreadPoolExecutor(max_workers=len(self._shards))
         self._L = None                            # the C ABI, loaded with the first search
         self._grp = None
+        self._grp_lock = threading.Lock()
         if data:
             self.add_batch(np.array([v.id for v in data], dtype=np.uint64),
                            np.array([np.asarray(v.values, dtype=np.float32) for v in data], dtype=np.float32),
@@ -71,15 +72,18 @@ class MultiGpuFlatIndex:
 
     def _group(self):
         """The vl_group over the current shard handles (re-created after a re-split replaces them)."""
-        if self._L is None:
-            self._L = lib()
-        if self._grp is None:
-            arr = (C.c_void_p * len(self._shards))(*[s.handle for s in self._shards])
-            g = C.c_void_p()
-            st = self._L.vl_group_create(arr, len(self._shards), C.byref(g))
-            if st != VL_OK:
-                raise VectorLiteError(st, _err())
-            self._grp = g
+        if self._grp is not None:
+            return self._grp
+        with self._grp_lock:                      # searches are re-entrant (read lock): create the group once
+            if self._L is None:
+                self._L = lib()
+            if self._grp is None:
+                arr = (C.c_void_p * len(self._shards))(*[s.handle for s in self._shards])
+                g = C.c_void_p()
+                st = self._L.vl_group_create(arr, len(self._shards), C.byref(g))
+                if st != VL_OK:
+                    raise VectorLiteError(st, _err())
+                self._grp = g
         return self._grp
 
     def _drop_group(self) -> None:
