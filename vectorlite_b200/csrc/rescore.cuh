@@ -106,8 +106,9 @@ __device__ __forceinline__ void rank_and_certify(const FinalizeParams& p, uint32
                 // bf16 round-to-nearest: x̃ = x(1+δ), |δ| <= 2^-8 in the worst case (an element just above a power
                 // of two), ~2^-9.5 RMS.  Single-query mirror scans round ONE operand (fp32 query):
                 // |Σx̃q − Σxq| <= 2^-8·‖x‖‖q‖ = 0.00391, + fp32 accumulation (pitch·2^-24) < tc_abs = 0.0040: rigorous.
-                // The tensor-core batches round BOTH operands: tc_abs then covers 2× the RMS-level error
-                // ((E_x + E_q)·‖x‖‖q‖ with E = ‖x̃−x‖/‖x‖ ≈ 0.0011 on real-valued data) but not the adversarial
+                // The tensor-core batches round BOTH operands: tc_abs then covers the Cauchy–Schwarz bound
+                // (E_x + E_q + E_x·E_q)·‖x‖‖q‖ for the error norms real-valued data has (E = ‖x̃−x‖/‖x‖ ≈ 0.0017, so
+                // ≈ 0.0033), but not the adversarial
                 // 2^-7 worst case of every element sitting on a rounding boundary with aligned signs; the
                 // measured-norm form of the bound (E_x from the mirror build, E_q per query) is the next step
                 // (DESIGN.md §3, §10).
