@@ -123,3 +123,12 @@ def test_rust_bindings_name_only_exported_symbols(vl):
     shim = open(os.path.join(ROOT, "rust", "vectorlite-src-index", "cuda.rs")).read()
     for name in set(re.findall(r"sys::(vl_[a-z0-9_]+)\s*\(", shim)):
         assert name in bound, f"cuda.rs calls sys::{name}, which the sys crate does not bind"
+
+
+def test_prepared_patches_still_apply():
+    """experiments/*.patch (compile-checked changes waiting for GPU validation) apply to the current tree."""
+    import glob
+    import subprocess
+    for patch in sorted(glob.glob(os.path.join(ROOT, "experiments", "*.patch"))):
+        r = subprocess.run(["git", "apply", "--check", patch], cwd=ROOT, capture_output=True, text=True)
+        assert r.returncode == 0, (patch, r.stderr)
