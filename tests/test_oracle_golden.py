@@ -221,3 +221,25 @@ def test_synth_rows_properties(oracle_mod):
     assert abs(float(a.mean())) < 0.01 and abs(float(a.std()) - 1 / math.sqrt(384)) < 0.005
     c = oracle_mod.synth_rows(43, 0, 64, 384)
     assert not np.array_equal(a, c)
+
+
+def test_bench_reference_arm_helpers_run_on_cpu(oracle_mod):
+    """bench.py's reference-arm legs (CPU only): the flat baseline with its clone / single-thread brackets and the
+    restated-HNSW block, on a tiny store."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vl_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rows = bench.synth_host_rows(oracle_mod, 42, 3000, bench.DIM, 2)
+    assert np.array_equal(rows, oracle_mod.synth_rows(42, 0, 3000, bench.DIM))
+    q = oracle_mod.synth_rows(43, 0, 4, bench.DIM)
+    qps, dt, ids = bench.cpu_flat_qps(oracle_mod, rows, q, 10, 0, 2)
+    qps_c, _, ids_c = bench.cpu_flat_qps(oracle_mod, rows, q, 10, 0, 2, clone_bytes=16)
+    assert qps > 0 and qps_c > 0 and np.array_equal(ids, ids_c) and ids.shape == (4, 10)
+    h = bench.hnsw_reference_cpu(oracle_mod, 2, n=600, efc=40, clusters=16, nq=32)
+    assert h["rows"] == 600 and set(h["sweep"]) == {"0", "64"}
+    for rec in h["sweep"].values():
+        assert 0.0 <= rec["recall_at_10"] <= 1.0 and rec["qps_1_thread"] > 0 and rec["qps_2_threads"] > 0
+    assert h["sweep"]["64"]["recall_at_10"] >= h["sweep"]["0"]["recall_at_10"]
