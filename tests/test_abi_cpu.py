@@ -132,3 +132,13 @@ def test_prepared_patches_still_apply():
     for patch in sorted(glob.glob(os.path.join(ROOT, "experiments", "*.patch"))):
         r = subprocess.run(["git", "apply", "--check", patch], cwd=ROOT, capture_output=True, text=True)
         assert r.returncode == 0, (patch, r.stderr)
+
+
+def test_adversarial_rounding_counter_example_arithmetic():
+    """experiments/adversarial_bf16_rounding.py: the arithmetic of the input on which a constant 0.0040 bound with BOTH
+    operands rounded certifies a wrong top-k while the measured-norm bound refuses (DESIGN.md §3 caveat)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vl_adv", os.path.join(ROOT, "experiments", "adversarial_bf16_rounding.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.cpu_demo()
