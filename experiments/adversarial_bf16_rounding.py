@@ -1,6 +1,7 @@
-"""A constructed input on which the tensor-core batched path's CONSTANT bf16 bound (tc_abs = 0.0040·‖x‖‖q‖, both
-operands rounded) certifies a wrong top-k — and on which the measured-norm bound of
-experiments/measured_norm_certificate.patch refuses the certificate (→ exact path → right answer).  DESIGN.md §3.
+"""A constructed input on which a constant bf16 bound of 0.0040·‖x‖‖q‖ with BOTH operands rounded (the tensor-core
+batched path's constant until the end of round 1) certifies a wrong top-k — and on which the worst-case constant
+0.0079 now in csrc/batch.h, like the measured-norm bound of experiments/measured_norm_certificate.patch, refuses the
+certificate (→ exact path → right answer).  DESIGN.md §3.
 
 Dot product, d = 384.  Every element of the query q and of row A is u = 1 + 2^-8 − 2^-20, which bf16 rounds DOWN to
 1.0 (relative error ≈ −2^-8 on both operands → −2^-7 on A·q).  Rows C (10 of them) and B (≥ 54) are bf16-exact mixes
@@ -9,8 +10,7 @@ of 1.0 and 1.0078125 whose exact scores lie just below A's, while their approxim
 so A — the true best row — is not among the K' = 64 kept rows, and kth_exact(C) > worst_approx(B) + 0.004·‖x‖max‖q‖.
 
   python experiments/adversarial_bf16_rounding.py          # CPU: the arithmetic of the counter-example
-  python experiments/adversarial_bf16_rounding.py gpu      # GPU: batched search vs oracle (expected to DIFFER on
-                                                           # the unpatched tree, to AGREE with the patch applied)
+  python experiments/adversarial_bf16_rounding.py gpu      # GPU: batched search vs oracle (must AGREE)
 """
 import os
 import sys
@@ -55,8 +55,10 @@ def cpu_demo():
     print(f"approx A {ap(a):.3f}  C {ap(c):.3f}  B {ap(b):.3f}")
     print("A excluded by the approximate scan:", ap(a) < worst, "| A is the true best row:", ex(a) > kth)
     print("constant bound 0.0040 certifies:", kth > worst + 0.0040 * maxn * qn)
+    print("worst-case constant 0.0079 certifies:", kth > worst + 0.0079 * maxn * qn)
     print(f"measured bound {measured:.5f} certifies:", kth > worst + measured * maxn * qn)
-    assert ap(a) < worst and ex(a) > kth and kth > worst + 0.0040 * maxn * qn and not kth > worst + measured * maxn * qn
+    assert ap(a) < worst and ex(a) > kth and kth > worst + 0.0040 * maxn * qn
+    assert not kth > worst + measured * maxn * qn and not kth > worst + 0.0079 * maxn * qn
 
 
 def gpu_check():
@@ -71,7 +73,7 @@ def gpu_check():
     print("oracle ids ", list(map(int, oi)))
     print("device ids ", list(map(int, gi[0])), "stats", idx.stats())
     same = list(map(int, gi[0])) == list(map(int, oi))
-    print("AGREE" if same else "DIFFER (the constant bound certified a top-k without row %d)" % pos_a)
+    print("AGREE" if same else "DIFFER (a certificate passed for a top-k without row %d)" % pos_a)
     return same
 
 

@@ -502,7 +502,8 @@ static int launch_single_queries(vl_index* h, const FlatView& v, const float* dq
         CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
         h->prof_n += 1;
     }
-    CU(launch_flat_finalize(v, dq, m, k, metric, ws, out, 1.0f, stream, mirror ? BatchTensor().tc_abs : 0.0));
+    // mirror scans round ONE operand (the rows; the query stays fp32): 2^-8 + pitch·2^-24 < 0.0040 (rescore.cuh)
+    CU(launch_flat_finalize(v, dq, m, k, metric, ws, out, 1.0f, stream, mirror ? 0.0040 : 0.0));
     h->stats[ST_LAUNCHES] += 2;
     if (mirror) h->stats[ST_BF16_SCANS] += m;
     if (used_bf16) *used_bf16 = mirror != nullptr;

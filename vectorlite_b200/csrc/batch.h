@@ -17,7 +17,9 @@ struct BatchTensor {      // bf16 mirror of the arena for the tcgen05 path (batc
     const void* rows_bf16 = nullptr;   // [n][pitch] bf16 (cosine: rows pre-scaled by 1/‖row‖)
     const void* rows_bf16_raw = nullptr;  // [n][pitch] bf16, unscaled (dot, L2)
     const float* sq_norm = nullptr;    // [n] ‖row‖² fp32 (L2 via ‖x‖²+‖q‖²−2x·q)
-    double tc_abs = 0.0040;            // certificate: |approx − exact| <= tc_abs·‖x‖·‖q‖ (see rescore.cuh for what it covers)
+    // certificate: |approx − exact| <= tc_abs·‖x‖·‖q‖.  BOTH operands are rounded to bf16 here (worst case 2^-8
+    // relative per element, each side): (1 + 2^-8)² − 1 = 0.0078278, + K·2^-23 for the fp32 accumulation → 0.0079.
+    double tc_abs = 0.0079;
     void* scratch = nullptr;           // TcState*
 };
 

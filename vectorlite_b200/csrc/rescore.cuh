@@ -105,13 +105,11 @@ __device__ __forceinline__ void rank_and_certify(const FinalizeParams& p, uint32
             if (p.tc_abs > 0.0) {
                 // bf16 round-to-nearest: x̃ = x(1+δ), |δ| <= 2^-8 in the worst case (an element just above a power
                 // of two), ~2^-9.5 RMS.  Single-query mirror scans round ONE operand (fp32 query):
-                // |Σx̃q − Σxq| <= 2^-8·‖x‖‖q‖ = 0.00391, + fp32 accumulation (pitch·2^-24) < tc_abs = 0.0040: rigorous.
-                // The tensor-core batches round BOTH operands: tc_abs then covers the Cauchy–Schwarz bound
-                // (E_x + E_q + E_x·E_q)·‖x‖‖q‖ for the error norms real-valued data has (E = ‖x̃−x‖/‖x‖ ≈ 0.0017, so
-                // ≈ 0.0033), but not the adversarial
-                // 2^-7 worst case of every element sitting on a rounding boundary with aligned signs; the
-                // measured-norm form of the bound (E_x from the mirror build, E_q per query) is the next step
-                // (DESIGN.md §3, §10).
+                // |Σx̃q − Σxq| <= 2^-8·‖x‖‖q‖ = 0.00391, + fp32 accumulation (pitch·2^-24) < tc_abs = 0.0040.
+                // The tensor-core batches round BOTH operands: |Σx̃q̃ − Σxq| <= ((1+2^-8)² − 1)·‖x‖‖q‖ = 0.00783,
+                // + K·2^-23 for the accumulation < tc_abs = 0.0079.  Both are worst-case bounds (every element on a
+                // rounding boundary, aligned signs: experiments/adversarial_bf16_rounding.py); the measured-norm form
+                // (E_x + E_q + E_x·E_q ≈ 0.0034 on real-valued data) would halve the batched one.
                 const double qn = *s_qnorm;
                 const double maxn = sqrt(__longlong_as_double(p.stats->max_norm_sq_bits));
                 if (p.metric == COSINE) {       // rows pre-normalised: scan units are cos·‖q‖
