@@ -107,6 +107,9 @@ int vl_hnsw_build_info(const vl_index* h, uint64_t* out_builder, uint64_t* out_m
  * (hnsw.rs:113-174) / 1000 (hnsw.rs:478) through convert_distance_to_similarity (hnsw.rs:51-75), bit for bit,
  * including its second division by 1000 for cosine and dot product; results ordered by that score. */
 int vl_hnsw_set_score_mode(vl_index* h, int mode);
+/* Device beam width of a search = factor x ef, where ef is the reference's ef (hnsw.rs:437: min(k, len), or the
+ * `ef` argument of vl_index_search when > 0).  1 = equal ef.  Range [1, 64]. */
+int vl_hnsw_set_beam_factor(vl_index* h, uint32_t factor);
 /* Structural audit of the graph (all levels): out6 = nodes, layer-0 edges, self loops, duplicate edges,
  * invalid targets (out of range / absent from the level / after a gap), isolated layer-0 nodes. */
 int vl_hnsw_graph_check(const vl_index* h, uint64_t* out6);
@@ -126,13 +129,17 @@ int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdi
 int vl_index_search_f64(vl_index* h, const double* queries, uint32_t nq, uint32_t qdim, uint32_t k,
                         int metric, uint32_t ef, uint64_t* out_ids, double* out_scores,
                         uint32_t* out_counts);
-/* Same computation with DEVICE-resident queries [nq][dim] and DEVICE outputs, enqueued on
- * `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) without host synchronisation.
+/* Same computation with DEVICE-resident queries [nq][dim] (dense, as the host API takes them; when dim is not
+ * a multiple of 4 they are repacked on the stream into a zero-padded staging buffer at the arena pitch) and
+ * DEVICE outputs, enqueued on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) without host
+ * synchronisation.
  * d_out_pos (may be NULL) receives storage positions (+ the handle's position base, see
  * vl_index_set_pos_base) — what a row-sharded merge tie-breaks on.  d_out_flags[q]: bit0 = the
  * optimality certificate failed (caller must re-run that query through vl_index_search or in
  * VL_MODE_EXACT), bit1 = non-finite fp32 score seen, bit2 = NaN similarity, bit3 = candidate buffer
- * overflow (implies bit0), bit4 = a peer shard's results did not arrive (vl_index_search_exchange). */
+ * overflow (implies bit0), bit4 = a peer shard's results did not arrive (vl_index_search_exchange; treat like
+ * bit0: the merged list is incomplete).  No retry happens here: the host API (vl_index_search) moves a failing
+ * query through larger over-selections, the fp32 arena and finally the exact path by itself. */
 int vl_index_search_device(vl_index* h, const float* d_queries, uint32_t nq, uint32_t k, int metric,
                            uint32_t ef, uint64_t* d_out_ids, double* d_out_scores,
                            uint64_t* d_out_pos, uint32_t* d_out_counts, uint32_t* d_out_flags,
@@ -223,7 +230,10 @@ int vl_index_set_pos_base(vl_index* h, uint64_t base);
  * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited,
  * [6] single-query scans served from the bf16 mirror of the rows (AUTO mode, 128/256/384-d, all four metrics),
  * [7] single-query host searches that were combined with concurrent callers into a batched launch,
- * [8] mirror scans whose certificate did not hold under the bf16 bound and were re-run on the fp32 arena. */
+ * [8] queries whose certificate did not hold after a bf16 scan (mirror / tensor cores) and that were re-run at the
+ *     next level (larger over-selection K', then the fp32 arena, then the exact path),
+ * [9] queries re-run on the fp32 arena, [10] queries served at the boosted over-selection from the start (the
+ *     handle remembers data whose top-k gaps are below the bf16 bound). */
 int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n);
 /* Pipelined device searches (flat, vl_index_search_device only).  When enabled, consecutive searches
  * enqueued on one stream overlap through programmatic dependent launch: the scan of search i+1

@@ -82,6 +82,12 @@ def _load():
     L.vlo_hnsw_num_layers.argtypes = [C.c_void_p]
     L.vlo_hnsw_layer_len.restype = C.c_size_t
     L.vlo_hnsw_layer_len.argtypes = [C.c_void_p, C.c_size_t]
+    L.vlo_hnsw_export_zero.restype = None
+    L.vlo_hnsw_export_zero.argtypes = [C.c_void_p, u64p]
+    L.vlo_hnsw_export_layer.restype = None
+    L.vlo_hnsw_export_layer.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, u64p]
+    L.vlo_hnsw_strict_evals.restype = C.c_uint64
+    L.vlo_hnsw_strict_evals.argtypes = [C.c_void_p]
     L.vlo_hnsw_levels.restype = None
     L.vlo_hnsw_levels.argtypes = [C.c_size_t, C.c_size_t, u32p]
     L.vlo_synth_rows_f32.restype = None
@@ -216,6 +222,23 @@ class HNSW:
                                                _p(oi, C.c_uint64), _p(os_, C.c_double),
                                                _p(cnts, C.c_uint32), C.byref(vis))
         return st, oi, os_, cnts, vis.value
+
+    def export_zero(self, M0: int):
+        n = self.layer_len(0)
+        out = np.zeros((n, M0), dtype=np.uint64)
+        self._L.vlo_hnsw_export_zero(self._h, _p(out, C.c_uint64))
+        return out
+
+    def export_layer(self, l: int, M: int):
+        n = self.layer_len(l)
+        zn = np.zeros(n, dtype=np.uint64)
+        nn = np.zeros(n, dtype=np.uint64)
+        nb = np.zeros((n, M), dtype=np.uint64)
+        self._L.vlo_hnsw_export_layer(self._h, l, _p(zn, C.c_uint64), _p(nn, C.c_uint64), _p(nb, C.c_uint64))
+        return zn, nn, nb
+
+    def strict_evals(self):
+        return self._L.vlo_hnsw_strict_evals(self._h)
 
     def num_layers(self):
         return self._L.vlo_hnsw_num_layers(self._h)

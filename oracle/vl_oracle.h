@@ -93,6 +93,11 @@ int vlo_hnsw_search_batch_f32(const vlo_hnsw* h, const float* queries, size_t nq
 /* graph introspection for tests */
 size_t vlo_hnsw_num_layers(const vlo_hnsw* h);           /* upper layers */
 size_t vlo_hnsw_layer_len(const vlo_hnsw* h, size_t l);  /* l=0 → zero layer */
+/* layer-0 adjacency [len][M0], empty slot = UINT64_MAX; upper layer l >= 1 */
+void vlo_hnsw_export_zero(const vlo_hnsw* h, uint64_t* out);
+void vlo_hnsw_export_layer(const vlo_hnsw* h, size_t l, uint64_t* zero_node, uint64_t* next_node, uint64_t* nb);
+/* distances that fell inside the guard band of the accelerated functors and were decided by the strict ones */
+uint64_t vlo_hnsw_strict_evals(const vlo_hnsw* h);
 /* first n levels drawn by the crate's random_level() for a given M (ChaCha12, zero seed) */
 void vlo_hnsw_levels(size_t M, size_t n, uint32_t* out_levels);
 

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <unordered_map>
@@ -72,6 +73,91 @@ inline uint64_t distance(int metric, const double* a, const double* b, size_t n)
         default: return dist_dot(a, b, n);
     }
 }
+
+// ---- Accelerated evaluation of the SAME functors (results identical to the functions above) ----
+// The restated insert evaluates ~10^4-10^5 distances per row at ef_construction = 400, each a serial
+// f64 chain (~0.6 us at 384-d); a 1M-row fixture would take days.  The functors only expose
+// floor(v * 1000) of a real value v.  `fast_*` evaluates the sums with 8 independent accumulators
+// (vectorisable); re-association moves an f64 sum of <= 4096 products by < 1e-12 relative to
+// sum|terms|, i.e. the pre-floor value by < 1e-8 for |v|*1000 < 1e4.  If the fast value lies further
+// than GUARD from every integer (and from the clamp / zero edges), the strict left-to-right
+// evaluation has the same floor and the fast result is returned; otherwise the strict functor is
+// evaluated.  Either way the returned u64 is exactly what `distance()` returns
+// (tests/test_oracle_golden.py::test_hnsw_fast_functors_identical compares whole graphs).
+constexpr double GUARD = 1e-6;
+
+#define VLO_FAST_ATTR __attribute__((optimize("O3"), target_clones("avx2", "default")))
+
+typedef double v4d __attribute__((vector_size(32)));
+typedef float v4f __attribute__((vector_size(16)));
+inline __attribute__((always_inline)) v4d load4(const double* p) { v4d v; std::memcpy(&v, p, 32); return v; }
+inline __attribute__((always_inline)) v4d load4(const float* p) { v4f v; std::memcpy(&v, p, 16); return __builtin_convertvector(v, v4d); }
+inline __attribute__((always_inline)) double hsum(v4d a, v4d b) { const v4d t = a + b; return (t[0] + t[1]) + (t[2] + t[3]); }
+
+template <class TA, class TB>
+inline __attribute__((always_inline)) void sums3(const TA* a, const TB* b, size_t n, double& dot, double& aa, double& bb) {
+    v4d d0 = {0, 0, 0, 0}, d1 = d0, p0 = d0, p1 = d0, q0 = d0, q1 = d0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const v4d x0 = load4(a + i), y0 = load4(b + i), x1 = load4(a + i + 4), y1 = load4(b + i + 4);
+        d0 += x0 * y0; p0 += x0 * x0; q0 += y0 * y0;
+        d1 += x1 * y1; p1 += x1 * x1; q1 += y1 * y1;
+    }
+    dot = hsum(d0, d1); aa = hsum(p0, p1); bb = hsum(q0, q1);
+    for (; i < n; ++i) {
+        const double x = static_cast<double>(a[i]), y = static_cast<double>(b[i]);
+        dot += x * y; aa += x * x; bb += y * y;
+    }
+}
+// kind 0: sum (a-b)^2, 1: sum |a-b|, 2: sum a*b
+template <int KIND, class TA, class TB>
+inline __attribute__((always_inline)) double sum1(const TA* a, const TB* b, size_t n) {
+    v4d d0 = {0, 0, 0, 0}, d1 = d0;
+    size_t i = 0;
+    auto term = [](v4d x, v4d y) -> v4d {
+        if (KIND == 0) { const v4d t = x - y; return t * t; }
+        if (KIND == 1) { const v4d t = x - y; return t < 0 ? -t : t; }
+        return x * y;
+    };
+    for (; i + 8 <= n; i += 8) {
+        d0 += term(load4(a + i), load4(b + i));
+        d1 += term(load4(a + i + 4), load4(b + i + 4));
+    }
+    double r = hsum(d0, d1);
+    for (; i < n; ++i) {
+        const double x = static_cast<double>(a[i]), y = static_cast<double>(b[i]);
+        r += KIND == 0 ? (x - y) * (x - y) : KIND == 1 ? std::fabs(x - y) : x * y;
+    }
+    return r;
+}
+
+// pre-floor value of the functor from fast sums; returns false when the strict functor must decide
+template <class TA, class TB>
+inline __attribute__((always_inline)) bool fast_value(int metric, const TA* a, const TB* b, size_t n, double& v) {
+    switch (metric) {
+        case VLO_EUCLIDEAN: v = std::sqrt(sum1<0>(a, b, n)) * 1000.0; break;
+        case VLO_MANHATTAN: v = sum1<1>(a, b, n) * 1000.0; break;
+        case VLO_COSINE: {
+            double dot, aa, bb;
+            sums3(a, b, n, dot, aa, bb);
+            if (!(aa > 1e-300) || !(bb > 1e-300)) return false;
+            v = (1.0 - dot / (std::sqrt(aa) * std::sqrt(bb))) * 1000.0;
+            break;
+        }
+        default: {
+            const double dot = sum1<2>(a, b, n);
+            if (!(std::fabs(dot) < 999.0)) return false;  // near / beyond the clamp
+            v = 1000.0 - dot;
+            break;
+        }
+    }
+    if (!(v > GUARD) || !(v < 1e9)) return false;      // NaN, <= 0 edge, huge
+    const double f = v - std::floor(v);
+    return f > GUARD && f < 1.0 - GUARD;
+}
+VLO_FAST_ATTR bool fast_value_dd(int metric, const double* a, const double* b, size_t n, double& v) { return fast_value(metric, a, b, n, v); }
+VLO_FAST_ATTR bool fast_value_df(int metric, const double* a, const float* b, size_t n, double& v) { return fast_value(metric, a, b, n, v); }
+VLO_FAST_ATTR bool fast_value_ff(int metric, const float* a, const float* b, size_t n, double& v) { return fast_value(metric, a, b, n, v); }
 
 // ---- rand 0.8.5 StdRng == ChaCha12Rng (rand_chacha 0.3), from_seed([0u8;32]):
 // 64-bit block counter in words 12-13, stream 0; BlockRng yields the u32 words of
@@ -148,6 +234,10 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
     size_t dim, M, M0, efc;
     int metric;
     std::vector<double> features;               // [n][dim]
+    std::vector<float> features32;              // same values when every inserted row is f32-representable
+    bool all32 = true;                          // (then the fast functors read half the bytes)
+    bool fast = true;                           // VLO_HNSW_STRICT=1 disables the accelerated evaluation
+    mutable uint64_t strict_evals = 0;          // distances the guard band sent to the strict functor
     std::vector<size_t> zero;                   // [n][M0]
     struct Layer {
         std::vector<size_t> zero_node, next_node;
@@ -159,6 +249,35 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
 
     size_t len() const { return zero.size() / M0; }
     const double* feat(size_t i) const { return features.data() + i * dim; }
+    void push_feature(const double* q) {
+        features.insert(features.end(), q, q + dim);
+        if (all32) {
+            for (size_t i = 0; i < dim && all32; ++i) all32 = static_cast<double>(static_cast<float>(q[i])) == q[i];
+            if (all32) for (size_t i = 0; i < dim; ++i) features32.push_back(static_cast<float>(q[i]));
+            else std::vector<float>().swap(features32);
+        }
+    }
+    // functor(query, stored node) and functor(stored, stored): == distance(metric, ., ., dim)
+    uint64_t dist_q(const double* q, size_t node) const {
+        if (fast) {
+            double v;
+            const bool ok = all32 ? fast_value_df(metric, q, features32.data() + node * dim, dim, v)
+                                  : fast_value_dd(metric, q, feat(node), dim, v);
+            if (ok) return static_cast<uint64_t>(v);
+            ++strict_evals;
+        }
+        return distance(metric, q, feat(node), dim);
+    }
+    uint64_t dist_nodes(size_t a, size_t b) const {
+        if (fast) {
+            double v;
+            const bool ok = all32 ? fast_value_ff(metric, features32.data() + a * dim, features32.data() + b * dim, dim, v)
+                                  : fast_value_dd(metric, feat(a), feat(b), dim, v);
+            if (ok) return static_cast<uint64_t>(v);
+            ++strict_evals;
+        }
+        return distance(metric, feat(a), feat(b), dim);
+    }
 
     size_t random_level() {
         const double uniform =
@@ -172,7 +291,7 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
     void initialize_searcher(const double* q, Searcher& s) const {
         s.clear(len());
         const size_t entry = layers.empty() ? 0 : layers.back().zero_node[0];
-        const Neighbor c{0, distance(metric, q, feat(entry), dim)};
+        const Neighbor c{0, dist_q(q, entry)};
         ++s.evals;
         s.candidates.push_back(c);
         s.nearest.push_back(c);
@@ -190,7 +309,7 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
                 const size_t neighbor = nb[j];
                 const size_t node_to_visit = layer ? layer->zero_node[neighbor] : neighbor;
                 if (!s.seen_insert(node_to_visit)) continue;  // one seen-set shared by all layers
-                const uint64_t d = distance(metric, q, feat(node_to_visit), dim);
+                const uint64_t d = dist_q(q, node_to_visit);
                 ++s.evals;
                 // partition_point(|n| n.distance <= d): ties go AFTER equals
                 const size_t pos =
@@ -221,7 +340,6 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
         size_t* tn = layer == 0 ? zero.data() + target_ix * M0
                                 : layers[layer - 1].neighbors.data() + target_ix * M;
         const size_t tz = layer == 0 ? target_ix : layers[layer - 1].zero_node[target_ix];
-        const double* tf = feat(tz);
         size_t empty_point = 0;  // partition_point(|&n| n != !0): slots fill left → right
         while (empty_point < deg && tn[empty_point] != NONE) ++empty_point;
         if (empty_point != deg) {
@@ -234,14 +352,14 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
         for (size_t ix = 0; ix < deg; ++ix) {  // min_by_key(Reverse(d)) → FIRST of the equally-worst
             const size_t n = tn[ix];
             const size_t nz = layer == 0 ? n : layers[layer - 1].zero_node[n];
-            const uint64_t d = distance(metric, tf, feat(nz), dim);
+            const uint64_t d = dist_nodes(tz, nz);
             if (!have || d > worst_d) {
                 have = true;
                 worst_d = d;
                 worst_ix = ix;
             }
         }
-        if (distance(metric, q, tf, dim) < worst_d) tn[worst_ix] = node_ix;  // strict <
+        if (dist_q(q, tz) < worst_d) tn[worst_ix] = node_ix;  // strict <
     }
 
     void create_node(const double* q, const std::vector<Neighbor>& nearest, size_t layer) {
@@ -270,7 +388,7 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
         size_t cap = level >= layers.size() ? efc : 1;
         if (len() == 0) {
             zero.insert(zero.end(), M0, NONE);
-            features.insert(features.end(), q, q + dim);
+            push_feature(q);
             while (layers.size() < level) {
                 Layer L;
                 L.zero_node.push_back(0);
@@ -296,7 +414,7 @@ struct Graph {  // hnsw::Hnsw<Met, Vec<f64>, StdRng, M, M0>
         }
         search_layer_impl(q, s, nullptr, cap);
         create_node(q, s.nearest, 0);
-        features.insert(features.end(), q, q + dim);
+        push_feature(q);
         const size_t zero_node = len() - 1;
         while (layers.size() < level) {
             Layer L;
@@ -405,6 +523,8 @@ vlo_hnsw* vlo_hnsw_create(size_t dim, int metric, size_t M, size_t M0, size_t ef
     h->g.M0 = M0;
     h->g.efc = efc ? efc : 400;  // crate default Params::ef_construction
     h->g.metric = metric;
+    const char* strict = std::getenv("VLO_HNSW_STRICT");
+    h->g.fast = !(strict && strict[0] == '1');
     return h;
 }
 void vlo_hnsw_destroy(vlo_hnsw* h) { delete h; }
@@ -495,6 +615,18 @@ size_t vlo_hnsw_layer_len(const vlo_hnsw* h, size_t l) {
     if (l == 0) return h->g.len();
     return l - 1 < h->g.layers.size() ? h->g.layers[l - 1].len() : 0;
 }
+
+/* layer-0 adjacency [len][M0] (empty slot = UINT64_MAX) and the number of guard-band fallbacks */
+void vlo_hnsw_export_zero(const vlo_hnsw* h, uint64_t* out) {
+    for (size_t i = 0; i < h->g.zero.size(); ++i) out[i] = static_cast<uint64_t>(h->g.zero[i]);
+}
+/* upper layer l (1-based): zero_node[len], next_node[len], neighbors[len][M] */
+void vlo_hnsw_export_layer(const vlo_hnsw* h, size_t l, uint64_t* zero_node, uint64_t* next_node, uint64_t* nb) {
+    const auto& L = h->g.layers[l - 1];
+    for (size_t i = 0; i < L.len(); ++i) { zero_node[i] = L.zero_node[i]; next_node[i] = L.next_node[i]; }
+    for (size_t i = 0; i < L.neighbors.size(); ++i) nb[i] = static_cast<uint64_t>(L.neighbors[i]);
+}
+uint64_t vlo_hnsw_strict_evals(const vlo_hnsw* h) { return h->g.strict_evals; }
 
 void vlo_hnsw_levels(size_t M, size_t n, uint32_t* out_levels) {
     Graph g;

@@ -36,6 +36,7 @@ extern "C" {
     // (0 = exact Flat similarity, 1 = the reference's quantised score, hnsw.rs:478 + 51-75, bit for bit)
     pub fn vl_hnsw_set_builder(h: *mut vl_index, builder: c_int) -> c_int;
     pub fn vl_hnsw_set_score_mode(h: *mut vl_index, mode: c_int) -> c_int;
+    pub fn vl_hnsw_set_beam_factor(h: *mut vl_index, factor: u32) -> c_int;
     pub fn vl_last_error() -> *const c_char;
 }
 

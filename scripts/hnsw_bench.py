@@ -25,11 +25,17 @@ t = time.time(); h.add_batch(ids, rows); h.build(); build_s = time.time() - t
 out = {"n": n, "clusters": clusters, "M": M, "M0": M0, "ef_construction": efc, "nq": nq, "build_seconds": build_s,
        "builder": h.build_info(), "graph": h.graph_check(), "build_threads": os.cpu_count(), "flat_exact_batch_seconds": t_flat, "sweep": {}}
 print("built in", build_s, flush=True)
-for ef in (0, 16, 32, 64, 128, 256):
-    h.search_batch(queries[:256], k, metric, ef)
-    t = time.time(); gi, gs, gc = h.search_batch(queries, k, metric, ef); dt = time.time() - t
-    hit = sum(len(set(map(int, gi[i, :gc[i]])) & set(map(int, truth[i]))) for i in range(nq))
-    out["sweep"][str(ef)] = {"recall_at_10": hit / (nq * k), "qps_e2e": nq / dt,
-                             "visited_per_query": h.stats()["hnsw_visited"] / nq, "beam": 8 * (ef or k)}
-    print(ef, out["sweep"][str(ef)], flush=True)
+factors = [int(x) for x in os.environ.get("BEAM_FACTORS", "1,8").split(",")]
+for f in factors:
+    h.set_beam_factor(f)
+    sweep = {}
+    for ef in (0, 16, 32, 64, 128, 256):
+        h.search_batch(queries[:256], k, metric, ef)
+        t = time.time(); gi, gs, gc = h.search_batch(queries, k, metric, ef); dt = time.time() - t
+        hit = sum(len(set(map(int, gi[i, :gc[i]])) & set(map(int, truth[i]))) for i in range(nq))
+        sweep[str(ef)] = {"recall_at_10": hit / (nq * k), "qps_e2e": nq / dt,
+                          "visited_per_query": h.stats()["hnsw_visited"] / nq, "beam": f * (ef or k)}
+        print("factor", f, "ef", ef, sweep[str(ef)], flush=True)
+    out["sweep"]["factor_%d" % f] = sweep
+out["flat_stats"] = flat.stats()
 print(json.dumps(out))

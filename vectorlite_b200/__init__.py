@@ -129,6 +129,7 @@ def lib():
         "vl_hnsw_set_builder": (i32, [vp, i32]),
         "vl_hnsw_build_info": (i32, [vp, u64p, u64p]),
         "vl_hnsw_set_score_mode": (i32, [vp, i32]),
+        "vl_hnsw_set_beam_factor": (i32, [vp, u32]),
         "vl_hnsw_graph_check": (i32, [vp, u64p]),
         "vl_index_search": (i32, [vp, fp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
         "vl_index_search_f64": (i32, [vp, dp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
@@ -310,10 +311,10 @@ class _CudaIndex:
         return ids[:got.value], rows[:got.value]
 
     def stats(self) -> dict:
-        out = np.zeros(9, dtype=np.uint64)
-        self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 9)
+        out = np.zeros(11, dtype=np.uint64)
+        self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 11)
         keys = ["launches", "fast_queries", "exact_queries", "h2d_bytes", "d2h_bytes", "hnsw_visited", "bf16_scans",
-                "combined_queries", "bf16_retries"]
+                "combined_queries", "bf16_retries", "fp32_retries", "boosted_queries"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def set_mode(self, mode: Mode) -> None:
@@ -401,6 +402,13 @@ class HNSWIndex(_CudaIndex):
     def set_builder(self, builder: str) -> None:
         """Where bulk adds into an empty index build the graph: "auto" (device from 4096 rows), "host", "device"."""
         st = self._L.vl_hnsw_set_builder(self._h, self.BUILDERS[builder])
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+
+    def set_beam_factor(self, factor: int) -> None:
+        """Device beam width = factor x ef (ef = the reference's min(k, len), hnsw.rs:437, or the `ef` argument);
+        1 = equal ef."""
+        st = self._L.vl_hnsw_set_beam_factor(self._h, int(factor))
         if st != VL_OK:
             raise VectorLiteError(st, _err())
 

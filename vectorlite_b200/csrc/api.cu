@@ -18,6 +18,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "batch.h"
@@ -44,7 +45,8 @@ static int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(_e));                                                \
     } while (0)
 
-enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_COMBINED = 7, ST_BF16_RETRY = 8, ST_N = 9 };
+enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_COMBINED = 7,
+       ST_BF16_RETRY = 8, ST_FP32_RETRY = 9, ST_BOOSTED = 10, ST_N = 11 };
 
 namespace {
 
@@ -61,6 +63,11 @@ static uint32_t batch_min_for(bool tensor_path, bool mirror_scans = false) {
 }
 constexpr uint32_t BATCH_CHUNK = 1024;   // queries per batched pass
 constexpr uint32_t BATCH_CAPQ = 4096;    // candidate slots per query
+
+struct Boost {   // adaptive over-selection state of one search path (single-query scans / batches), see search_levels
+    std::atomic<int> on{0};
+    std::atomic<uint32_t> base_ok_run{0};
+};
 
 struct Slot {  // one in-flight search: stream + scratch, all sized on demand
     cudaStream_t stream = nullptr;
@@ -140,6 +147,8 @@ struct vl_index {
     std::vector<Pending*> comb_queue;
     bool comb_leader = false;
     size_t comb_expect = 1;   // size of the batch that just completed: how many callers the next leader may wait for
+    // ---- adaptive over-selection (search_levels) ----
+    Boost boost_single, boost_batch;
     // ---- hnsw ----
     HnswPtr hnsw;
     int hnsw_metric = -1;
@@ -480,7 +489,7 @@ static int single_query_mirror(vl_index* h, const FlatView& v, int metric, cudaS
 // scan + finalize of up to NQ_CHUNK single queries (bf16 mirror when allowed and available, else the fp32 arena)
 static int launch_single_queries(vl_index* h, const FlatView& v, const float* dq, uint32_t m, uint32_t k, int metric,
                                  const ScanWork& w, const SearchOut& out, bool pipelined, bool allow_bf16,
-                                 cudaStream_t stream, bool* used_bf16) {
+                                 cudaStream_t stream, bool* used_bf16, int kp_base = 0) {
     const void* mirror = nullptr;
     const float* sqn = nullptr;
     if (allow_bf16) {
@@ -502,11 +511,189 @@ static int launch_single_queries(vl_index* h, const FlatView& v, const float* dq
         CU(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], stream));
         h->prof_n += 1;
     }
-    // mirror scans round ONE operand (the rows; the query stays fp32): 2^-8 + pitch·2^-24 < 0.0040 (rescore.cuh)
-    CU(launch_flat_finalize(v, dq, m, k, metric, ws, out, 1.0f, stream, mirror ? 0.0040 : 0.0));
+    CertAux aux;
+    aux.kp_base = kp_base;
+    if (mirror) {
+        // mirror scans round ONE operand (the rows; the query stays fp32): worst case 2^-8 + pitch·2^-24 < 0.0040,
+        // or the rounding error measured while the mirror was built, whichever is smaller (rescore.cuh)
+        aux.tc_abs = 0.0040;
+        if (h->tc.ex_bits) {
+            aux.e_x = h->tc.ex_bits + (metric == VL_METRIC_COSINE ? 0 : 1);
+            aux.e_x1 = h->tc.ex_bits + 2;
+        }
+    }
+    CU(launch_flat_finalize(v, dq, m, k, metric, ws, out, 1.0f, stream, aux));
     h->stats[ST_LAUNCHES] += 2;
     if (mirror) h->stats[ST_BF16_SCANS] += m;
     if (used_bf16) *used_bf16 = mirror != nullptr;
+    return VL_OK;
+}
+
+// ---- over-selection levels of a host search --------------------------------------------------------------
+// A search over-selects K' candidates by approximate score, re-scores them in f64 and certifies that no excluded
+// row can reach the top-k (rescore.cuh).  When the certificate of a query does not hold, ONLY that query moves on:
+//   level 0  approximate scan at the handle's current over-selection (bf16 mirror / tensor cores where they
+//            apply, else the fp32 arena): K' = pick_kp(k), or kp_big(K') while the handle is boosted;
+//   level 1  the same scan at kp_big(K') — more candidates widen the gap between the k-th exact score and the
+//            worst kept approximate score (clustered data: top-10 / top-64 cosine gap 0.003, top-10 / top-256 0.006);
+//   level 2  fp32 arena at kp_big(K') (error bound ~2^-24·pitch instead of the bf16 one);
+//   level 3  exact path: every row in f64, stable radix sort (heavy ties: all-equal mock embeddings).
+// Failing queries are compacted and re-run TOGETHER (as a batch when there are enough of them).  The handle
+// remembers tight data: if a quarter of a level-0 pass fails, later searches start at kp_big directly (one pass
+// instead of two); the finalize kernel reports whether the base K' alone would have certified (FLAG_BASE_OK), and
+// after 256 consecutive such queries the boost is dropped again.
+static int kp_big(int kp) { return std::min<int>(KP_MAX, std::max(4 * kp, 256)); }
+
+struct PassCfg {
+    bool use_bf16 = true;   // bf16 mirror / tensor cores allowed
+    bool exact = false;
+    int Kp = 64;
+    int kp_base = 0;
+};
+
+static bool pass_is_batched(const vl_index* h, uint32_t m, int metric, bool use_bf16, bool exact) {
+    const bool tc_ok = use_bf16 && h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
+    return !exact && m >= batch_min_for(tc_ok && h->dim <= 384, use_bf16 && mirror_scans_apply(h));
+}
+
+// one pass over m staged host queries; leaves ids / scores / counts / flags of the m queries in the slot's pinned
+// mirrors (s.h_*).  `batched_out` reports which pipeline ran.
+static int run_pass(vl_index* h, Slot& s, const FlatView& v, const float* queries, uint32_t m, uint32_t qdim, uint32_t k,
+                    int metric, const PassCfg& cfg, bool* bf16_used) {
+    const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
+    const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
+    const bool tc_ok = cfg.use_bf16 && h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
+    const bool batched = pass_is_batched(h, m, metric, cfg.use_bf16, cfg.exact);
+    *bf16_used = false;
+    int st = slot_reserve(h, s, m, k, cfg.Kp, batched ? 1 : grid_x);
+    if (st) return st;
+    for (uint32_t q = 0; q < m; ++q) {
+        float* d = s.h_q + static_cast<size_t>(q) * h->pitch;
+        memcpy(d, queries + static_cast<size_t>(q) * qdim, h->dim * sizeof(float));
+        for (uint32_t c = h->dim; c < h->pitch; ++c) d[c] = 0.f;
+    }
+    const size_t qbytes = static_cast<size_t>(m) * h->pitch * sizeof(float);
+    CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
+    h->stats[ST_H2D] += qbytes;
+    SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
+    if (cfg.exact) {
+        for (uint32_t q = 0; q < m; ++q) {
+            st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
+            if (st) return st;
+        }
+    } else if (batched) {
+        BatchWork bw;
+        if ((st = slot_reserve_batch(s, m, &bw))) return st;
+        uint64_t nl = 0;
+        if (tc_ok) {
+            std::lock_guard<std::mutex> lk(h->tc_mu);  // shared bf16 query staging + maps
+            CU(tc_prepare(&h->tc, v, h->cap, metric, m, s.stream));
+            BatchTensor bt;
+            bt.usable = h->tc.usable;
+            bt.scratch = &h->tc;
+            *bf16_used = bt.usable;
+            CU(launch_batch_flat(v, s.d_q, m, k, metric, cfg.Kp, bw, out, &bt, &nl, s.stream, cfg.kp_base));
+            CU(cudaStreamSynchronize(s.stream));
+        } else {
+            CU(launch_batch_flat(v, s.d_q, m, k, metric, cfg.Kp, bw, out, nullptr, &nl, s.stream, cfg.kp_base));
+        }
+        h->stats[ST_LAUNCHES] += nl;
+    } else {
+        // few queries: the finalize kernel writes its (tiny) results straight into the pinned host mirror (UVA
+        // zero-copy), which saves the D2H copy operation on the latency path
+        SearchOut hout{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
+        ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, cfg.Kp};
+        w.early = m <= NQ_CHUNK ? s.early : nullptr;
+        if ((st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, cfg.use_bf16, s.stream, bf16_used,
+                                        cfg.kp_base)))
+            return st;
+        CU(cudaStreamSynchronize(s.stream));
+        h->stats[ST_D2H] += static_cast<size_t>(m) * (k * 16 + 8);
+        return VL_OK;
+    }
+    CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    h->stats[ST_D2H] += static_cast<size_t>(m) * (k * 16 + 8);
+    return VL_OK;
+}
+
+// results of m host queries (contiguous [m][qdim]) at `level` and, for the queries whose certificate fails, the
+// levels after it.  *nan is set when a NaN similarity was seen (the reference panics, flat.rs:116).
+static int search_levels(vl_index* h, Slot& s, const FlatView& v, const float* queries, uint32_t m, uint32_t qdim,
+                         uint32_t k, int metric, int level, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
+                         bool* nan) {
+    const int Kp0 = pick_kp(k), Kp1 = kp_big(Kp0);
+    const bool fast = h->mode != VL_MODE_EXACT && k <= 256;
+    if (!fast) level = 3;
+    const bool bf16_possible = h->mode == VL_MODE_AUTO;
+    PassCfg cfg;
+    Boost* boost = nullptr;
+    if (level == 0) {
+        boost = pass_is_batched(h, m, metric, bf16_possible, false) ? &h->boost_batch : &h->boost_single;
+        const bool boosted = boost->on.load(std::memory_order_relaxed) != 0 && Kp1 > Kp0;
+        cfg.use_bf16 = bf16_possible;
+        cfg.Kp = boosted ? Kp1 : Kp0;
+        cfg.kp_base = boosted ? Kp0 : 0;
+        if (boosted) h->stats[ST_BOOSTED] += m;
+    } else if (level == 1) {
+        cfg.use_bf16 = bf16_possible;
+        cfg.Kp = Kp1;
+    } else if (level == 2) {
+        cfg.use_bf16 = false;
+        cfg.Kp = Kp1;
+    } else {
+        cfg.exact = true;
+        cfg.Kp = Kp0;
+    }
+    bool bf16_used = false;
+    int st = run_pass(h, s, v, queries, m, qdim, k, metric, cfg, &bf16_used);
+    if (st) return st;
+    if (level > 0 && !cfg.exact && !bf16_used) h->stats[ST_FP32_RETRY] += m;
+    std::vector<uint32_t> failed;
+    uint32_t base_ok = 0;
+    for (uint32_t q = 0; q < m; ++q) {
+        const uint32_t f = s.h_flags[q];
+        if (f & FLAG_NAN) *nan = true;
+        if (!cfg.exact && (f & FLAG_CERT_FAIL)) {
+            failed.push_back(q);
+            continue;
+        }
+        if (!cfg.exact) h->stats[ST_FAST] += 1;
+        base_ok += (f & FLAG_BASE_OK) != 0;
+        memcpy(out_ids + static_cast<size_t>(q) * k, s.h_ids + static_cast<size_t>(q) * k, k * 8);
+        memcpy(out_scores + static_cast<size_t>(q) * k, s.h_scores + static_cast<size_t>(q) * k, k * 8);
+        out_counts[q] = s.h_counts[q];
+    }
+    if (boost && Kp1 > Kp0) {
+        if (cfg.kp_base) {   // boosted pass: drop the boost after 256 consecutive queries the base K' would have served
+            if (base_ok == m) {
+                if (boost->base_ok_run.fetch_add(m) + m >= 256) { boost->on = 0; boost->base_ok_run = 0; }
+            } else {
+                boost->base_ok_run = 0;
+            }
+        } else if (failed.size() * 4 >= m) {   // tight data: start the next searches at the larger K'
+            boost->on = 1;
+            boost->base_ok_run = 0;
+        }
+    }
+    if (failed.empty()) return VL_OK;
+    // next level for the failing queries only
+    const int next = bf16_used ? (cfg.Kp < Kp1 ? 1 : 2) : (cfg.Kp < Kp1 ? 2 : 3);
+    if (bf16_used) h->stats[ST_BF16_RETRY] += failed.size();
+    const uint32_t mf = static_cast<uint32_t>(failed.size());
+    std::vector<float> fq(static_cast<size_t>(mf) * qdim);
+    std::vector<uint64_t> fi(static_cast<size_t>(mf) * k);
+    std::vector<double> fs(static_cast<size_t>(mf) * k);
+    std::vector<uint32_t> fc(mf);
+    for (uint32_t i = 0; i < mf; ++i)
+        memcpy(fq.data() + static_cast<size_t>(i) * qdim, queries + static_cast<size_t>(failed[i]) * qdim, qdim * sizeof(float));
+    st = search_levels(h, s, v, fq.data(), mf, qdim, k, metric, next, fi.data(), fs.data(), fc.data(), nan);
+    if (st) return st;
+    for (uint32_t i = 0; i < mf; ++i) {
+        memcpy(out_ids + static_cast<size_t>(failed[i]) * k, fi.data() + static_cast<size_t>(i) * k, k * 8);
+        memcpy(out_scores + static_cast<size_t>(failed[i]) * k, fs.data() + static_cast<size_t>(i) * k, k * 8);
+        out_counts[failed[i]] = fc[i];
+    }
     return VL_OK;
 }
 
@@ -526,105 +713,20 @@ static int flat_search_impl(vl_index* h, const float* queries, uint32_t nq, uint
     struct Rel { vl_index* h; Slot* s; ~Rel() { release_slot(h, s); } } rel{h, sp};
 
     const FlatView v = view_of(h);
-    const bool fast = h->mode != VL_MODE_EXACT && k <= 256;
-    const int Kp = pick_kp(k);
-    const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
-    const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
-    int rc = VL_OK;
     const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
-    const bool batched = fast && nq >= batch_min_for(tensor_path, mirror_scans_apply(h));
+    const bool batched = h->mode != VL_MODE_EXACT && k <= 256 && nq >= batch_min_for(tensor_path, mirror_scans_apply(h));
     const uint32_t chunk = batched ? BATCH_CHUNK : NQ_CHUNK;
-    for (uint32_t q0 = 0; q0 < nq && rc == VL_OK; q0 += chunk) {
+    bool nan = false;
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t m = std::min(chunk, nq - q0);
-        int st = slot_reserve(h, s, m, k, Kp, batched ? 1 : grid_x);
+        int st = search_levels(h, s, v, queries + static_cast<size_t>(q0) * qdim, m, qdim, k, metric, 0,
+                               out_ids + static_cast<size_t>(q0) * k, out_scores + static_cast<size_t>(q0) * k,
+                               out_counts + q0, &nan);
         if (st) return st;
-        for (uint32_t q = 0; q < m; ++q) {
-            float* d = s.h_q + static_cast<size_t>(q) * h->pitch;
-            memcpy(d, queries + static_cast<size_t>(q0 + q) * qdim, h->dim * sizeof(float));
-            for (uint32_t c = h->dim; c < h->pitch; ++c) d[c] = 0.f;
-        }
-        const size_t qbytes = static_cast<size_t>(m) * h->pitch * sizeof(float);
-        CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
-        h->stats[ST_H2D] += qbytes;
-        bool zero_copy = false;
-        if (fast) {
-            SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
-            if (batched) {
-                BatchWork bw;
-                if ((st = slot_reserve_batch(s, m, &bw))) return st;
-                uint64_t nl = 0;
-                const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
-                if (want_tc) {
-                    std::lock_guard<std::mutex> lk(h->tc_mu);  // shared bf16 query staging + maps
-                    CU(tc_prepare(&h->tc, v, h->cap, metric, m, s.stream));
-                    BatchTensor bt;
-                    bt.usable = h->tc.usable;
-                    bt.scratch = &h->tc;
-                    CU(launch_batch_flat(v, s.d_q, m, k, metric, Kp, bw, out, &bt, &nl, s.stream));
-                    CU(cudaStreamSynchronize(s.stream));
-                } else {
-                    CU(launch_batch_flat(v, s.d_q, m, k, metric, Kp, bw, out, nullptr, &nl, s.stream));
-                }
-                h->stats[ST_LAUNCHES] += nl;
-            } else {
-                // few queries: the finalize kernel writes its (tiny) results straight into the pinned host
-                // mirror (UVA zero-copy), which saves the D2H copy operation on the latency path
-                zero_copy = true;
-                SearchOut hout{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
-                ScanWork w{s.cand, s.cand_count, s.cand_max, s.ctl, grid_x, Kp};
-                w.early = m <= NQ_CHUNK ? s.early : nullptr;
-                bool used_bf16 = false;
-                if ((st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, true, s.stream, &used_bf16)))
-                    return st;
-                if (used_bf16) {
-                    // a bf16 certificate that does not hold (top-k gaps below the bf16 bound) is retried on
-                    // the fp32 scan before anything falls back to the exact path
-                    CU(cudaStreamSynchronize(s.stream));
-                    bool retry = false;
-                    for (uint32_t q = 0; q < m; ++q) retry |= (s.h_flags[q] & FLAG_CERT_FAIL) != 0;
-                    if (retry) {
-                        h->stats[ST_BF16_RETRY] += m;
-                        if ((st = launch_single_queries(h, v, s.d_q, m, k, metric, w, hout, false, false, s.stream, nullptr)))
-                            return st;
-                    }
-                }
-            }
-            if (!zero_copy) CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaStreamSynchronize(s.stream));
-            bool any_fail = false;
-            for (uint32_t q = 0; q < m; ++q) {
-                if (s.h_flags[q] & FLAG_CERT_FAIL) any_fail = true; else h->stats[ST_FAST] += 1;
-            }
-            if (any_fail) {
-                if (zero_copy) CU(cudaMemcpyAsync(s.d_out, s.h_out, s.out_used, cudaMemcpyHostToDevice, s.stream));
-                for (uint32_t q = 0; q < m; ++q)
-                    if (s.h_flags[q] & FLAG_CERT_FAIL) {
-                        st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
-                        if (st) return st;
-                    }
-                CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
-                CU(cudaStreamSynchronize(s.stream));
-            }
-        } else {
-            for (uint32_t q = 0; q < m; ++q) {
-                st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
-                if (st) return st;
-            }
-            CU(cudaMemcpyAsync(s.h_out, s.d_out, s.out_used, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaStreamSynchronize(s.stream));
-        }
-        h->stats[ST_D2H] += static_cast<size_t>(m) * (k * 16 + 8);
-        for (uint32_t q = 0; q < m; ++q) {
-            if (s.h_flags[q] & FLAG_NAN) {
-                // the reference panics (partial_cmp().unwrap(), flat.rs:116) as soon as n >= 2
-                if (h->n >= 2) rc = fail(VL_ERR_NAN, "similarity is NaN (the reference panics at flat.rs:116)");
-            }
-            memcpy(out_ids + static_cast<size_t>(q0 + q) * k, s.h_ids + static_cast<size_t>(q) * k, k * 8);
-            memcpy(out_scores + static_cast<size_t>(q0 + q) * k, s.h_scores + static_cast<size_t>(q) * k, k * 8);
-            out_counts[q0 + q] = s.h_counts[q];
-        }
     }
-    return rc;
+    // the reference panics (partial_cmp().unwrap(), flat.rs:116) as soon as n >= 2
+    if (nan && h->n >= 2) return fail(VL_ERR_NAN, "similarity is NaN (the reference panics at flat.rs:116)");
+    return VL_OK;
 }
 
 }  // namespace
@@ -831,10 +933,15 @@ int vl_index_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint
     if (!h || (n && (!ids || !rows))) return fail(VL_ERR_INVALID, "null argument");
     DeviceGuard dg(h->device);
     if (h->type == VL_INDEX_HNSW) {
-        // hnsw.rs:363-399: dup check against live ids, then append to the arena and the graph
-        for (uint64_t i = 0; i < n; ++i)
-            if (hnsw_has_id(h->hnsw.get(), ids[i]))
-                return fail(VL_ERR_DUP_ID, "Vector ID %llu already exists", static_cast<unsigned long long>(ids[i]));
+        // hnsw.rs:363-399: dup check against live ids AND inside the batch (the reference adds one vector at a
+        // time and rejects the second occurrence, hnsw.rs:369), all-or-nothing, before anything is touched
+        {
+            std::unordered_set<uint64_t> seen;
+            if (n > 1) seen.reserve(n * 2);
+            for (uint64_t i = 0; i < n; ++i)
+                if (hnsw_has_id(h->hnsw.get(), ids[i]) || (n > 1 && !seen.insert(ids[i]).second))
+                    return fail(VL_ERR_DUP_ID, "Vector ID %llu already exists", static_cast<unsigned long long>(ids[i]));
+        }
         const uint64_t first = h->n;
         // arena rows are addressed by internal index; ids are tracked by the HNSW state
         std::vector<uint64_t> internal(n);
@@ -845,7 +952,10 @@ int vl_index_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint
         (void)was_identity;
         uint64_t nl = 0;
         st = hnsw_add_rows(h->hnsw.get(), ids, rows, n, h->d_rows, h->pitch, h->mut_stream, &nl);
-        if (st) return fail(st, "hnsw insert failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (st) {
+            h->n = first;   // roll the arena back: rows past n are never read, the graph was not extended
+            return fail(st, "hnsw insert failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
         h->stats[ST_LAUNCHES] += nl;
         return VL_OK;
     }
@@ -935,6 +1045,13 @@ int vl_hnsw_set_builder(vl_index* h, int builder) {
     return VL_OK;
 }
 
+int vl_hnsw_set_beam_factor(vl_index* h, uint32_t factor) {
+    if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
+    if (factor < 1 || factor > 64) return fail(VL_ERR_INVALID, "beam factor must be in [1, 64]");
+    hnsw_set_beam_mult(h->hnsw.get(), factor);
+    return VL_OK;
+}
+
 int vl_hnsw_set_score_mode(vl_index* h, int mode) {
     if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
     if (mode != 0 && mode != 1) return fail(VL_ERR_INVALID, "score mode must be 0 (exact) or 1 (reference-quantised)");
@@ -982,11 +1099,9 @@ int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdi
         auto impl = [&](const float* q, uint32_t m, uint32_t bk, int, uint32_t bef, uint64_t* ids, double* sc,
                         uint32_t* cnt) -> int {
             DeviceGuard dg(h->device);
-            int st = hnsw_upload(h->hnsw.get(), h->mut_stream);
-            if (st) return fail(st, "hnsw graph upload failed");
             uint64_t visited = 0, launches = 0;
-            st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, q, m, bk, bef, ids, sc, cnt, h->mut_stream,
-                                  &visited, &launches);
+            // uploads a changed graph under its exclusive lock, then searches on a stream of its own
+            int st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, q, m, bk, bef, ids, sc, cnt, &visited, &launches);
             h->stats[ST_HNSW_VISITED] = visited;
             h->stats[ST_LAUNCHES] += launches;
             if (st) return fail(st, "hnsw search failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1016,6 +1131,22 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
     const int Kp = pick_kp(k);
     const uint32_t tiles = (v.n + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS;
     const int grid_x = static_cast<int>(std::min<uint32_t>(tiles, h->max_grid_x));
+    if (h->pitch != h->dim) {
+        // The kernels read rows and queries at the arena pitch (dim rounded up to 4 floats, zero padded, 16-byte
+        // aligned float4 loads).  The ABI takes queries as [nq][dim]: repack them into a padded staging buffer.
+        const size_t need = static_cast<size_t>(nq) * h->pitch;
+        if (need > s.q_cap) {
+            CU(cudaStreamSynchronize(stream));   // an earlier search may still read the old staging buffer
+            if (s.d_q) cudaFree(s.d_q);
+            s.d_q = nullptr; s.q_cap = 0;
+            CU(cudaMalloc(&s.d_q, need * sizeof(float)));
+            s.q_cap = need;
+        }
+        CU(cudaMemsetAsync(s.d_q, 0, need * sizeof(float), stream));
+        CU(cudaMemcpy2DAsync(s.d_q, h->pitch * sizeof(float), d_queries, h->dim * sizeof(float), h->dim * sizeof(float), nq,
+                             cudaMemcpyDeviceToDevice, stream));
+        d_queries = s.d_q;
+    }
     auto out_at = [&](uint32_t q0) {
         SearchOut out = o;
         out.ids = o.ids + static_cast<size_t>(q0) * k;

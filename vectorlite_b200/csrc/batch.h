@@ -30,6 +30,6 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& tc, const fl
 // full pipeline: init → 3 staged scans with per-query selects → rescore/certify.  tc may be null.
 cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k, int metric,
                               int Kp, const BatchWork& w, const SearchOut& out, const BatchTensor* tc,
-                              uint64_t* launches, cudaStream_t s);
+                              uint64_t* launches, cudaStream_t s, int kp_base = 0);
 
 }  // namespace vl

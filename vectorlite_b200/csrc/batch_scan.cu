@@ -19,6 +19,7 @@
 // K chunks of 32 columns staged through registers into transposed, odd-pitch shared tiles.
 #include "batch.h"
 #include "rescore.cuh"
+#include "tc_state.h"
 #include "topk.cuh"
 
 namespace vl {
@@ -398,7 +399,7 @@ template <int METRIC>
 static cudaError_t launch_rescore_stream(const FinalizeParams& p, const BatchWork& w, uint32_t nq, int KpR,
                                          size_t smem, cudaStream_t s) {
     auto kern = batch_rescore_stream_kernel<METRIC>;
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {   // dynamic + the kernel's static shared memory must stay under the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
@@ -443,7 +444,7 @@ cudaError_t batch_scan_cuda_cores(const FlatView& v, const float* d_q, uint32_t 
 
 cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k, int metric,
                               int Kp, const BatchWork& w, const SearchOut& out, const BatchTensor* tc,
-                              uint64_t* launches, cudaStream_t s) {
+                              uint64_t* launches, cudaStream_t s, int kp_base) {
     cudaError_t e;
     static bool attr[64] = {};
     int dev = 0;
@@ -492,7 +493,13 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = 1.0;
     p.tc_abs = use_tc ? tc->tc_abs : 0.0;
+    if (use_tc) {   // measured rounding-error norms of the mirror that was scanned and of this batch's queries
+        const TcState* ts = static_cast<const TcState*>(tc->scratch);
+        p.e_x = ts->ex_bits ? ts->ex_bits + (metric == COSINE ? 0 : 1) : nullptr;
+        p.e_q = ts->eq;
+    }
     p.peers = out.peers;
+    p.kp_base = kp_base;
     const int KpR = (Kp + 31) & ~31;
     if (nq >= 8 && KpR + RS_SPARE <= 1024) {   // many queries: small streaming CTAs, one wave
         p.CH = KpR <= 64 ? 32 : 16;

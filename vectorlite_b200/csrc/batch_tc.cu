@@ -386,46 +386,68 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 // fp32 arena rows → bf16 mirror [n][KP] (cosine: scaled by 1/‖row‖), zero padded to KP
 __global__ void to_bf16_rows_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm, uint64_t first,
                                     uint64_t n, uint32_t dim, uint32_t pitch, uint32_t KP, int normalise,
-                                    __nv_bfloat16* out, float* sq_norm) {
+                                    __nv_bfloat16* out, float* sq_norm, uint32_t* ex_bits, uint32_t* ex1_bits) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
     for (uint64_t r = warp; r < n; r += nwarps) {
         const float* src = rows + (first + r) * pitch;
         const float sc = normalise ? inv_norm[first + r] : 1.f;
-        double ss = 0.0;
+        double ss = 0.0, ref2 = 0.0, err2 = 0.0, err1 = 0.0;   // ‖x‖², ‖x̂‖² (what is rounded), ‖x̃−x̂‖², ‖x̃−x̂‖₁
         for (uint32_t c = lane; c < KP; c += 32) {
             const float x = c < dim ? src[c] : 0.f;
             ss += static_cast<double>(x) * x;
-            out[(first + r) * KP + c] = __float2bfloat16_rn(x * sc);
+            const float xs = x * sc;
+            const __nv_bfloat16 b = __float2bfloat16_rn(xs);
+            const double d = static_cast<double>(__bfloat162float(b)) - static_cast<double>(xs);
+            ref2 += static_cast<double>(xs) * xs;
+            err2 += d * d;
+            err1 += fabs(d);
+            out[(first + r) * KP + c] = b;
         }
-        if (sq_norm) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-            if (lane == 0) sq_norm[first + r] = static_cast<float>(ss);
+        for (int o = 16; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+            ref2 += __shfl_xor_sync(0xFFFFFFFFu, ref2, o);
+            err2 += __shfl_xor_sync(0xFFFFFFFFu, err2, o);
+            err1 += __shfl_xor_sync(0xFFFFFFFFu, err1, o);
+        }
+        if (lane == 0) {
+            if (sq_norm) sq_norm[first + r] = static_cast<float>(ss);
+            // measured relative rounding error of this row, rounded UP to fp32; non-negative floats order like
+            // their bit patterns, so an integer atomicMax keeps the maximum over all rows
+            if (ex_bits && ref2 > 0.0) atomicMax(ex_bits, __float_as_uint(__double2float_ru(sqrt(err2 / ref2) * 1.000001)));
+            if (ex1_bits) atomicMax(ex1_bits, __float_as_uint(__double2float_ru(err1 * 1.000001)));
         }
     }
 }
 
 // fp32 queries [nq][pitch] → bf16 [nq_pad][KP] (+ ‖q‖² for L2); rows >= nq are zero
 __global__ void to_bf16_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t nq_pad, uint32_t dim,
-                                       uint32_t pitch, uint32_t KP, __nv_bfloat16* out, float* qn2) {
+                                       uint32_t pitch, uint32_t KP, __nv_bfloat16* out, float* qn2, float* eq) {
     const uint32_t r = blockIdx.x;
-    double ss = 0.0;
+    double ss = 0.0, err2 = 0.0;
     for (uint32_t c = threadIdx.x; c < KP; c += blockDim.x) {
         const float x = (r < nq && c < dim) ? q[static_cast<size_t>(r) * pitch + c] : 0.f;
         ss += static_cast<double>(x) * x;
-        out[static_cast<size_t>(r) * KP + c] = __float2bfloat16_rn(x);
+        const __nv_bfloat16 b = __float2bfloat16_rn(x);
+        const double d = static_cast<double>(__bfloat162float(b)) - static_cast<double>(x);
+        err2 += d * d;
+        out[static_cast<size_t>(r) * KP + c] = b;
     }
-    __shared__ double s_red[32];
+    __shared__ double s_red[32], s_err[32];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+        err2 += __shfl_xor_sync(0xFFFFFFFFu, err2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = ss; s_err[threadIdx.x >> 5] = err2; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (uint32_t i = 0; i < (blockDim.x + 31) / 32; ++i) t += s_red[i];
+        double t = 0.0, e = 0.0;
+        for (uint32_t i = 0; i < (blockDim.x + 31) / 32; ++i) { t += s_red[i]; e += s_err[i]; }
         qn2[r] = static_cast<float>(t);
+        if (eq) eq[r] = t > 0.0 ? __double2float_ru(sqrt(e / t) * 1.000001) : 0.f;   // E_q = ‖q̃−q‖/‖q‖, rounded up
     }
     (void)nq_pad;
 }
@@ -474,6 +496,7 @@ int tc_cluster_size() {
 void tc_state_free(TcState* t) {
     if (!t) return;
     cudaFree(t->rows_norm); cudaFree(t->rows_raw); cudaFree(t->sq_norm); cudaFree(t->q_bf16); cudaFree(t->qn2);
+    cudaFree(t->eq); cudaFree(t->ex_bits);
     *t = TcState();
 }
 
@@ -485,6 +508,7 @@ cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int me
     if (t->cap < arena_cap || t->KP != KP) {  // (re)allocate lazily per mirror below
         cudaFree(t->rows_norm); cudaFree(t->rows_raw); cudaFree(t->sq_norm);
         t->rows_norm = t->rows_raw = nullptr; t->sq_norm = nullptr;
+        if (t->ex_bits) cudaMemsetAsync(t->ex_bits, 0, 3 * sizeof(uint32_t), s);
         t->built_norm = t->built_raw = 0;
         t->cap = arena_cap;
         t->KP = KP;
@@ -496,6 +520,10 @@ cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int me
         if ((e = cudaMalloc(mirror, t->cap * KP * 2)) != cudaSuccess) { t->usable = false; cudaGetLastError(); return cudaSuccess; }
         *built = 0;
     }
+    if (!t->ex_bits) {
+        if ((e = cudaMalloc(&t->ex_bits, 3 * sizeof(uint32_t))) != cudaSuccess) { t->usable = false; cudaGetLastError(); return cudaSuccess; }
+        cudaMemsetAsync(t->ex_bits, 0, 3 * sizeof(uint32_t), s);
+    }
     if (!cosine && !t->sq_norm) {
         if ((e = cudaMalloc(&t->sq_norm, t->cap * 4)) != cudaSuccess) { t->usable = false; cudaGetLastError(); return cudaSuccess; }
     }
@@ -503,16 +531,18 @@ cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int me
         const uint64_t m = v.n - *built;
         uint64_t blocks = std::min<uint64_t>((m + 7) / 8, 148 * 16);
         tc::to_bf16_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-            v.rows, v.inv_norm, *built, m, v.dim, v.pitch, KP, cosine ? 1 : 0, *mirror, cosine ? nullptr : t->sq_norm);
+            v.rows, v.inv_norm, *built, m, v.dim, v.pitch, KP, cosine ? 1 : 0, *mirror, cosine ? nullptr : t->sq_norm,
+            t->ex_bits + (cosine ? 0 : 1), cosine ? nullptr : t->ex_bits + 2);
         *built = v.n;
         t->maps_n = 0;  // force re-encode
     }
     const uint32_t nq_pad = (nq + tc::BM - 1) / tc::BM * tc::BM;
     if (t->q_cap < nq_pad) {
-        cudaFree(t->q_bf16); cudaFree(t->qn2);
-        t->q_bf16 = nullptr; t->qn2 = nullptr;
+        cudaFree(t->q_bf16); cudaFree(t->qn2); cudaFree(t->eq);
+        t->q_bf16 = nullptr; t->qn2 = nullptr; t->eq = nullptr;
         if ((e = cudaMalloc(&t->q_bf16, static_cast<size_t>(nq_pad) * KP * 2)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&t->qn2, static_cast<size_t>(nq_pad) * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&t->eq, static_cast<size_t>(nq_pad) * 4)) != cudaSuccess) return e;
         t->q_cap = nq_pad;
     }
     t->usable = true;
@@ -548,7 +578,7 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     const int CS = tc_cluster_size();
     if (lo == 0) {  // first stage of a batch: convert the queries, (re)encode the maps
         tc::to_bf16_queries_kernel<<<nq_pad, 128, 0, s>>>(d_q, nq, nq_pad, v.dim, v.pitch, KP,
-                                                        static_cast<__nv_bfloat16*>(t->q_bf16), t->qn2);
+                                                        static_cast<__nv_bfloat16*>(t->q_bf16), t->qn2, t->eq);
         const void* mirror = metric == COSINE ? t->rows_norm : t->rows_raw;
         if (t->maps_n != v.n || t->maps_base != mirror || t->maps_cs != CS) {
             if (!make_map(&t->map_x, mirror, v.n, KP, tc::BN / CS)) return cudaErrorUnknown;

@@ -14,6 +14,7 @@ constexpr uint32_t FLAG_NONFINITE = 2u;   // a non-finite approximate score was 
 constexpr uint32_t FLAG_NAN = 4u;         // an exact similarity is NaN (reference panics)
 constexpr uint32_t FLAG_OVERFLOW = 8u;    // a candidate buffer overflowed → re-run exact
 constexpr uint32_t FLAG_EXCHANGE = 16u;   // a peer's results did not arrive in time (row-sharded exchange)
+constexpr uint32_t FLAG_BASE_OK = 32u;    // host searches only: the base over-selection K' alone would have certified
 
 constexpr uint32_t INVALID_POS = 0xFFFFFFFFu;
 

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(ExchangeMerge m) {
     __syncthreads();   // every read of the slot is done
     if (tid == 0) {
         m.out_counts[q] = cnt;
-        m.out_flags[q] = s_flags | (s_fail ? FLAG_EXCHANGE : 0u);
+        // a block that never arrived leaves the merged list incomplete: raise the "do not use" bit with it
+        m.out_flags[q] = s_flags | (s_fail ? (FLAG_EXCHANGE | FLAG_CERT_FAIL) : 0u);
     }
     // ---- acknowledge: peer g may overwrite its block of this slot (next use) --------------------------
     if (tid < G && tid != m.self) red_add_release_sys(m.ack[tid], 1u);

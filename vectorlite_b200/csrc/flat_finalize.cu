@@ -153,7 +153,7 @@ static size_t finalize_smem(int Kp, int CH) {
 
 cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k,
                                  int metric, const ScanWork& w, const SearchOut& out, float eps_scale,
-                                 cudaStream_t s, double tc_abs) {
+                                 cudaStream_t s, const CertAux& aux) {
     // choose the staging chunk so that the tile fits in ~180 KB of shared memory
     const size_t budget = 180 * 1024;
     int CH = static_cast<int>((v.dim + 3) / 4 * 4);
@@ -178,7 +178,7 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
     p.out_ids = out.ids; p.out_scores = out.scores; p.out_pos = out.pos;
     p.out_counts = out.counts; p.out_flags = out.flags;
     p.eps_scale = eps_scale;
-    p.tc_abs = tc_abs;
+    p.tc_abs = aux.tc_abs; p.e_x = aux.e_x; p.e_q = aux.e_q; p.e_x1 = aux.e_x1; p.kp_base = aux.kp_base;
     p.peers = out.peers;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nq);

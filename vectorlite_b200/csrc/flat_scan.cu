@@ -374,7 +374,7 @@ static cudaError_t launch_one(const void* rows, const float* aux, uint32_t n, ui
                               uint32_t nq, const ScanWork& w, bool pipelined, cudaStream_t s) {
     const size_t smem = flat_scan_smem_bytes(pitch);
     auto kern = flat_scan_kernel<METRIC, NCH, BF16>;
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return e;

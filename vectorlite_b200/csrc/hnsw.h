@@ -29,16 +29,20 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
                   uint32_t pitch, cudaStream_t stream, uint64_t* launches);
 void hnsw_set_builder(HnswState* s, int builder);
 void hnsw_set_score_mode(HnswState* s, uint32_t mode);
+void hnsw_set_beam_mult(HnswState* s, uint32_t mult);
+uint32_t hnsw_beam_mult(const HnswState* s);
 // [0] builder used by the last bulk add (1 host, 2 device), [1] its wall time in microseconds
 void hnsw_build_info(const HnswState* s, uint64_t out[2]);
 bool hnsw_soft_delete(HnswState* s, uint64_t id);
 void hnsw_graph_check(const HnswState* s, uint64_t out[6]);
 // live rows in insertion order: up to `cap` starting at live position `first` (rows come from the host copy)
 uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows);
-// flatten + upload the graph if it changed since the last upload
+// flatten + upload the graph if it changed since the last upload (takes the graph lock exclusively)
 int hnsw_upload(HnswState* s, cudaStream_t stream);
+// Re-entrant: uploads a changed graph under the exclusive graph lock, then searches under the shared lock on a
+// stream / scratch set of its own (pool of HnswState::MAX_CTX).
 int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,
                      uint32_t k, uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
-                     cudaStream_t stream, uint64_t* visited, uint64_t* launches);
+                     uint64_t* visited, uint64_t* launches);
 
 }  // namespace vl

@@ -277,7 +277,7 @@ int run_batch(const BuildGraph& bg, const HnswDeviceGraph& dg, const float* d_ro
     if (st) return st;
     const size_t sel_smem = HB_WARPS * (static_cast<size_t>(efc) * 8 + 2 * HB_MAX_DEG * 4);
     auto ksel = hnsw_build_select_kernel<METRIC>;
-    if (sel_smem > 48 * 1024) cudaFuncSetAttribute(ksel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem));
+    if (sel_smem > 40 * 1024) cudaFuncSetAttribute(ksel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem));
     ksel<<<(nb + HB_WARPS - 1) / HB_WARPS, HB_THREADS, sel_smem, s>>>(bg, d_order, nb, lvl, d_W, d_wcount, efc, d_pairs,
                                                                      d_pair_dist);
     const uint32_t npairs = nb * bg.M;

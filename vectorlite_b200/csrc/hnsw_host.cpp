@@ -14,6 +14,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
 #include <thread>
@@ -200,14 +201,15 @@ struct Builder {
                     ta[m] = q;
                     unlock(t);
                 } else {
+                    // lock(t) is held across the whole re-selection: dropping it between the copy and the write-back
+                    // let a concurrent thread's append / re-selection on t be overwritten by this (then stale)
+                    // selection — lost edges, run-to-run recall variation.  select() only reads row data and the
+                    // lists of OTHER nodes are not touched, so no second lock is taken while t is held.
                     tmp.clear();
                     tmp.emplace_back(e.first, q);
                     for (uint32_t j = 0; j < m; ++j) tmp.emplace_back(dist(t, ta[j]), ta[j]);
-                    unlock(t);  // distances to other rows computed outside the lock would race with ta;
-                                // we copied under the lock, the re-selection below works on the copy
                     std::sort(tmp.begin(), tmp.end());
                     select(tmp, c, sc);
-                    lock(t);
                     for (uint32_t j = 0; j < c; ++j) ta[j] = j < sc.sel.size() ? sc.sel[j].second : HNSW_NONE;
                     unlock(t);
                 }
@@ -257,19 +259,22 @@ HnswState* hnsw_state_create(uint32_t dim, int metric, uint32_t M, uint32_t M0, 
     s->M = M;
     s->M0 = M0;
     s->efc = efc;
+    if (const char* e = std::getenv("VL_HNSW_BEAM_MULT")) s->beam_mult = static_cast<uint32_t>(std::max(1, atoi(e)));
     return s;
 }
 
 void hnsw_state_release_device(HnswState* s) {
     cudaFree(s->d_adj0); cudaFree(s->d_upper_off); cudaFree(s->d_upper); cudaFree(s->d_level);
-    cudaFree(s->d_deleted); cudaFree(s->d_ids); cudaFree(s->d_inv_norm); cudaFree(s->d_q);
-    cudaFree(s->d_out); cudaFreeHost(s->h_out); cudaFree(s->d_visited);
-
+    cudaFree(s->d_deleted); cudaFree(s->d_ids); cudaFree(s->d_inv_norm);
+    for (auto& c : s->ctxs) {
+        cudaFree(c->d_q); cudaFree(c->d_out); cudaFreeHost(c->h_out); cudaFree(c->d_visited); cudaFreeHost(c->h_visited);
+        if (c->stream) cudaStreamDestroy(c->stream);
+    }
+    s->ctxs.clear();
     s->d_adj0 = s->d_upper_off = s->d_upper = nullptr;
     s->d_level = s->d_deleted = nullptr;
-    s->d_ids = nullptr; s->d_inv_norm = nullptr; s->d_q = nullptr; s->d_out = nullptr; s->h_out = nullptr;
-    s->d_visited = nullptr;
-    s->d_n_cap = s->d_upper_cap = s->q_cap = s->out_cap = 0;
+    s->d_ids = nullptr; s->d_inv_norm = nullptr;
+    s->d_n_cap = s->d_upper_cap = 0;
     s->dirty = s->deleted_dirty = true;
 }
 
@@ -291,6 +296,8 @@ uint64_t hnsw_live(const HnswState* s) { return s->live; }
 
 void hnsw_set_builder(HnswState* s, int builder) { s->builder = builder; }
 void hnsw_set_score_mode(HnswState* s, uint32_t mode) { s->score_mode = mode; }
+void hnsw_set_beam_mult(HnswState* s, uint32_t mult) { s->beam_mult = mult < 1 ? 1 : mult; }
+uint32_t hnsw_beam_mult(const HnswState* s) { return s->beam_mult; }
 void hnsw_build_info(const HnswState* s, uint64_t out[2]) {
     out[0] = static_cast<uint64_t>(s->last_builder);
     out[1] = s->last_build_us;
@@ -366,8 +373,12 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
     nthreads = std::max(1u, std::min(nthreads, 64u));
     uint32_t start = first;
     {
+        // sequential path: the visited stamps live in the state, so a single add costs O(visited), not O(total)
         Builder::Scratch sc;
-        sc.stamp.assign(total, 0);
+        sc.stamp.swap(s->seq_stamp);
+        sc.epoch = s->seq_epoch;
+        if (sc.stamp.size() < total) sc.stamp.resize(total + total / 4 + 64, 0);
+        struct Keep { HnswState* s; Builder::Scratch* sc; ~Keep() { sc->stamp.swap(s->seq_stamp); s->seq_epoch = sc->epoch; } } keep{s, &sc};
         const uint32_t seq_end = static_cast<uint32_t>(std::min<uint64_t>(total, std::max<uint32_t>(first, 256)));
         for (; start < seq_end; ++start) b.insert(start, sc);
         if (nthreads == 1 || total - start < 1024) {
@@ -462,7 +473,8 @@ int hnsw_reserve_device(HnswState* s, size_t n) {
     return 0;
 }
 
-int hnsw_upload(HnswState* s, cudaStream_t stream) {
+// caller holds graph_mu exclusively (or is the single writer)
+static int upload_locked(HnswState* s, cudaStream_t stream) {
     const size_t n = s->level.size();
     if (n == 0) return 0;
     if (s->dirty) {
@@ -483,61 +495,101 @@ int hnsw_upload(HnswState* s, cudaStream_t stream) {
     return 0;
 }
 
+int hnsw_upload(HnswState* s, cudaStream_t stream) {
+    std::unique_lock<std::shared_mutex> lk(s->graph_mu);
+    return upload_locked(s, stream);
+}
+
+static HnswState::SearchCtx* acquire_ctx(HnswState* s) {
+    std::unique_lock<std::mutex> lk(s->ctx_mu);
+    for (;;) {
+        for (auto& c : s->ctxs)
+            if (!c->busy) { c->busy = true; return c.get(); }
+        if (static_cast<int>(s->ctxs.size()) < HnswState::MAX_CTX) {
+            auto c = std::make_unique<HnswState::SearchCtx>();
+            if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaMalloc(&c->d_visited, 8) != cudaSuccess || cudaMallocHost(&c->h_visited, 8) != cudaSuccess) {
+                cudaFree(c->d_visited);
+                cudaStreamDestroy(c->stream);
+                return nullptr;
+            }
+            c->busy = true;
+            s->ctxs.push_back(std::move(c));
+            return s->ctxs.back().get();
+        }
+        s->ctx_cv.wait(lk);
+    }
+}
+static void release_ctx(HnswState* s, HnswState::SearchCtx* c) {
+    { std::lock_guard<std::mutex> lk(s->ctx_mu); c->busy = false; }
+    s->ctx_cv.notify_one();
+}
+
 int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,
                      uint32_t k, uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
-                     cudaStream_t stream, uint64_t* visited, uint64_t* launches) {
-    std::lock_guard<std::mutex> lk(s->search_mu);
+                     uint64_t* visited, uint64_t* launches) {
+    HnswState::SearchCtx* c = acquire_ctx(s);
+    if (!c) return 6;
+    struct Rel { HnswState* s; HnswState::SearchCtx* c; ~Rel() { release_ctx(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+    // The first search after an add / delete uploads the graph — exclusively: hnsw_reserve_device may free and
+    // reallocate the device arrays, which no concurrent reader may be using (this used to run outside
+    // any lock).  Mutators are excluded from readers by the caller (RwLock, client.rs:245), so `dirty` can only be
+    // set while no search is in flight; the flags are re-checked under the lock.
+    if (s->dirty || s->deleted_dirty) {
+        std::unique_lock<std::shared_mutex> up(s->graph_mu);
+        if (s->dirty || s->deleted_dirty)
+            if (int st = upload_locked(s, stream)) return st;
+    }
+    std::shared_lock<std::shared_mutex> rd(s->graph_mu);
     // hnsw.rs:437: ef = max_candidates = min(k, live); `ef` > 0 is the additive sweep knob
     const uint32_t maxc = static_cast<uint32_t>(std::min<uint64_t>(k, s->live));
     uint32_t ef_search = ef == 0 ? maxc : std::max(ef, maxc);
     const size_t qf = static_cast<size_t>(nq) * pitch;
-    if (qf > s->q_cap) {
-        cudaFree(s->d_q);
-        s->d_q = nullptr;
-        if (cudaMalloc(&s->d_q, qf * sizeof(float)) != cudaSuccess) return 7;
-        s->q_cap = qf;
+    if (qf > c->q_cap) {
+        cudaFree(c->d_q);
+        c->d_q = nullptr; c->q_cap = 0;
+        if (cudaMalloc(&c->d_q, qf * sizeof(float)) != cudaSuccess) return 7;
+        c->q_cap = qf;
     }
     const size_t on = static_cast<size_t>(nq) * k;
     const size_t need = on * 16 + static_cast<size_t>(nq) * 4;
-    if (need > s->out_cap) {
-        cudaFree(s->d_out); cudaFreeHost(s->h_out);
-        s->d_out = nullptr; s->h_out = nullptr;
-        if (cudaMalloc(&s->d_out, need) != cudaSuccess) return 7;
-        if (cudaMallocHost(&s->h_out, need) != cudaSuccess) return 7;
-        s->out_cap = need;
+    if (need > c->out_cap) {
+        cudaFree(c->d_out); cudaFreeHost(c->h_out);
+        c->d_out = nullptr; c->h_out = nullptr; c->out_cap = 0;
+        if (cudaMalloc(&c->d_out, need) != cudaSuccess) return 7;
+        if (cudaMallocHost(&c->h_out, need) != cudaSuccess) return 7;
+        c->out_cap = need;
     }
-    if (!s->d_visited && cudaMalloc(&s->d_visited, 8) != cudaSuccess) return 7;
-    cudaMemsetAsync(s->d_visited, 0, 8, stream);
+    cudaMemsetAsync(c->d_visited, 0, 8, stream);
     HnswDeviceGraph g;
     g.adj0 = s->d_adj0; g.upper_off = s->d_upper_off; g.upper = s->d_upper; g.level = s->d_level;
     g.deleted = s->d_deleted; g.ids = s->d_ids; g.inv_norm = s->d_inv_norm;
     g.n = static_cast<uint32_t>(s->level.size()); g.M = s->M; g.M0 = s->M0; g.entry = s->entry;
     g.max_level = s->max_level;
-    uint64_t* d_ids = reinterpret_cast<uint64_t*>(s->d_out);
-    double* d_scores = reinterpret_cast<double*>(s->d_out + on * 8);
-    uint32_t* d_counts = reinterpret_cast<uint32_t*>(s->d_out + on * 16);
+    uint64_t* d_ids = reinterpret_cast<uint64_t*>(c->d_out);
+    double* d_scores = reinterpret_cast<double*>(c->d_out + on * 8);
+    uint32_t* d_counts = reinterpret_cast<uint32_t*>(c->d_out + on * 16);
     // One launch for the whole batch: splitting it into wave-sized chunks (to overlap the query upload with the
     // search) was measured 25 % SLOWER — every launch pays its own tail of slow queries.
     if (pitch == s->dim) {
-        cudaMemcpyAsync(s->d_q, queries, qf * sizeof(float), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(c->d_q, queries, qf * sizeof(float), cudaMemcpyHostToDevice, stream);
     } else {
-        cudaMemsetAsync(s->d_q, 0, qf * sizeof(float), stream);
-        cudaMemcpy2DAsync(s->d_q, pitch * sizeof(float), queries, s->dim * sizeof(float), s->dim * sizeof(float),
+        cudaMemsetAsync(c->d_q, 0, qf * sizeof(float), stream);
+        cudaMemcpy2DAsync(c->d_q, pitch * sizeof(float), queries, s->dim * sizeof(float), s->dim * sizeof(float),
                           nq, cudaMemcpyHostToDevice, stream);
     }
-    int st = hnsw_launch_search(g, d_rows, pitch, s->dim, s->metric, s->d_q, nq, k, ef_search, d_ids, d_scores,
-                                d_counts, s->d_visited, stream, s->score_mode);
+    int st = hnsw_launch_search(g, d_rows, pitch, s->dim, s->metric, c->d_q, nq, k, ef_search, d_ids, d_scores,
+                                d_counts, c->d_visited, stream, s->score_mode, s->beam_mult);
     if (st) return st;
-    const uint64_t nlaunch = 1;
-    unsigned long long vis = 0;
-    cudaMemcpyAsync(s->h_out, s->d_out, need, cudaMemcpyDeviceToHost, stream);
-    cudaMemcpyAsync(&vis, s->d_visited, 8, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(c->h_out, c->d_out, need, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(c->h_visited, c->d_visited, 8, cudaMemcpyDeviceToHost, stream);
     if (cudaStreamSynchronize(stream) != cudaSuccess) return 6;
-    memcpy(out_ids, s->h_out, on * 8);
-    memcpy(out_scores, s->h_out + on * 8, on * 8);
-    memcpy(out_counts, s->h_out + on * 16, static_cast<size_t>(nq) * 4);
-    *visited = vis;
-    *launches = nlaunch;
+    memcpy(out_ids, c->h_out, on * 8);
+    memcpy(out_scores, c->h_out + on * 8, on * 8);
+    memcpy(out_counts, c->h_out + on * 16, static_cast<size_t>(nq) * 4);
+    *visited = *c->h_visited;
+    *launches = 1;
     return 0;
 }
 

@@ -330,11 +330,11 @@ template <int METRIC, bool BUILD, int WARPS>
 static int launch_warps(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
     if (p.pitch == 384) {
         auto k = hnsw_search_kernel<METRIC, 3, BUILD, WARPS>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (smem > 40 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         k<<<nq, WARPS * 32, smem, s>>>(p);
     } else {
         auto k = hnsw_search_kernel<METRIC, 0, BUILD, WARPS>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (smem > 40 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         k<<<nq, WARPS * 32, smem, s>>>(p);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 6;
@@ -427,7 +427,7 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
-                       cudaStream_t stream, uint32_t score_mode) {
+                       cudaStream_t stream, uint32_t score_mode, uint32_t beam_mult) {
     if (k > HN_K_MAX) return 9;
     HnswParams p;
     p.g = g;
@@ -436,11 +436,12 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.pitch = pitch;
     p.dim = dim;
     p.k = k;
-    // `ef` is the reference's nominal ef.  The reference's layer search (crate hnsw 0.11) pops a
-    // LIFO stack with no distance-based early exit and evaluates ~160·ef nodes per query; a sorted
-    // beam of width W evaluates ~20·W.  W = 8·ef is therefore the equal-work setting, and the one at
-    // which recall@10 is >= the reference restatement's at every ef of the sweep (tests/bench).
-    uint64_t W = static_cast<uint64_t>(ef < 1 ? 1 : ef) * HN_BEAM_MULT;
+    // `ef` is the reference's ef (hnsw.rs:437: min(k, len); > 0 = the additive sweep knob).  The device beam is
+    // W = beam_mult x ef.  beam_mult = 1 is EQUAL ef; the reference's layer search (crate hnsw 0.11) pops a LIFO
+    // stack with no distance-based early exit and evaluates far more nodes per unit of ef than a sorted beam
+    // (measured visit counts sit next to the recall figures in bench.py / tests/golden), so larger factors trade
+    // the visit-count gap for recall (vl_hnsw_set_beam_factor).
+    uint64_t W = static_cast<uint64_t>(ef < 1 ? 1 : ef) * (beam_mult < 1 ? 1 : beam_mult);
     if (W < k) W = k;
     if (W > HN_EF_MAX) W = HN_EF_MAX;
     p.out_ids = d_out_ids;

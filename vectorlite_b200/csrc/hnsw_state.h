@@ -4,8 +4,10 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -48,6 +50,7 @@ struct HnswState {
     std::mutex entry_mu;
     int builder = 0;                   // HNSW_BUILDER_*
     uint32_t score_mode = 0;           // 0 exact flat similarity, 1 reference-quantised (hnsw.rs:478 + 51-75)
+    uint32_t beam_mult = 8;            // device beam width = beam_mult x ef (vl_hnsw_set_beam_factor)
     int last_builder = 0;              // builder used by the last bulk add
     uint64_t last_build_us = 0;
     // ---- device copy ----
@@ -56,17 +59,32 @@ struct HnswState {
     size_t d_n_cap = 0, d_upper_cap = 0;
     bool dirty = true;          // graph changed since last upload
     bool deleted_dirty = true;
-    // ---- search scratch (single in-flight batch; callers serialise through the handle mutex) ----
-    std::mutex search_mu;
-    float* d_q = nullptr; size_t q_cap = 0;
-    unsigned char* d_out = nullptr; unsigned char* h_out = nullptr; size_t out_cap = 0;
-    unsigned long long* d_visited = nullptr;
+    // ---- reader side (src/client.rs:398: many searches under one read lock) ----
+    // graph_mu: a search holds it shared while its kernel reads the device graph; the first search after a
+    // mutation takes it exclusively to upload (hnsw_upload may reallocate the device arrays).  Searches run on
+    // their own streams / scratch (a small pool), never on the handle's mutation stream.
+    std::shared_mutex graph_mu;
+    struct SearchCtx {
+        cudaStream_t stream = nullptr;
+        float* d_q = nullptr; size_t q_cap = 0;
+        unsigned char* d_out = nullptr; unsigned char* h_out = nullptr; size_t out_cap = 0;
+        unsigned long long* d_visited = nullptr;
+        unsigned long long* h_visited = nullptr;
+        bool busy = false;
+    };
+    static constexpr int MAX_CTX = 4;
+    std::mutex ctx_mu;
+    std::condition_variable ctx_cv;
+    std::vector<std::unique_ptr<SearchCtx>> ctxs;
+    // ---- host-builder scratch kept across single adds (hnsw.rs:363-399 inserts one vector at a time) ----
+    std::vector<uint32_t> seq_stamp;
+    uint32_t seq_epoch = 0;
 };
 
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
-                       cudaStream_t stream, uint32_t score_mode = 0);
+                       cudaStream_t stream, uint32_t score_mode = 0, uint32_t beam_mult = 1);
 
 // hnsw_search.cu, construction mode: node d_order[i]'s row is query i; beam of `ef` on `level`
 int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,

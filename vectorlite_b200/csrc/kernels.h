@@ -76,11 +76,21 @@ cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t
 // query; scores in the tensor-core path's scan units, certified with its bf16 bound (finalize: tc_abs > 0)
 cudaError_t launch_flat_scan_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
                                   uint32_t nq, int metric, const ScanWork& w, bool pipelined, cudaStream_t s);
+// Certificate inputs of a scan over the bf16 mirror (rescore.cuh).  tc_abs > 0: the candidates come from a bf16 scan,
+// |approx − exact| <= tc_abs·‖x‖·‖q‖ in the worst case; e_x / e_q / e_x1: the rounding-error norms measured when the
+// mirror was built and the queries were converted (the smaller of the two bounds is used).  kp_base > 0: the kernel
+// also reports FLAG_BASE_OK when the first kp_base candidates alone would have certified the result.
+struct CertAux {
+    double tc_abs = 0.0;
+    const uint32_t* e_x = nullptr;
+    const float* e_q = nullptr;
+    const uint32_t* e_x1 = nullptr;
+    int kp_base = 0;
+};
 // merge per-CTA candidates, fp64 rescore in reference order, rank, certify (grid = nq)
-// tc_abs > 0: the candidates come from a bf16 scan, |approx − exact| <= tc_abs·‖x‖·‖q‖
 cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k,
                                  int metric, const ScanWork& w, const SearchOut& out, float eps_scale,
-                                 cudaStream_t s, double tc_abs = 0.0);
+                                 cudaStream_t s, const CertAux& aux = CertAux());
 size_t flat_scan_smem_bytes(uint32_t pitch);
 int flat_scan_max_grid_x(int device, uint32_t pitch);
 bool flat_scan_bf16_supports(uint32_t pitch);   // rows of 128 / 256 / 384 elements

@@ -18,6 +18,9 @@ struct TcState {
     uint64_t built_norm = 0, built_raw = 0;
     void* q_bf16 = nullptr;        // bf16 [q_cap][KP]
     float* qn2 = nullptr;          // fp32 [q_cap]
+    float* eq = nullptr;           // fp32 [q_cap] E_q = ‖q̃−q‖/‖q‖ of the last converted batch (certificate)
+    uint32_t* ex_bits = nullptr;   // [3] float bits, maxima over rows (integer atomicMax): [0] ‖x̃−x̂‖/‖x̂‖ of the normalised
+                                   // mirror, [1] the same for the raw mirror, [2] ‖x̃−x‖₁ of the raw mirror (manhattan)
     uint32_t q_cap = 0;
     alignas(64) CUtensorMap map_x;
     alignas(64) CUtensorMap map_q;

@@ -112,6 +112,7 @@ class ShardedFlatIndex:
         self._ring = {}          # (nq, k) -> pipelined buffer sets
         self._side = None        # side stream for the exchange (all-gather + merge)
         self._seq = 0
+        self.last_retried = 0    # queries of the last search() that were re-run after a failed certificate
 
     def fill_synthetic(self, seed: int, n_total: int, clusters: int = 0):
         lo, hi = shard_range(n_total, self.world, self.rank)
@@ -283,7 +284,10 @@ class ShardedFlatIndex:
 
     def search(self, queries: np.ndarray, k: int, metric: SimilarityMetric):
         """Host in / host out (the e2e path): H2D of the queries, sharded search, D2H of the merged
-        top-k.  A shard whose certificate fails re-runs its queries through the exact path."""
+        top-k.  Queries for which some shard's certificate failed (bit0 of the OR-ed flags, identical on every
+        rank) are re-run — those queries only — through each shard's host search, which walks the larger
+        over-selection / fp32 / exact levels by itself, and merged again.  A peer whose results did not arrive
+        within the exchange's bounded wait (bit4) leaves the merged list incomplete: that raises."""
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         nq = queries.shape[0]
         b = self._buffers(nq, k)
@@ -295,38 +299,50 @@ class ShardedFlatIndex:
             b["h_blob"].copy_(b["blob"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             hb = b["h_blob"].numpy()
-            h_flg = hb[2 * nk:].view(np.int32)[nq:2 * nq]
+            h_flg = hb[2 * nk:].view(np.int32)[nq:2 * nq].reshape(1, nq)
         else:                                              # NCCL baseline: per-shard flags [G, nq]
             b["h_blob"].copy_(b["blob"], non_blocking=True)
             h_flg = flg.cpu().numpy()
             hb = b["h_blob"].numpy()
-        if int((h_flg & 1).max()) != 0:
-            return self._search_exact(queries, k, metric)
-        return (hb[:nk].view(np.uint64).reshape(nq, k).copy(), hb[nk:2 * nk].view(np.float64).reshape(nq, k).copy(),
-                hb[2 * nk:].view(np.uint32)[:nq].copy())
+        any_flg = np.bitwise_or.reduce(h_flg, axis=0)
+        if int((any_flg & 16).max()) != 0:
+            raise VectorLiteError(6, "row-sharded exchange: a peer shard's results did not arrive within the bounded "
+                                     "wait (flag bit4); the merged top-k would be incomplete")
+        out_ids = hb[:nk].view(np.uint64).reshape(nq, k).copy()
+        out_sc = hb[nk:2 * nk].view(np.float64).reshape(nq, k).copy()
+        out_cnt = hb[2 * nk:].view(np.uint32)[:nq].copy()
+        failed = np.nonzero(any_flg & 1)[0]
+        self.last_retried = int(failed.size)
+        if failed.size:
+            ri, rs, rc = self._search_retry(queries[failed], k, metric)
+            out_ids[failed], out_sc[failed], out_cnt[failed] = ri, rs, rc
+        return out_ids, out_sc, out_cnt
 
-    def _search_exact(self, queries, k, metric):
-        # every rank saw the same gathered flags → all ranks take this branch together
-        gi, gs, gc = self.local.search_batch(queries, k, metric)  # host API handles the fallback
+    def _search_retry(self, queries, k, metric):
+        # every rank saw the same OR-ed flags → all ranks take this branch together, with the same queries
+        gi, gs, gc = self.local.search_batch(queries, k, metric)  # host API: larger K' → fp32 → exact, failing queries only
         nq = queries.shape[0]
-        b = self._buffers(nq, k)
-        r = self.rank
-        dev = torch.device("cuda", self.device)
         if self.world == 1:
             return gi, gs, gc
+        dev = torch.device("cuda", self.device)
+        r = self.rank
         nk = nq * k
-        blk = torch.zeros(b["blk"] // 8, dtype=torch.int64)
+        blk_words = int(lib().vl_packed_result_bytes(nq, k)) // 8
+        packed = torch.zeros((self.world, blk_words), dtype=torch.int64, device=dev)
+        blk = torch.zeros(blk_words, dtype=torch.int64)
         blk[0:nk] = torch.from_numpy(gi.view(np.int64).reshape(-1))
         blk[nk:2 * nk] = torch.from_numpy(gs.view(np.int64).reshape(-1))
         blk[2 * nk:3 * nk] = torch.from_numpy(gi.astype(np.int64).reshape(-1))   # sharded stores: id == global position
         blk.view(torch.int32)[6 * nk:6 * nk + nq] = torch.from_numpy(gc.view(np.int32))
-        b["packed"][r].copy_(blk.to(dev))
-        dist.all_gather_into_tensor(b["packed"].view(-1), b["packed"][r].clone(), group=self.group)
-        stream = _current_stream()
-        st = lib().vl_merge_topk_packed_device(self.device, self.world, nq, k, b["packed"].data_ptr(),
-                                               b["o_ids"].data_ptr(), b["o_sc"].data_ptr(), b["o_pos"].data_ptr(),
-                                               b["o_cnt"].data_ptr(), C.c_void_p(stream))
+        mine = blk.to(dev)
+        dist.all_gather_into_tensor(packed.view(-1), mine, group=self.group)
+        o_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        o_sc = torch.zeros((nq, k), dtype=torch.float64, device=dev)
+        o_pos = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        o_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
+        st = lib().vl_merge_topk_packed_device(self.device, self.world, nq, k, packed.data_ptr(), o_ids.data_ptr(),
+                                               o_sc.data_ptr(), o_pos.data_ptr(), o_cnt.data_ptr(),
+                                               C.c_void_p(_current_stream()))
         if st != VL_OK:
             raise VectorLiteError(st, _err())
-        return (b["o_ids"].cpu().numpy().view(np.uint64), b["o_sc"].cpu().numpy(),
-                b["o_cnt"].cpu().numpy().view(np.uint32))
+        return (o_ids.cpu().numpy().view(np.uint64), o_sc.cpu().numpy(), o_cnt.cpu().numpy().view(np.uint32))
