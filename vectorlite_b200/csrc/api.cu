@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "batch.h"
+#include "combiner.h"
 #include "hnsw.h"
 #include "kernels.h"
 #include "tc_state.h"
@@ -137,16 +138,7 @@ struct vl_index {
     TcState tc;
     std::mutex tc_mu;
     // ---- combiner: concurrent single-query callers are coalesced into one batched launch ----
-    struct Pending {
-        const float* q; uint32_t k; int metric; uint32_t ef;
-        uint64_t* ids; double* scores; uint32_t* count;
-        int rc = VL_OK; bool done = false; std::string err;
-    };
-    std::mutex comb_mu;
-    std::condition_variable comb_cv;
-    std::vector<Pending*> comb_queue;
-    bool comb_leader = false;
-    size_t comb_expect = 1;   // size of the batch that just completed: how many callers the next leader may wait for
+    Combiner comb;
     // ---- adaptive over-selection (search_levels) ----
     Boost boost_single, boost_batch;
     // ---- hnsw ----
@@ -742,114 +734,21 @@ extern "C" {
 const char* vl_last_error(void) { return g_err; }
 const char* vl_version(void) { return "vectorlite-b200 0.1.0 (sm_100a)"; }
 
-// Combiner shared by the flat and HNSW host searches.  The reference serves searches from many worker threads
-// under a read lock (client.rs:398, server.rs:258-275): concurrent SINGLE-query callers on one handle are combined
-// — the first one in becomes the leader, runs whatever has queued up behind the running launch as ONE batched
-// search (flat: the tensor-core pipeline serves up to 128 queries in the time of 1.6 single-query scans; HNSW: one
-// CTA per query, all in flight together) and hands the results back.  A lone caller runs its own query at once: no
-// added latency, no timer.  `impl(queries, m, ids, scores, counts)` is the uncombined search of m queries.
-constexpr size_t COMBINE_MAX = 128;
-static int combine_wait_us() {
-    static const int us = [] { const char* e = getenv("VL_COMBINE_WAIT_US"); return e ? std::max(0, atoi(e)) : 100; }();
-    return us;
-}
-using SearchImpl = std::function<int(const float*, uint32_t, uint32_t, int, uint32_t, uint64_t*, double*, uint32_t*)>;
-static int combined_search(vl_index* h, const float* query, uint32_t qdim, uint32_t k, int metric, uint32_t ef,
-                           uint64_t* out_ids, double* out_scores, uint32_t* out_counts, const SearchImpl& impl) {
-    vl_index::Pending me;
-    me.q = query; me.k = k; me.metric = metric; me.ef = ef; me.ids = out_ids; me.scores = out_scores; me.count = out_counts;
-    std::unique_lock<std::mutex> lk(h->comb_mu);
-    h->comb_queue.push_back(&me);
-    while (!me.done) {
-        if (h->comb_leader) {
-            h->comb_cv.wait(lk);
-            continue;
-        }
-        // leader: take the head of the queue and everything behind it with the same (k, metric, ef)
-        h->comb_leader = true;
-        if (h->comb_expect > 1 && h->comb_queue.size() < h->comb_expect) {
-            // Re-forming cohort: the callers of the batch that just completed are waking up and coming back with
-            // their next query.  Without this the first one back (usually the old leader) runs a batch of ONE while
-            // the other callers queue behind it — measured at 16 callers: batches alternate 1, 15, 1, 15 …
-            // Bounded (combine_wait_us, default 100 µs), and only after a batch that DID combine callers: a lone
-            // caller (comb_expect == 1) never waits.
-            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(combine_wait_us());
-            while (h->comb_queue.size() < h->comb_expect && std::chrono::steady_clock::now() < deadline) {
-                lk.unlock();
-                std::this_thread::yield();
-                lk.lock();
-            }
-        }
-        std::vector<vl_index::Pending*> batch;
-        const uint32_t bk = h->comb_queue.front()->k, bef = h->comb_queue.front()->ef;
-        const int bm = h->comb_queue.front()->metric;
-        for (auto it = h->comb_queue.begin(); it != h->comb_queue.end() && batch.size() < COMBINE_MAX;) {
-            if ((*it)->k == bk && (*it)->metric == bm && (*it)->ef == bef) {
-                batch.push_back(*it);
-                it = h->comb_queue.erase(it);
-            } else {
-                ++it;
-            }
-        }
-        lk.unlock();
-        const uint32_t m = static_cast<uint32_t>(batch.size());
-        int rc;
-        std::string err;
-        if (m == 1) {
-            vl_index::Pending* p = batch[0];
-            rc = impl(p->q, 1u, bk, bm, bef, p->ids, p->scores, p->count);
-            if (rc != VL_OK) err = vl_last_error();
-        } else {
-            std::vector<float> qs(static_cast<size_t>(m) * qdim);
-            std::vector<uint64_t> ids(static_cast<size_t>(m) * bk);
-            std::vector<double> sc(static_cast<size_t>(m) * bk);
-            std::vector<uint32_t> cnt(m);
-            for (uint32_t i = 0; i < m; ++i) memcpy(qs.data() + static_cast<size_t>(i) * qdim, batch[i]->q, qdim * sizeof(float));
-            rc = impl(qs.data(), m, bk, bm, bef, ids.data(), sc.data(), cnt.data());
-            if (rc != VL_OK) err = vl_last_error();
-            for (uint32_t i = 0; i < m; ++i) {
-                memcpy(batch[i]->ids, ids.data() + static_cast<size_t>(i) * bk, bk * sizeof(uint64_t));
-                memcpy(batch[i]->scores, sc.data() + static_cast<size_t>(i) * bk, bk * sizeof(double));
-                *batch[i]->count = cnt[i];
-            }
-            h->stats[ST_COMBINED] += m;
-        }
-        std::vector<int> rcs(m, rc);
-        std::vector<std::string> errs(m, err);
-        if (rc != VL_OK && m > 1) {   // a batch-level failure (e.g. one NaN query) must not leak to the other callers
-            for (uint32_t i = 0; i < m; ++i) {
-                vl_index::Pending* p = batch[i];
-                rcs[i] = impl(p->q, 1u, bk, bm, bef, p->ids, p->scores, p->count);
-                errs[i] = rcs[i] != VL_OK ? std::string(vl_last_error()) : std::string();
-            }
-        }
-        lk.lock();
-        for (uint32_t i = 0; i < m; ++i) {
-            batch[i]->rc = rcs[i];
-            batch[i]->err = errs[i];
-            batch[i]->done = true;
-        }
-        h->comb_leader = false;
-        h->comb_expect = m;
-        h->comb_cv.notify_all();
-    }
-    lk.unlock();
-    if (me.rc != VL_OK) return fail(me.rc, "%s", me.err.c_str());   // re-raise in the caller's thread
-    return VL_OK;
-}
-
-static bool combiner_enabled() {
-    static const bool on = getenv("VL_DISABLE_COMBINER") == nullptr;
-    return on;
-}
+// Combiner (combiner.h) shared by the flat and HNSW host searches and by the shard group: concurrent SINGLE-query
+// callers on one handle are combined into one batched search by the first caller in.
+static bool combiner_enabled() { return Combiner::enabled(); }
 
 int flat_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
                 uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
-    if (!combiner_enabled() || nq != 1 || h->n == 0 || k == 0 || qdim != h->dim)
+    // Small stores (a scan of a few tens of microseconds, BASELINE config 1: 10K rows) are served per caller on
+    // the handle's stream pool: a combined batch would wait for its cohort longer than the scan takes.
+    const bool tiny = static_cast<uint64_t>(h->n) * h->pitch < (1ull << 24);
+    if (!combiner_enabled() || nq != 1 || h->n == 0 || k == 0 || qdim != h->dim || tiny)
         return flat_search_impl(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
-    return combined_search(h, queries, qdim, k, metric, 0u, out_ids, out_scores, out_counts,
-                           [&](const float* q, uint32_t m, uint32_t bk, int bm, uint32_t, uint64_t* ids, double* sc,
-                               uint32_t* cnt) { return flat_search_impl(h, q, m, qdim, bk, bm, ids, sc, cnt); });
+    return h->comb.search(queries, qdim, k, metric, 0u, out_ids, out_scores, out_counts,
+                          [&](const float* q, uint32_t m, uint32_t bk, int bm, uint32_t, uint64_t* ids, double* sc,
+                              uint32_t* cnt) { return flat_search_impl(h, q, m, qdim, bk, bm, ids, sc, cnt); },
+                          &h->stats[ST_COMBINED]);
 }
 
 static int create_common(uint32_t dim, int device, vl_index** out, int type) {
@@ -1108,7 +1007,7 @@ int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdi
             return VL_OK;
         };
         if (combiner_enabled() && nq == 1)   // concurrent single-query callers share one launch
-            return combined_search(h, queries, qdim, k, metric, ef, out_ids, out_scores, out_counts, impl);
+            return h->comb.search(queries, qdim, k, metric, ef, out_ids, out_scores, out_counts, impl, &h->stats[ST_COMBINED]);
         return impl(queries, nq, k, metric, ef, out_ids, out_scores, out_counts);
     }
     return flat_search(h, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);

@@ -22,10 +22,7 @@
 #include <vector>
 
 #include "../../include/vectorlite_cuda.h"
-
-namespace vl {
-void set_last_error(const char* msg);   // api.cu: the thread-local string behind vl_last_error()
-}
+#include "combiner.h"
 
 namespace {
 
@@ -58,6 +55,7 @@ struct vl_group {
     std::condition_variable cv;
     std::deque<Task> queue;
     bool stop = false;
+    vl::Combiner comb;   // concurrent single-query callers → ONE fan-out of a small batch to all shards
 
     void run_shard(Call* c, uint32_t s) {
         c->ids[s].resize(static_cast<size_t>(c->nq) * c->k);
@@ -121,12 +119,28 @@ void vl_group_destroy(vl_group* g) {   // the shards stay alive: they belong to 
 
 uint32_t vl_group_size(const vl_group* g) { return g ? static_cast<uint32_t>(g->shards.size()) : 0u; }
 
+static int group_search_impl(vl_group* g, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                             uint64_t* out_ids, double* out_scores, uint32_t* out_counts);
+
 int vl_group_search(vl_group* g, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
                     uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
     if (!g || !out_ids || !out_scores || !out_counts || (!queries && nq)) {
         vl::set_last_error("null argument");
         return VL_ERR_INVALID;
     }
+    // One query per call from many threads (the reference's serving pattern, client.rs:398): the first caller in
+    // runs whatever queued up behind the running search as one batch — ONE fan-out to the shards (where it takes
+    // the tensor-core pipeline) and one merge, instead of callers x shards helper hand-offs.
+    if (vl::Combiner::enabled() && nq == 1 && k > 0 && qdim == g->dim && g->shards.size() > 1)
+        return g->comb.search(queries, qdim, k, metric, 0u, out_ids, out_scores, out_counts,
+                              [g, qdim](const float* q, uint32_t m, uint32_t bk, int bm, uint32_t, uint64_t* ids, double* sc,
+                                        uint32_t* cnt) { return group_search_impl(g, q, m, qdim, bk, bm, ids, sc, cnt); },
+                              nullptr);
+    return group_search_impl(g, queries, nq, qdim, k, metric, out_ids, out_scores, out_counts);
+}
+
+static int group_search_impl(vl_group* g, const float* queries, uint32_t nq, uint32_t qdim, uint32_t k, int metric,
+                             uint64_t* out_ids, double* out_scores, uint32_t* out_counts) {
     for (size_t i = 0; i < static_cast<size_t>(nq) * k; ++i) { out_ids[i] = ~0ull; out_scores[i] = 0.0; }
     for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0u;
     // shards that hold rows; flat.rs:99-104: the dimension is only checked when the store is non-empty
