@@ -9,6 +9,8 @@ n = int(os.environ.get("N", 1_000_000)); B = int(os.environ.get("B", 1024)); k =
 reps = int(os.environ.get("REPS", 10))
 idx = ShardedFlatIndex(384, rank=0, world=1, device=0)
 idx.fill_synthetic(42, n)
+if os.environ.get("PIPELINED", "1") != "0":
+    idx.local.set_pipelined(True)     # consecutive batches are chained with programmatic dependent launch
 q = torch.from_numpy(oracle.synth_rows(43, 1000, B, 384)).cuda()
 out = {}
 for m in [vl.SimilarityMetric(int(x)) for x in os.environ.get("METRICS", "0").split(",")]:

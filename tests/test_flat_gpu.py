@@ -547,7 +547,7 @@ def test_concurrent_single_query_callers_are_combined(vl, oracle_mod):
     client.rs:398 under a read lock): the handle combines what queues up behind a running launch into one batched
     search.  Every caller must still get exactly its own oracle answer; errors stay with their caller."""
     import threading
-    n, dim, k, T, per = 20000, 384, 10, 8, 12
+    n, dim, k, T, per = 60000, 384, 10, 8, 12      # (stores below 2^24 elements are served per caller, uncombined)
     rows = oracle_mod.synth_rows(42, 0, n, dim)
     q = oracle_mod.synth_rows(43, 0, T * per, dim)
     idx = vl.FlatIndex(dim)

@@ -86,11 +86,15 @@ struct Slot {  // one in-flight search: stream + scratch, all sized on demand
     uint64_t* d_ids = nullptr; double* d_scores = nullptr; uint32_t* d_counts = nullptr; uint32_t* d_flags = nullptr;
     uint64_t* h_ids = nullptr; double* h_scores = nullptr; uint32_t* h_counts = nullptr; uint32_t* h_flags = nullptr;
     size_t out_used = 0;
-    // batched pipeline scratch
-    uint64_t* b_cand = nullptr; size_t b_cand_cap = 0;
-    uint32_t* b_count = nullptr; size_t b_count_cap = 0;
-    float* b_tau = nullptr; size_t b_tau_cap = 0;
-    uint32_t* b_qflags = nullptr; size_t b_qflags_cap = 0;
+    // batched pipeline scratch; two sets so that pipelined device searches can chain batches (batch.h)
+    struct BatchSet {
+        uint64_t* cand = nullptr; size_t cand_cap = 0;
+        uint32_t* count = nullptr; size_t count_cap = 0;
+        float* tau = nullptr; size_t tau_cap = 0;
+        uint32_t* qflags = nullptr; size_t qflags_cap = 0;
+    } bset[2];
+    float* b_gmax = nullptr; size_t b_gmax_cap = 0;
+    uint32_t batch_parity = 0;
     // exact path
     double* d_exact = nullptr; size_t exact_cap = 0;
     uint32_t* d_exflags = nullptr;
@@ -221,20 +225,24 @@ int slot_reserve(vl_index* h, Slot& s, uint32_t nq, uint32_t k, int Kp, int grid
     return VL_OK;
 }
 
-int slot_reserve_batch(Slot& s, uint32_t nq, BatchWork* w) {
+int slot_reserve_batch(Slot& s, uint32_t nq, BatchWork* w, uint32_t set = 0) {
     int st;
-    if ((st = grow_dev(s.b_cand, s.b_cand_cap, static_cast<size_t>(nq) * BATCH_CAPQ))) return st;
-    if ((st = grow_dev(s.b_count, s.b_count_cap, nq))) return st;
-    if ((st = grow_dev(s.b_tau, s.b_tau_cap, nq))) return st;
-    if ((st = grow_dev(s.b_qflags, s.b_qflags_cap, nq))) return st;
-    w->cand = s.b_cand; w->count = s.b_count; w->tau = s.b_tau; w->qflags = s.b_qflags; w->capq = BATCH_CAPQ;
+    Slot::BatchSet& b = s.bset[set & 1u];
+    if ((st = grow_dev(b.cand, b.cand_cap, static_cast<size_t>(nq) * BATCH_CAPQ))) return st;
+    if ((st = grow_dev(b.count, b.count_cap, nq))) return st;
+    if ((st = grow_dev(b.tau, b.tau_cap, nq))) return st;
+    if ((st = grow_dev(b.qflags, b.qflags_cap, nq))) return st;
+    if ((st = grow_dev(s.b_gmax, s.b_gmax_cap, static_cast<size_t>(nq) * GMAX_STRIDE))) return st;
+    w->cand = b.cand; w->count = b.count; w->tau = b.tau; w->qflags = b.qflags; w->capq = BATCH_CAPQ;
+    w->gmax = s.b_gmax;
     return VL_OK;
 }
 
 void slot_free(Slot& s) {
     cudaFree(s.d_q); cudaFreeHost(s.h_q); cudaFree(s.cand); cudaFree(s.cand_count); cudaFree(s.cand_max); cudaFree(s.ctl); cudaFree(s.early);
     cudaFree(s.d_out); cudaFreeHost(s.h_out);
-    cudaFree(s.b_cand); cudaFree(s.b_count); cudaFree(s.b_tau); cudaFree(s.b_qflags);
+    for (auto& b : s.bset) { cudaFree(b.cand); cudaFree(b.count); cudaFree(b.tau); cudaFree(b.qflags); }
+    cudaFree(s.b_gmax);
     cudaFree(s.d_exact); cudaFree(s.d_exflags);
     exact_scratch_free(s.exs);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -1062,7 +1070,9 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
             const uint32_t m = std::min(BATCH_CHUNK, nq - q0);
             BatchWork bw;
-            int st = slot_reserve_batch(s, m, &bw);
+            // pipelined handles chain consecutive batches (PDL): alternate the scratch set the rescore kernel reads
+            const uint32_t parity = h->pipelined ? (s.batch_parity++ & 1u) : 0u;
+            int st = slot_reserve_batch(s, m, &bw, parity);
             if (st) return st;
             const SearchOut out = out_at(q0);
             uint64_t nl = 0;
@@ -1071,6 +1081,8 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
                 CU(tc_prepare(&h->tc, v, h->cap, metric, m, stream));
                 bt.usable = h->tc.usable;
                 bt.scratch = &h->tc;
+                bt.chain_batches = h->pipelined;
+                bt.parity = parity;
             }
             CU(launch_batch_flat(v, d_queries + static_cast<size_t>(q0) * h->pitch, m, k, metric, Kp, bw, out,
                                  want_tc ? &bt : nullptr, &nl, stream));

@@ -17,6 +17,9 @@
 // Tile kernel: CTA = 256 threads, 128 rows × 128 queries, 8×8 micro-tile per thread with rows and
 // queries interleaved by 16 (conflict-free shared-memory reads, query reads are warp broadcasts),
 // K chunks of 32 columns staged through registers into transposed, odd-pitch shared tiles.
+#include <cmath>
+#include <cstdlib>
+
 #include "batch.h"
 #include "rescore.cuh"
 #include "tc_state.h"
@@ -169,6 +172,8 @@ __global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint3
     __shared__ unsigned long long s_min;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();                              // the scan that produced the candidates is complete and visible
+    if (tid == 0) pdl_launch_dependents();   // the next stage's scan may be launched (its epilogue waits for us)
     const int n = static_cast<int>(n_override ? n_override : min(count[q], capq));
     if (n <= Kp) {
         if (tid == 0) count[q] = n;  // clamp (overflow already flagged); threshold unchanged
@@ -232,6 +237,35 @@ __global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint3
     }
 }
 
+// Threshold estimation (tensor path, large stores): tau[q] = the Kp-th largest of the G group maxima written by the
+// SCAN_GROUPMAX stage — Kp disjoint groups each hold a row scoring >= it, so it is a valid lower bound of the Kp-th
+// best score of the store.  One warp per query; the exact Kp-th largest is built bit by bit on the orderable
+// pattern (32 count-and-vote steps over <= 32 values per lane).
+__global__ void __launch_bounds__(256) batch_tau_kernel(const float* __restrict__ gmax, uint32_t G, int Kp, float* tau,
+                                                        uint32_t nq) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    if (q >= nq) return;
+    uint32_t v[GMAX_STRIDE / 32];
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(GMAX_STRIDE / 32); ++i) {
+        const uint32_t g = static_cast<uint32_t>(i) * 32 + lane;
+        v[i] = g < G ? f32_orderable(__ldcg(gmax + static_cast<size_t>(q) * GMAX_STRIDE + g)) : 0u;
+    }
+    uint32_t T = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = T | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < static_cast<int>(GMAX_STRIDE / 32); ++i) cnt += v[i] >= c;
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (cnt >= Kp) T = c;
+    }
+    if (lane == 0) tau[q] = (G >= static_cast<uint32_t>(Kp) && T != 0u) ? orderable_f32(T) : -INFINITY;
+}
+
 // per query: load the (sorted, <= Kp) survivors and run the shared rescore / rank / certify phases
 __global__ void __launch_bounds__(FIN_THREADS) batch_rescore_kernel(FinalizeParams p, const uint32_t* count,
                                                                        const uint32_t* qflags, uint32_t capq) {
@@ -293,6 +327,8 @@ __global__ void batch_rescore_stream_kernel(FinalizeParams p, const uint32_t* co
     __shared__ int s_nan;
     const uint32_t qi = blockIdx.x;
     const int tid = threadIdx.x, nthreads = blockDim.x;
+    pdl_wait();                              // the last select is complete and visible
+    if (tid == 0) pdl_launch_dependents();   // chained batches: the next batch's query conversion may start
     const int nc = static_cast<int>(min(count[qi], static_cast<uint32_t>(p.Kp)));
     // ---- sort the (<= Kp, unordered) survivors by key, descending: rank by counting ------------------
     const uint64_t* mine = p.cand + static_cast<size_t>(qi) * capq;
@@ -403,8 +439,18 @@ static cudaError_t launch_rescore_stream(const FinalizeParams& p, const BatchWor
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    kern<<<nq, KpR + RS_SPARE, smem, s>>>(p, w.count, w.qflags, w.capq, KpR);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nq);
+    cfg.blockDim = dim3(KpR + RS_SPARE);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;   // joins the batch's PDL chain (the kernel starts with griddepcontrol.wait)
+    return cudaLaunchKernelEx(&cfg, kern, p, static_cast<const uint32_t*>(w.count), static_cast<const uint32_t*>(w.qflags),
+                              w.capq, KpR);
 }
 
 static size_t rescore_smem(int Kp, int CH) {
@@ -454,26 +500,72 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
         if ((e = cudaFuncSetAttribute(batch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e;
         attr[dev & 63] = true;
     }
-    batch_init_kernel<<<(nq + 255) / 256, 256, 0, s>>>(nq, w.count, w.tau, w.qflags);
+    const bool use_tc = tc && tc->usable && metric != MANHATTAN;
+    // (tensor path: the per-query state is reset by the query-conversion kernel, batch_tc.cu)
+    if (!use_tc) batch_init_kernel<<<(nq + 255) / 256, 256, 0, s>>>(nq, w.count, w.tau, w.qflags);
     uint64_t nl = 1;
     // Geometric stage schedule: after a select, tau is the K'-th best of the first S rows, so the next
     // stage over rows [S, r·S) keeps ≈ K'·(r−1) survivors per query; r is chosen so that this stays
     // below half the candidate buffer (capq = 4096 → r = 16 for K' = 64, 9 for K' = 224, 4 for K' = 512).
-    const bool use_tc = tc && tc->usable && metric != MANHATTAN;
     uint32_t sel_len = 2;
     while (sel_len < w.capq) sel_len <<= 1;
     uint32_t ratio = w.capq / (2u * static_cast<uint32_t>(Kp));
     ratio = ratio < 2u ? 2u : (ratio > 16u ? 16u : ratio);
+    static const int forced_ratio = [] { const char* e = getenv("VL_BATCH_RATIO"); return e ? atoi(e) : 0; }();
+    if (forced_ratio >= 2) ratio = static_cast<uint32_t>(forced_ratio);
     uint32_t lo = 0;
     uint64_t hi64 = min(v.n, min(w.capq, 4096u));   // stage 0: everything is kept
+    // Tensor path on large stores: instead of keeping (and selecting from) every score of the first 4096 rows, an
+    // ESTIMATION stage scans the first S0 = 32·G rows writing only the maximum of every 32-row group; the Kp-th
+    // largest group maximum is the first threshold — as tight as the exact Kp-th best of S_eq rows, where a group
+    // exceeds it with probability Kp/G, i.e. a row with p = 1 − (1 − Kp/G)^(1/32): S_eq = Kp/p ≈ 15K rows for
+    // Kp = 64, G = 512.  Those rows are scanned again by the first filtered stage (1.6 % of a 1M-row store), which can
+    // therefore be ~4x longer at the same survivor count: one stage and the 4096-key select less per batch.
+    static const bool no_estimate = getenv("VL_BATCH_NO_ESTIMATE") != nullptr;
+    const uint32_t G = Kp <= 256 ? 512u : GMAX_STRIDE;
+    const uint32_t S0 = G * 32u;
+    const bool estimate = use_tc && w.gmax && !no_estimate && v.n >= 4ull * S0 && static_cast<uint32_t>(Kp) * 2u <= G;
+    if (estimate) {
+        if ((e = batch_scan_tensor(v, *tc, d_queries, nq, metric, 0, S0, w, s, true, SCAN_GROUPMAX)) != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((nq + 7) / 8);
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if ((e = cudaLaunchKernelEx(&cfg, batch_tau_kernel, static_cast<const float*>(w.gmax), G, Kp, w.tau, nq)) != cudaSuccess)
+            return e;
+        nl += 2;
+        const double p_row = 1.0 - pow(1.0 - static_cast<double>(Kp) / G, 1.0 / 32.0);
+        hi64 = static_cast<uint64_t>(static_cast<double>(Kp) / p_row) * ratio;
+    }
+    bool first = !estimate;
     while (lo < v.n) {
         uint32_t hi = static_cast<uint32_t>(hi64 > v.n ? v.n : hi64);
-        if (lo > 0) hi = min(v.n, (hi + 255u) & ~255u);   // later stages start on 256-row tile boundaries
-        if (use_tc) e = batch_scan_tensor(v, *tc, d_queries, nq, metric, lo, hi, w, s);
+        const uint32_t mode = (use_tc && first && hi <= w.capq) ? SCAN_DIRECT : SCAN_FILTER;
+        if (lo > 0 || estimate) hi = min(v.n, (hi + 255u) & ~255u);   // filtered stages end on 256-row tile boundaries
+        if (use_tc) e = batch_scan_tensor(v, *tc, d_queries, nq, metric, lo, hi, w, s, first, mode);
         else e = batch_scan_cuda_cores(v, d_queries, nq, metric, lo, hi, w, s);
         if (e != cudaSuccess) return e;
-        const uint32_t n_override = (use_tc && lo == 0 && hi <= w.capq) ? hi - lo : 0u;  // tensor stage 0 is atomics-free
-        batch_select_kernel<<<nq, 256, sel_len * sizeof(uint64_t), s>>>(w.cand, w.count, w.tau, w.capq, Kp, n_override);
+        first = false;
+        const uint32_t n_override = mode == SCAN_DIRECT ? hi - lo : 0u;  // tensor stage 0 of a small store is atomics-free
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nq);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = sel_len * sizeof(uint64_t);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if ((e = cudaLaunchKernelEx(&cfg, batch_select_kernel, w.cand, w.count, w.tau, w.capq, Kp, n_override)) != cudaSuccess)
+                return e;
+        }
         nl += 2;
         lo = hi;
         hi64 = static_cast<uint64_t>(hi) * ratio;
@@ -496,12 +588,14 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     if (use_tc) {   // measured rounding-error norms of the mirror that was scanned and of this batch's queries
         const TcState* ts = static_cast<const TcState*>(tc->scratch);
         p.e_x = ts->ex_bits ? ts->ex_bits + (metric == COSINE ? 0 : 1) : nullptr;
-        p.e_q = ts->eq;
+        p.e_q = ts->eq + static_cast<size_t>(tc->parity & 1u) * ts->q_cap;
     }
     p.peers = out.peers;
     p.kp_base = kp_base;
     const int KpR = (Kp + 31) & ~31;
     if (nq >= 8 && KpR + RS_SPARE <= 1024) {   // many queries: small streaming CTAs, one wave
+        // (16-column chunks would let the CTA fit beside a resident scan CTA of a chained next batch — measured
+        // SLOWER, 0.732 vs 0.705 ms per 1024-query batch: the gathers then compete with the MMA stage's TMA stream)
         p.CH = KpR <= 64 ? 32 : 16;
         const size_t smem = rescore_stream_smem(KpR, p.CH, v.pitch);
         switch (metric) {

@@ -125,7 +125,10 @@ struct Params {
     uint32_t* count;
     uint32_t* qflags;
     uint32_t capq, nq, row_lo, row_hi, kch, qblocks, tiles;
-    uint32_t direct;        // stage 0: every score is kept, slot = row − row_lo, no atomics
+    uint32_t direct;        // stage 0 of small stores: every score is kept, slot = row − row_lo, no atomics
+    uint32_t groupmax;      // threshold-estimation stage: only the maximum of every 32-row group is written
+    float* gmax;            // [nq][GMAX_STRIDE]
+    uint32_t pdl_first;     // first kernel of the batch's PDL chain: EVERY warp waits for the query conversion
 };
 
 template <int METRIC, int CS>
@@ -172,6 +175,16 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     const bool active = t0 < p.tiles && tstride > 0;
+    // Programmatic dependent launch: the kernels of a batch (convert → scan → select → scan → … → rescore) are
+    // chained so that each one is launched while its predecessor is still running; every kernel releases its
+    // dependents only AFTER its own wait has returned, so a kernel never overlaps anything older than its direct
+    // predecessor.  Here the predecessor is the select that produced tau / count / cand: only the epilogue reads
+    // those, so the TMA producer and the MMA issuer start on the (immutable) bf16 rows and queries at once — except
+    // in the first scan of a batch, whose predecessor WRITES the bf16 queries.
+    if (p.pdl_first) {
+        pdl_wait();
+        if (threadIdx.x == 0) pdl_launch_dependents();
+    }
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -239,7 +252,11 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int cbase = ((warp - 2) >> 2) * (BN / 2);     // this warp's half of the tile's columns
         const uint32_t q = qblock * BM + quarter * 32 + lane;
         const bool qvalid = qblock < p.qblocks && q < p.nq;
-        float tau = qvalid ? __ldg(p.tau + q) : INFINITY;
+        if (!p.pdl_first) {
+            pdl_wait();                                        // the select before this stage is complete and visible
+            if (etid == 0) pdl_launch_dependents();
+        }
+        float tau = qvalid ? __ldcg(p.tau + q) : INFINITY;    // (written by the previous kernel: no read-only path)
         float qn = 0.f;
         if (METRIC == EUCLIDEAN) {
             qn = qvalid ? __ldg(p.qn2 + q) : 0.f;
@@ -286,6 +303,20 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 // one 32-column chunk: branch-free survivor mask (2 instructions per score), then a
                 // compact loop over the (rare) set bits — keeps the hot loop inside the instruction cache
                 auto process = [&](const uint32_t (&v)[32], int c0, float xn_lane) {   // xn_lane: ‖x‖² of column c0 + lane
+                    if (p.groupmax) {
+                        // Threshold estimation: the K'-th largest of the maxima of G disjoint row groups is reached by K'
+                        // distinct rows, hence a valid lower bound of the K'-th best score — no score is stored, the
+                        // rows are scanned again (filtered) by the next stage.
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float s = __uint_as_float(v[i]);
+                            if (METRIC == EUCLIDEAN) s = fmaf(2.f, s, -__shfl_sync(0xFFFFFFFFu, xn_lane, i)) - qn;
+                            if (row0 + c0 + i < p.row_hi) m = fmaxf(m, s);   // fmaxf drops NaNs: the bound only gets weaker
+                        }
+                        if (qvalid) p.gmax[static_cast<size_t>(q) * GMAX_STRIDE + ((row0 - p.row_lo + c0) >> 5)] = m;
+                        return;
+                    }
                     if (p.direct) {
                         // stage 0 keeps every score: transpose 32 queries × 16 columns through this warp's 2 KB of
                         // the (idle) survivor queue so that each half-warp stores 16 consecutive keys of ONE
@@ -424,8 +455,19 @@ __global__ void to_bf16_rows_kernel(const float* __restrict__ rows, const float*
 
 // fp32 queries [nq][pitch] → bf16 [nq_pad][KP] (+ ‖q‖² for L2); rows >= nq are zero
 __global__ void to_bf16_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t nq_pad, uint32_t dim,
-                                       uint32_t pitch, uint32_t KP, __nv_bfloat16* out, float* qn2, float* eq) {
+                                       uint32_t pitch, uint32_t KP, __nv_bfloat16* out, float* qn2, float* eq,
+                                       uint32_t* count, float* tau, uint32_t* qflags) {
     const uint32_t r = blockIdx.x;
+    // Chained batches (launched with the PDL attribute behind the previous batch's rescore kernel, which released us
+    // after ITS wait — every scan of that batch is complete, so the bf16 query staging may be overwritten; what the
+    // rescore still reads is double buffered).  This kernel only completes after the rescore has (wait at the end),
+    // which keeps "kernel j complete ⇒ kernel j−1 complete" true along the whole chain.
+    pdl_launch_dependents();            // the first scan may be launched: all of its warps wait for this grid
+    if (threadIdx.x == 0 && r < nq) {   // per-query state of the staged scan (was a kernel of its own)
+        count[r] = 0u;
+        tau[r] = -INFINITY;
+        qflags[r] = 0u;
+    }
     double ss = 0.0, err2 = 0.0;
     for (uint32_t c = threadIdx.x; c < KP; c += blockDim.x) {
         const float x = (r < nq && c < dim) ? q[static_cast<size_t>(r) * pitch + c] : 0.f;
@@ -449,6 +491,7 @@ __global__ void to_bf16_queries_kernel(const float* __restrict__ q, uint32_t nq,
         qn2[r] = static_cast<float>(t);
         if (eq) eq[r] = t > 0.0 ? __double2float_ru(sqrt(e / t) * 1.000001) : 0.f;   // E_q = ‖q̃−q‖/‖q‖, rounded up
     }
+    pdl_wait();
     (void)nq_pad;
 }
 
@@ -542,7 +585,7 @@ cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int me
         t->q_bf16 = nullptr; t->qn2 = nullptr; t->eq = nullptr;
         if ((e = cudaMalloc(&t->q_bf16, static_cast<size_t>(nq_pad) * KP * 2)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&t->qn2, static_cast<size_t>(nq_pad) * 4)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&t->eq, static_cast<size_t>(nq_pad) * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&t->eq, 2 * static_cast<size_t>(nq_pad) * 4)) != cudaSuccess) return e;   // [2][q_cap]: see BatchTensor::parity
         t->q_cap = nq_pad;
     }
     t->usable = true;
@@ -559,26 +602,41 @@ static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mq, const
     cfg.blockDim = dim3(tc::THREADS);
     cfg.dynamicSmemBytes = tc::SMEM_TOTAL;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CS;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = CS > 1 ? 1 : 0;
+    cfg.numAttrs = CS > 1 ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, mx, mq, p);
 }
 
 cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const float* d_q, uint32_t nq, int metric,
-                              uint32_t lo, uint32_t hi, const BatchWork& w, cudaStream_t s) {
+                              uint32_t lo, uint32_t hi, const BatchWork& w, cudaStream_t s, bool first, uint32_t mode) {
     TcState* t = static_cast<TcState*>(bt.scratch);
     if (!t || !t->usable) return cudaErrorNotSupported;
     const uint32_t KP = t->KP;
     const uint32_t nq_pad = (nq + tc::BM - 1) / tc::BM * tc::BM;
     const int CS = tc_cluster_size();
-    if (lo == 0) {  // first stage of a batch: convert the queries, (re)encode the maps
-        tc::to_bf16_queries_kernel<<<nq_pad, 128, 0, s>>>(d_q, nq, nq_pad, v.dim, v.pitch, KP,
-                                                        static_cast<__nv_bfloat16*>(t->q_bf16), t->qn2, t->eq);
+    if (first) {  // first scan of a batch: convert the queries, (re)encode the maps
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nq_pad);
+            cfg.blockDim = dim3(128);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = bt.chain_batches ? 1 : 0;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, tc::to_bf16_queries_kernel, d_q, nq, nq_pad, v.dim, v.pitch, KP,
+                                               static_cast<__nv_bfloat16*>(t->q_bf16), t->qn2,
+                                               t->eq + static_cast<size_t>(bt.parity & 1u) * t->q_cap, w.count, w.tau, w.qflags);
+            if (e != cudaSuccess) return e;
+        }
         const void* mirror = metric == COSINE ? t->rows_norm : t->rows_raw;
         if (t->maps_n != v.n || t->maps_base != mirror || t->maps_cs != CS) {
             if (!make_map(&t->map_x, mirror, v.n, KP, tc::BN / CS)) return cudaErrorUnknown;
@@ -594,7 +652,12 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     p.capq = w.capq; p.nq = nq; p.row_lo = lo; p.row_hi = hi; p.kch = KP / tc::BK;
     p.qblocks = nq_pad / tc::BM;
     p.tiles = (hi - lo + tc::BN - 1) / tc::BN;
-    p.direct = (lo == 0 && hi <= w.capq) ? 1u : 0u;
+    p.direct = mode == SCAN_DIRECT ? 1u : 0u;
+    p.groupmax = mode == SCAN_GROUPMAX ? 1u : 0u;
+    p.gmax = w.gmax;
+    p.pdl_first = first ? 1u : 0u;
+    if (p.direct && !(lo == 0 && hi <= w.capq)) return cudaErrorInvalidValue;
+    if (p.groupmax && (!w.gmax || (hi - lo + 31) / 32 > GMAX_STRIDE)) return cudaErrorInvalidValue;
     int sms = 148;
     int dev = 0;
     cudaGetDevice(&dev);
