@@ -109,6 +109,7 @@ struct Builder {
         uint32_t epoch = 0;
         std::vector<std::pair<float, uint32_t>> W, sel, pruned;
         std::vector<uint32_t> nb;
+        std::vector<uint64_t> touched;   // (node << 8) | level of adjacency rows written by this thread
     };
     using DI = std::pair<float, uint32_t>;
 
@@ -190,8 +191,10 @@ struct Builder {
             uint32_t* a = adj(q, l);
             for (size_t i = 0; i < mine.size(); ++i) a[i] = mine[i].second;
             unlock(q);
+            sc.touched.push_back((static_cast<uint64_t>(q) << 8) | static_cast<uint64_t>(l));
             for (const DI& e : mine) {  // back-links, capped at M (upper) / M0 (layer 0)
                 const uint32_t t = e.second;
+                sc.touched.push_back((static_cast<uint64_t>(t) << 8) | static_cast<uint64_t>(l));
                 lock(t);
                 uint32_t* ta = adj(t, l);
                 const uint32_t c = cap(l);
@@ -275,7 +278,8 @@ void hnsw_state_release_device(HnswState* s) {
     s->d_level = s->d_deleted = nullptr;
     s->d_ids = nullptr; s->d_inv_norm = nullptr;
     s->d_n_cap = s->d_upper_cap = 0;
-    s->dirty = s->deleted_dirty = true;
+    s->dirty = s->deleted_dirty = s->dirty_full = true;
+    s->uploaded_n = s->uploaded_upper = 0;
 }
 
 bool hnsw_has_id(const HnswState* s, uint64_t id) { return s->index_of.count(id) != 0; }
@@ -345,6 +349,7 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
     }
     s->live += n;
     s->dirty = true;
+    if (first == 0) s->dirty_full = true;
     auto finish = [&](int builder) {
         if (n >= 1024) {
             s->last_builder = builder;
@@ -378,7 +383,14 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
         sc.stamp.swap(s->seq_stamp);
         sc.epoch = s->seq_epoch;
         if (sc.stamp.size() < total) sc.stamp.resize(total + total / 4 + 64, 0);
-        struct Keep { HnswState* s; Builder::Scratch* sc; ~Keep() { sc->stamp.swap(s->seq_stamp); s->seq_epoch = sc->epoch; } } keep{s, &sc};
+        struct Keep {
+            HnswState* s; Builder::Scratch* sc;
+            ~Keep() {
+                sc->stamp.swap(s->seq_stamp);
+                s->seq_epoch = sc->epoch;
+                s->touched.insert(s->touched.end(), sc->touched.begin(), sc->touched.end());
+            }
+        } keep{s, &sc};
         const uint32_t seq_end = static_cast<uint32_t>(std::min<uint64_t>(total, std::max<uint32_t>(first, 256)));
         for (; start < seq_end; ++start) b.insert(start, sc);
         if (nthreads == 1 || total - start < 1024) {
@@ -399,6 +411,7 @@ int hnsw_add_rows(HnswState* s, const uint64_t* ids, const float* rows, uint64_t
             }
         });
     for (auto& x : th) x.join();
+    s->dirty_full = true;   // a parallel bulk insert rewrites a large part of the graph: upload it whole
     return finish(HNSW_BUILDER_HOST);
 }
 
@@ -478,20 +491,56 @@ static int upload_locked(HnswState* s, cudaStream_t stream) {
     const size_t n = s->level.size();
     if (n == 0) return 0;
     if (s->dirty) {
-        if (int st = hnsw_reserve_device(s, n)) return st;
-        cudaMemcpyAsync(s->d_adj0, s->adj0.data(), n * s->M0 * 4, cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(s->d_upper_off, s->upper_off.data(), n * 4, cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(s->d_level, s->level.data(), n, cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(s->d_ids, s->id_of.data(), n * 8, cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync(s->d_inv_norm, s->inv_norm.data(), n * 4, cudaMemcpyHostToDevice, stream);
-        if (!s->upper.empty())
-            cudaMemcpyAsync(s->d_upper, s->upper.data(), s->upper.size() * 4, cudaMemcpyHostToDevice, stream);
-        s->deleted_dirty = true;
+        const bool fits = n <= s->d_n_cap && s->upper.size() <= s->d_upper_cap && s->d_adj0 && (s->d_upper || s->upper.empty());
+        const bool partial = !s->dirty_full && fits && s->uploaded_n <= n && s->touched.size() <= 4096;
+        if (partial) {
+            // new nodes: contiguous tails of every per-node array and of the upper-level slots
+            const size_t n0 = s->uploaded_n, m = n - n0;
+            if (m) {
+                cudaMemcpyAsync(s->d_adj0 + n0 * s->M0, s->adj0.data() + n0 * s->M0, m * s->M0 * 4, cudaMemcpyHostToDevice, stream);
+                cudaMemcpyAsync(s->d_upper_off + n0, s->upper_off.data() + n0, m * 4, cudaMemcpyHostToDevice, stream);
+                cudaMemcpyAsync(s->d_level + n0, s->level.data() + n0, m, cudaMemcpyHostToDevice, stream);
+                cudaMemcpyAsync(s->d_ids + n0, s->id_of.data() + n0, m * 8, cudaMemcpyHostToDevice, stream);
+                cudaMemcpyAsync(s->d_inv_norm + n0, s->inv_norm.data() + n0, m * 4, cudaMemcpyHostToDevice, stream);
+                cudaMemcpyAsync(s->d_deleted + n0, s->deleted.data() + n0, m, cudaMemcpyHostToDevice, stream);
+            }
+            if (s->upper.size() > s->uploaded_upper)
+                cudaMemcpyAsync(s->d_upper + s->uploaded_upper, s->upper.data() + s->uploaded_upper,
+                                (s->upper.size() - s->uploaded_upper) * 4, cudaMemcpyHostToDevice, stream);
+            // re-written adjacency rows of older nodes (back-links), each once
+            std::sort(s->touched.begin(), s->touched.end());
+            s->touched.erase(std::unique(s->touched.begin(), s->touched.end()), s->touched.end());
+            for (const uint64_t t : s->touched) {
+                const size_t node = static_cast<size_t>(t >> 8);
+                const int lvl = static_cast<int>(t & 0xFF);
+                if (node >= n0) continue;   // part of the tail copied above (its upper slots too)
+                if (lvl == 0) {
+                    cudaMemcpyAsync(s->d_adj0 + node * s->M0, s->adj0.data() + node * s->M0, s->M0 * 4, cudaMemcpyHostToDevice, stream);
+                } else {
+                    const size_t off = (static_cast<size_t>(s->upper_off[node]) + lvl - 1) * s->M;
+                    if (off < s->uploaded_upper)
+                        cudaMemcpyAsync(s->d_upper + off, s->upper.data() + off, s->M * 4, cudaMemcpyHostToDevice, stream);
+                }
+            }
+        } else {
+            if (int st = hnsw_reserve_device(s, n)) return st;
+            cudaMemcpyAsync(s->d_adj0, s->adj0.data(), n * s->M0 * 4, cudaMemcpyHostToDevice, stream);
+            cudaMemcpyAsync(s->d_upper_off, s->upper_off.data(), n * 4, cudaMemcpyHostToDevice, stream);
+            cudaMemcpyAsync(s->d_level, s->level.data(), n, cudaMemcpyHostToDevice, stream);
+            cudaMemcpyAsync(s->d_ids, s->id_of.data(), n * 8, cudaMemcpyHostToDevice, stream);
+            cudaMemcpyAsync(s->d_inv_norm, s->inv_norm.data(), n * 4, cudaMemcpyHostToDevice, stream);
+            if (!s->upper.empty())
+                cudaMemcpyAsync(s->d_upper, s->upper.data(), s->upper.size() * 4, cudaMemcpyHostToDevice, stream);
+            s->deleted_dirty = true;
+        }
+        s->touched.clear();
+        s->uploaded_n = n;
+        s->uploaded_upper = s->upper.size();
     }
     if (s->deleted_dirty)
         cudaMemcpyAsync(s->d_deleted, s->deleted.data(), n, cudaMemcpyHostToDevice, stream);
     if (cudaStreamSynchronize(stream) != cudaSuccess) return 6;
-    s->dirty = s->deleted_dirty = false;
+    s->dirty = s->deleted_dirty = s->dirty_full = false;
     return 0;
 }
 

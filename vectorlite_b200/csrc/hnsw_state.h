@@ -59,6 +59,12 @@ struct HnswState {
     size_t d_n_cap = 0, d_upper_cap = 0;
     bool dirty = true;          // graph changed since last upload
     bool deleted_dirty = true;
+    // Incremental adds (host builder) only touch the new nodes' rows and the adjacency rows of their back-link
+    // targets: those are listed here so the next search uploads a few hundred bytes instead of the whole graph
+    // (~140 MB at 1M nodes).  `dirty_full` forces the full upload (device build, reallocation, too many rows).
+    bool dirty_full = true;
+    size_t uploaded_n = 0, uploaded_upper = 0;          // nodes / upper-array words already on the device
+    std::vector<uint64_t> touched;                      // (node << 8) | level of re-written adjacency rows
     // ---- reader side (src/client.rs:398: many searches under one read lock) ----
     // graph_mu: a search holds it shared while its kernel reads the device graph; the first search after a
     // mutation takes it exclusively to upload (hnsw_upload may reallocate the device arrays).  Searches run on
