@@ -107,6 +107,17 @@ int vl_hnsw_build_info(const vl_index* h, uint64_t* out_builder, uint64_t* out_m
  * (hnsw.rs:113-174) / 1000 (hnsw.rs:478) through convert_distance_to_similarity (hnsw.rs:51-75), bit for bit,
  * including its second division by 1000 for cosine and dot product; results ordered by that score. */
 int vl_hnsw_set_score_mode(vl_index* h, int mode);
+/* Graph persistence.  The reference does not serialise its graph (#[serde(skip)], hnsw.rs:199-200): on
+ * load it re-inserts every vector in HashMap order (hnsw.rs:322-348) and gets a different graph every time.  Here a
+ * saved index can restore the very graph it was searched with: vl_hnsw_export_graph writes levels + adjacency of
+ * all nodes into a caller buffer of vl_hnsw_graph_bytes bytes (VL_ERR_UNSUPPORTED if the graph holds soft-deleted
+ * nodes: their rows are not part of vl_index_export — rebuild on load instead, as the reference does);
+ * vl_hnsw_import_graph installs such a blob into an EMPTY index together with the rows in the exported order
+ * (vl_index_export), without building.  The blob is validated (parameters, sizes, structure audit). */
+int vl_hnsw_graph_bytes(const vl_index* h, uint64_t* out_bytes);
+int vl_hnsw_export_graph(const vl_index* h, void* buf, uint64_t cap, uint64_t* out_written);
+int vl_hnsw_import_graph(vl_index* h, const uint64_t* ids, const float* rows, uint64_t n, const void* blob,
+                         uint64_t bytes);
 /* Device beam width of a search = factor x ef, where ef is the reference's ef (hnsw.rs:437: min(k, len), or the
  * `ef` argument of vl_index_search when > 0).  1 = equal ef.  Range [1, 64]. */
 int vl_hnsw_set_beam_factor(vl_index* h, uint32_t factor);

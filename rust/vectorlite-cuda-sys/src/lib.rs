@@ -37,6 +37,9 @@ extern "C" {
     pub fn vl_hnsw_set_builder(h: *mut vl_index, builder: c_int) -> c_int;
     pub fn vl_hnsw_set_score_mode(h: *mut vl_index, mode: c_int) -> c_int;
     pub fn vl_hnsw_set_beam_factor(h: *mut vl_index, factor: u32) -> c_int;
+    pub fn vl_hnsw_graph_bytes(h: *const vl_index, out_bytes: *mut u64) -> c_int;
+    pub fn vl_hnsw_export_graph(h: *const vl_index, buf: *mut c_void, cap: u64, out_written: *mut u64) -> c_int;
+    pub fn vl_hnsw_import_graph(h: *mut vl_index, ids: *const u64, rows: *const f32, n: u64, blob: *const c_void, bytes: u64) -> c_int;
     pub fn vl_last_error() -> *const c_char;
 }
 

@@ -168,3 +168,51 @@ def test_batch_search_and_micro_batcher(vl):
     c.disable_micro_batching()
     assert [[(r.id, r.score) for r in a] for a in out] == [[(r.id, r.score) for r in a] for a in single]
     assert sum(served) == 64 and max(served) > 1          # concurrent callers really shared launches
+
+
+def test_hnsw_graph_is_persisted_and_restored(vl, tmp_path):
+    """the reference rebuilds its HNSW graph on every load, in HashMap order (hnsw.rs:199-200,
+    322-348) — a different graph each time.  The optional `.graph` side file restores the SAVED graph: same
+    adjacency (structure audit equal), same answers bit for bit, nothing rebuilt; a corrupt side file or a graph
+    with soft-deleted nodes falls back to the reference behaviour (rebuild)."""
+    import oracle
+    from vectorlite_b200 import collection as col
+    n, dim, k = 6000, 48, 10
+    M = vl.SimilarityMetric
+    rows = oracle.synth_rows(42, 0, n, dim, 32)
+    q = oracle.synth_rows(43, 0, 32, dim, 32)
+    ids = (np.arange(n, dtype=np.uint64) * 7 + 3)[::-1].copy()          # not sorted: the order must come from the side file
+    h = vl.HNSWIndex(dim, M.Cosine, ef_construction=100)
+    h.add_batch(ids, rows, [f"t{int(i)}" for i in ids], None)
+    c = col.Collection("g", h)
+    want = h.search_batch(q, k, M.Cosine, 16)
+    path = str(tmp_path / "g.vlc")
+    c.save_to_file(path)
+    import os
+    assert os.path.exists(path + col.GRAPH_SUFFIX)
+    c2 = col.Collection.load_from_file(path)
+    h2 = c2.index_read()
+    assert h2.len() == n and h2.graph_check() == h.graph_check()
+    assert h2.build_info()["builder"] == "none"                          # nothing was built
+    got = h2.search_batch(q, k, M.Cosine, 16)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint64), want[1].view(np.uint64))
+    assert h2.search(q[0], 1, M.Cosine)[0].text.startswith("t")
+    # the restored index keeps working as an index: incremental add + search
+    h2.add(vl.Vector(10**9, q[1]))
+    assert h2.search(q[1], 1, M.Cosine)[0].id == 10**9
+    # the .vlc alone is still a valid reference-format file: without the side file the graph is rebuilt
+    os.remove(path + col.GRAPH_SUFFIX)
+    c3 = col.Collection.load_from_file(path)
+    assert c3.index_read().len() == n and c3.index_read().graph_check()["invalid"] == 0
+    # corrupt side file → rebuild, never a broken graph
+    c.save_to_file(path)
+    with open(path + col.GRAPH_SUFFIX, "r+b") as f:
+        f.seek(16 + 8 * n + 200)
+        f.write(b"\xff" * 64)
+    c4 = col.Collection.load_from_file(path)
+    assert c4.index_read().len() == n and c4.index_read().graph_check()["invalid"] == 0
+    # soft-deleted nodes: no side file is written (their rows are not exported)
+    h.delete(int(ids[5]))
+    c.save_to_file(path)
+    assert not os.path.exists(path + col.GRAPH_SUFFIX)
+    assert col.Collection.load_from_file(path).index_read().len() == n - 1

@@ -130,6 +130,9 @@ def lib():
         "vl_hnsw_build_info": (i32, [vp, u64p, u64p]),
         "vl_hnsw_set_score_mode": (i32, [vp, i32]),
         "vl_hnsw_set_beam_factor": (i32, [vp, u32]),
+        "vl_hnsw_graph_bytes": (i32, [vp, u64p]),
+        "vl_hnsw_export_graph": (i32, [vp, vp, u64, u64p]),
+        "vl_hnsw_import_graph": (i32, [vp, u64p, fp, u64, vp, u64]),
         "vl_hnsw_graph_check": (i32, [vp, u64p]),
         "vl_index_search": (i32, [vp, fp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
         "vl_index_search_f64": (i32, [vp, dp, u32, u32, u32, i32, u32, u64p, dp, u32p]),
@@ -404,6 +407,32 @@ class HNSWIndex(_CudaIndex):
         st = self._L.vl_hnsw_set_builder(self._h, self.BUILDERS[builder])
         if st != VL_OK:
             raise VectorLiteError(st, _err())
+
+    def export_graph(self) -> bytes:
+        """Levels + adjacency of the current graph (vl_hnsw_export_graph); raises VectorLiteError (UNSUPPORTED) when
+        the graph holds soft-deleted nodes."""
+        nb = C.c_uint64(0)
+        st = self._L.vl_hnsw_graph_bytes(self._h, C.byref(nb))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        buf = np.empty(nb.value, dtype=np.uint8)
+        w = C.c_uint64(0)
+        st = self._L.vl_hnsw_export_graph(self._h, buf.ctypes.data_as(C.c_void_p), nb.value, C.byref(w))
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        return buf[:w.value].tobytes()
+
+    def import_graph(self, ids, rows, blob: bytes) -> None:
+        """Restore a saved graph into this EMPTY index over the rows it was exported with (same order)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        b = np.frombuffer(blob, dtype=np.uint8)
+        st = self._L.vl_hnsw_import_graph(self._h, _ptr(ids, C.c_uint64), _ptr(rows, C.c_float), rows.shape[0],
+                                          b.ctypes.data_as(C.c_void_p), b.size)
+        if st != VL_OK:
+            raise VectorLiteError(st, _err())
+        for i in ids:
+            self._meta.setdefault(int(i), ("", None))
 
     def set_beam_factor(self, factor: int) -> None:
         """Device beam width = factor x ef (ef = the reference's min(k, len), hnsw.rs:437, or the `ef` argument);

@@ -412,6 +412,51 @@ def collection_to_document(collection: Collection) -> dict:
             "index": index}
 
 
+GRAPH_SUFFIX = ".graph"          # optional side file next to the .vlc: the HNSW graph itself
+_GRAPH_MAGIC = b"VLGRAPH1"
+
+
+def _save_graph_side_file(idx, path: str) -> None:
+    """The reference does not persist its graph (#[serde(skip)], hnsw.rs:199-200) and rebuilds it on load in HashMap
+    order — a different graph after every load.  Next to the reference-compatible .vlc this writes the graph of a
+    single-device HNSW index (levels + adjacency, vl_hnsw_export_graph) with the insertion order of the ids, so a
+    reloaded collection answers with the very graph that was saved.  Indexes with soft-deleted nodes (or replicas on
+    several devices) have no side file and are rebuilt on load as before."""
+    side = path + GRAPH_SUFFIX
+    blob = None
+    if isinstance(idx, HNSWIndex) and idx.len() > 0:
+        try:
+            blob = idx.export_graph()
+        except VectorLiteError:
+            blob = None
+    if blob is None:
+        if os.path.exists(side):
+            os.remove(side)                                              # never leave a stale graph behind
+        return
+    ids, _ = idx.export()
+    tmp = side + ".tmp"
+    with open(tmp, "wb") as f:
+        f.write(_GRAPH_MAGIC)
+        f.write(np.uint64(len(ids)).tobytes())
+        f.write(np.ascontiguousarray(ids, dtype=np.uint64).tobytes())
+        f.write(blob)
+    os.replace(tmp, side)
+
+
+def _load_graph_side_file(path: str):
+    side = path + GRAPH_SUFFIX
+    if not os.path.exists(side):
+        return None
+    with open(side, "rb") as f:
+        raw = f.read()
+    if len(raw) < 16 or raw[:8] != _GRAPH_MAGIC:
+        return None
+    n = int(np.frombuffer(raw[8:16], dtype=np.uint64)[0])
+    if len(raw) < 16 + 8 * n:
+        return None
+    return np.frombuffer(raw[16:16 + 8 * n], dtype=np.uint64).copy(), raw[16 + 8 * n:]
+
+
 def save_collection_to_file(collection: Collection, path: str) -> None:
     doc = collection_to_document(collection)
     parent = os.path.dirname(os.path.abspath(path))
@@ -420,6 +465,7 @@ def save_collection_to_file(collection: Collection, path: str) -> None:
     with open(tmp, "w") as f:
         json.dump(doc, f, indent=2)                                      # to_string_pretty
     os.replace(tmp, path)                                                # atomic rename
+    _save_graph_side_file(collection.index_read(), path)
 
 
 def load_collection_from_file(path: str, device: int = 0, devices: Optional[Sequence[int]] = None,
@@ -450,13 +496,27 @@ def load_collection_from_file(path: str, device: int = 0, devices: Optional[Sequ
             raise PersistenceError("Invalid dimension: cannot be 0")      # hnsw.rs:288-290
         index = make_index(int(body["dim"]), IndexType.HNSW, SimilarityMetric[body["metric"]], device, devices)
         vv = body["vector_values"]
-        if vv:                                                           # hnsw.rs:322-348 re-inserts every vector
-            keys = sorted(vv, key=int)                                   # (deterministic order here; HashMap order there)
-            ids = np.array([int(k) for k in keys], dtype=np.uint64)
-            rows = np.array([vv[k] for k in keys], dtype=np.float32)
+        if vv:
             md = body.get("metadata", {})
-            index.add_batch(ids, rows, [md.get(k, {}).get("text", "") for k in keys],
-                            [md.get(k, {}).get("metadata") for k in keys])
+            restored = False
+            side = _load_graph_side_file(path) if isinstance(index, HNSWIndex) else None
+            if side is not None and len(side[0]) == len(vv) and all(str(int(i)) in vv for i in side[0]):
+                ids = side[0]                                            # the saved graph over the saved insertion order
+                rows = np.array([vv[str(int(i))] for i in ids], dtype=np.float32)
+                try:
+                    index.import_graph(ids, rows, side[1])
+                    for i in ids:
+                        m = md.get(str(int(i)), {})
+                        index._meta[int(i)] = (m.get("text", ""), m.get("metadata"))
+                    restored = True
+                except VectorLiteError:                                  # blob does not match: rebuild below
+                    restored = False
+            if not restored:                                             # hnsw.rs:322-348 re-inserts every vector
+                keys = sorted(vv, key=int)                               # (deterministic order here; HashMap order there)
+                ids = np.array([int(k) for k in keys], dtype=np.uint64)
+                rows = np.array([vv[k] for k in keys], dtype=np.float32)
+                index.add_batch(ids, rows, [md.get(k, {}).get("text", "") for k in keys],
+                                [md.get(k, {}).get("metadata") for k in keys])
     else:
         raise InvalidFormat(f"unknown index variant '{kind}'")
     return Collection(name, index)

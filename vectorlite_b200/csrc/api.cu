@@ -407,32 +407,41 @@ int flat_add_batch(vl_index* h, const uint64_t* ids, const float* rows, uint64_t
 // order-preserving removal of one storage position (flat.rs:94 `retain` keeps order)
 int flat_remove_pos(vl_index* h, uint32_t pos) {
     const uint64_t tail = h->n - pos - 1;
+    // the bf16 mirrors are positional too: shift them with the rows (rebuilding a mirror costs a pass over the
+    // whole arena — 4.5 ms on a 12.5M-row shard); a mirror that is only partly built is simply dropped
+    const bool keep_norm = h->tc.rows_norm && h->tc.built_norm == h->n;
+    const bool keep_raw = h->tc.rows_raw && h->tc.sq_norm && h->tc.built_raw == h->n;
     if (tail) {
-        const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / (h->pitch * sizeof(float)));
-        float* tmp = nullptr;
-        CU(cudaMalloc(&tmp, std::min(chunk_rows, tail) * h->pitch * sizeof(float)));
-        for (uint64_t off = 0; off < tail; off += chunk_rows) {
-            const uint64_t m = std::min(chunk_rows, tail - off);
-            const size_t bytes = m * h->pitch * sizeof(float);
-            cudaMemcpyAsync(tmp, h->d_rows + (pos + 1 + off) * h->pitch, bytes, cudaMemcpyDeviceToDevice, h->mut_stream);
-            cudaMemcpyAsync(h->d_rows + (pos + off) * h->pitch, tmp, bytes, cudaMemcpyDeviceToDevice, h->mut_stream);
-        }
-        // side arrays are small: bounce through tmp when it fits, else chunk as well
-        const uint64_t side_chunk = std::min<uint64_t>(tail, std::min(chunk_rows, tail) * h->pitch * sizeof(float) / 8);
-        for (uint64_t off = 0; off < tail; off += side_chunk) {
-            const uint64_t m = std::min(side_chunk, tail - off);
-            cudaMemcpyAsync(tmp, h->d_inv_norm + pos + 1 + off, m * 4, cudaMemcpyDeviceToDevice, h->mut_stream);
-            cudaMemcpyAsync(h->d_inv_norm + pos + off, tmp, m * 4, cudaMemcpyDeviceToDevice, h->mut_stream);
-            if (h->d_ids) {
-                cudaMemcpyAsync(tmp, h->d_ids + pos + 1 + off, m * 8, cudaMemcpyDeviceToDevice, h->mut_stream);
-                cudaMemcpyAsync(h->d_ids + pos + off, tmp, m * 8, cudaMemcpyDeviceToDevice, h->mut_stream);
+        const size_t chunk_bytes = 64ull << 20;
+        char* tmp = nullptr;
+        const size_t row_bytes = h->pitch * sizeof(float);
+        CU(cudaMalloc(&tmp, std::min<uint64_t>(chunk_bytes, tail * row_bytes)));
+        // overlapping device-to-device moves are bounced through tmp, chunk by chunk, front to back
+        auto shift = [&](void* base, size_t elem_bytes) {
+            if (!base) return;
+            char* b = static_cast<char*>(base);
+            const uint64_t per = std::max<uint64_t>(1, std::min<uint64_t>(chunk_bytes, tail * row_bytes) / elem_bytes);
+            for (uint64_t off = 0; off < tail; off += per) {
+                const uint64_t m = std::min(per, tail - off);
+                cudaMemcpyAsync(tmp, b + (pos + 1 + off) * elem_bytes, m * elem_bytes, cudaMemcpyDeviceToDevice, h->mut_stream);
+                cudaMemcpyAsync(b + (pos + off) * elem_bytes, tmp, m * elem_bytes, cudaMemcpyDeviceToDevice, h->mut_stream);
             }
+        };
+        shift(h->d_rows, row_bytes);
+        shift(h->d_inv_norm, sizeof(float));
+        shift(h->d_ids, sizeof(uint64_t));
+        if (keep_norm) shift(h->tc.rows_norm, static_cast<size_t>(h->tc.KP) * 2);
+        if (keep_raw) {
+            shift(h->tc.rows_raw, static_cast<size_t>(h->tc.KP) * 2);
+            shift(h->tc.sq_norm, sizeof(float));
         }
         cudaError_t e = cudaStreamSynchronize(h->mut_stream);
         cudaFree(tmp);
         CU(e);
     }
-    h->tc.built_norm = h->tc.built_raw = 0;  // bf16 mirrors are positional: rebuild lazily
+    h->tc.built_norm = keep_norm ? h->n - 1 : 0;
+    h->tc.built_raw = keep_raw ? h->n - 1 : 0;
+    h->tc.maps_n = 0;   // the TMA map encodes the row count
     const uint64_t id = h->ids_host[pos];
     h->id_to_pos.erase(id);
     h->ids_host.erase(h->ids_host.begin() + pos);
@@ -963,6 +972,39 @@ int vl_hnsw_set_score_mode(vl_index* h, int mode) {
     if (!h || h->type != VL_INDEX_HNSW) return fail(VL_ERR_INVALID, "not an HNSW index");
     if (mode != 0 && mode != 1) return fail(VL_ERR_INVALID, "score mode must be 0 (exact) or 1 (reference-quantised)");
     hnsw_set_score_mode(h->hnsw.get(), static_cast<uint32_t>(mode));
+    return VL_OK;
+}
+
+int vl_hnsw_graph_bytes(const vl_index* h, uint64_t* out_bytes) {
+    if (!h || h->type != VL_INDEX_HNSW || !out_bytes) return fail(VL_ERR_INVALID, "not an HNSW index");
+    *out_bytes = hnsw_graph_blob_bytes(h->hnsw.get());
+    return VL_OK;
+}
+
+int vl_hnsw_export_graph(const vl_index* h, void* buf, uint64_t cap, uint64_t* out_written) {
+    if (!h || h->type != VL_INDEX_HNSW || !buf) return fail(VL_ERR_INVALID, "not an HNSW index / null buffer");
+    size_t w = 0;
+    const int st = hnsw_export_graph(h->hnsw.get(), buf, cap, &w);
+    if (out_written) *out_written = w;
+    if (st == 9) return fail(VL_ERR_UNSUPPORTED, "the graph holds soft-deleted nodes whose rows are not exported; rebuild on load");
+    if (st) return fail(VL_ERR_INVALID, "graph buffer too small: need %llu bytes", static_cast<unsigned long long>(w));
+    return VL_OK;
+}
+
+int vl_hnsw_import_graph(vl_index* h, const uint64_t* ids, const float* rows, uint64_t n, const void* blob, uint64_t bytes) {
+    if (!h || h->type != VL_INDEX_HNSW || !ids || !rows || !blob) return fail(VL_ERR_INVALID, "null argument / not an HNSW index");
+    if (h->n != 0) return fail(VL_ERR_INVALID, "import_graph needs an empty index");
+    DeviceGuard dg(h->device);
+    std::vector<uint64_t> internal(n);
+    for (uint64_t i = 0; i < n; ++i) internal[i] = i;
+    int st = flat_add_batch(h, internal.data(), rows, n);
+    if (st) return st;
+    st = hnsw_import_graph(h->hnsw.get(), ids, rows, n, blob, bytes);
+    if (st) {
+        h->n = 0;
+        if (st == 2) return fail(VL_ERR_DUP_ID, "duplicate vector ids");
+        return fail(VL_ERR_INVALID, "graph blob does not match this index (parameters, row count or structure)");
+    }
     return VL_OK;
 }
 

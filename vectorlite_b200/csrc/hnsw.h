@@ -37,6 +37,14 @@ bool hnsw_soft_delete(HnswState* s, uint64_t id);
 void hnsw_graph_check(const HnswState* s, uint64_t out[6]);
 // live rows in insertion order: up to `cap` starting at live position `first` (rows come from the host copy)
 uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t* out_ids, float* out_rows);
+// Graph persistence.  The reference does not serialise its graph (#[serde(skip)], hnsw.rs:199-200) and
+// re-inserts every vector on load in HashMap order (hnsw.rs:322-348): a different graph after every load.  The blob
+// holds levels + adjacency of all nodes (versioned header, little endian); import installs it over the same rows
+// in the same order without building.  Export refuses graphs with soft-deleted nodes (their rows are not part of
+// vl_index_export): 9 = unsupported.  Import validates sizes, parameters and the structure (graph_check).
+size_t hnsw_graph_blob_bytes(const HnswState* s);
+int hnsw_export_graph(const HnswState* s, void* buf, size_t cap, size_t* written);
+int hnsw_import_graph(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n, const void* blob, size_t bytes);
 // flatten + upload the graph if it changed since the last upload (takes the graph lock exclusively)
 int hnsw_upload(HnswState* s, cudaStream_t stream);
 // Re-entrant: uploads a changed graph under the exclusive graph lock, then searches under the shared lock on a

@@ -468,6 +468,106 @@ uint64_t hnsw_export(const HnswState* s, uint64_t first, uint64_t cap, uint64_t*
     return written;
 }
 
+// ---- graph persistence ------------------------------------------------------------------------------------
+namespace {
+struct GraphBlobHeader {
+    char magic[8];          // "VLHNSWG1"
+    uint32_t dim, metric, M, M0, efc;
+    int32_t max_level;
+    uint32_t entry, reserved;
+    uint64_t n, upper_words, rng_state;
+};
+}  // namespace
+
+size_t hnsw_graph_blob_bytes(const HnswState* s) {
+    const size_t n = s->level.size();
+    return sizeof(GraphBlobHeader) + n /*level*/ + n * 4 /*upper_off*/ + n * s->M0 * 4 + s->upper.size() * 4;
+}
+
+int hnsw_export_graph(const HnswState* s, void* buf, size_t cap, size_t* written) {
+    const size_t n = s->level.size();
+    if (s->live != n) return 9;   // soft-deleted nodes: their rows are not exported, the graph cannot be restored
+    const size_t need = hnsw_graph_blob_bytes(s);
+    if (written) *written = need;
+    if (!buf || cap < need) return 5;
+    GraphBlobHeader hd;
+    std::memset(&hd, 0, sizeof hd);
+    std::memcpy(hd.magic, "VLHNSWG1", 8);
+    hd.dim = s->dim; hd.metric = static_cast<uint32_t>(s->metric); hd.M = s->M; hd.M0 = s->M0; hd.efc = s->efc;
+    hd.max_level = s->max_level; hd.entry = s->entry; hd.n = n; hd.upper_words = s->upper.size();
+    hd.rng_state = s->rng_state;
+    char* p = static_cast<char*>(buf);
+    std::memcpy(p, &hd, sizeof hd); p += sizeof hd;
+    std::memcpy(p, s->level.data(), n); p += n;
+    std::memcpy(p, s->upper_off.data(), n * 4); p += n * 4;
+    std::memcpy(p, s->adj0.data(), n * s->M0 * 4); p += n * s->M0 * 4;
+    if (!s->upper.empty()) std::memcpy(p, s->upper.data(), s->upper.size() * 4);
+    return 0;
+}
+
+int hnsw_import_graph(HnswState* s, const uint64_t* ids, const float* rows, uint64_t n, const void* blob, size_t bytes) {
+    if (!s->level.empty() || n == 0 || n >= 0x7FFFFFFFull) return 5;
+    if (bytes < sizeof(GraphBlobHeader)) return 5;
+    GraphBlobHeader hd;
+    std::memcpy(&hd, blob, sizeof hd);
+    if (std::memcmp(hd.magic, "VLHNSWG1", 8) != 0 || hd.dim != s->dim || hd.metric != static_cast<uint32_t>(s->metric) ||
+        hd.M != s->M || hd.M0 != s->M0 || hd.n != n || hd.entry >= n || hd.max_level < 0 || hd.max_level > 30)
+        return 5;
+    const size_t need = sizeof(GraphBlobHeader) + n + n * 4 + n * s->M0 * 4 + hd.upper_words * 4;
+    if (bytes != need || hd.upper_words % s->M != 0) return 5;
+    const char* p = static_cast<const char*>(blob) + sizeof hd;
+    s->level.assign(reinterpret_cast<const uint8_t*>(p), reinterpret_cast<const uint8_t*>(p) + n); p += n;
+    s->upper_off.resize(n); std::memcpy(s->upper_off.data(), p, n * 4); p += n * 4;
+    s->adj0.resize(n * s->M0); std::memcpy(s->adj0.data(), p, n * s->M0 * 4); p += n * s->M0 * 4;
+    s->upper.resize(hd.upper_words);
+    if (hd.upper_words) std::memcpy(s->upper.data(), p, hd.upper_words * 4);
+    // structural validation before anything is trusted: slot ranges, then the audit every builder output passes
+    bool ok = s->level[hd.entry] == hd.max_level;
+    const size_t slots = hd.upper_words / s->M;
+    for (size_t i = 0; i < n && ok; ++i) {
+        if (s->level[i] > hd.max_level) ok = false;
+        if (s->level[i] > 0) ok = ok && s->upper_off[i] != HNSW_NONE && static_cast<size_t>(s->upper_off[i]) + s->level[i] <= slots;
+    }
+    uint64_t chk[6] = {0, 0, 0, 0, 0, 0};
+    if (ok) {
+        hnsw_graph_check(s, chk);
+        ok = chk[2] == 0 && chk[3] == 0 && chk[4] == 0;
+    }
+    if (!ok) {
+        s->level.clear(); s->upper_off.clear(); s->adj0.clear(); s->upper.clear();
+        return 5;
+    }
+    s->vecs.assign(rows, rows + n * s->dim);
+    s->inv_norm.resize(n);
+    s->deleted.assign(n, 0);
+    s->id_of.assign(ids, ids + n);
+    s->index_of.clear();
+    s->index_of.reserve(n * 2);
+    for (uint64_t i = 0; i < n; ++i) {
+        double ss = 0.0;
+        const float* v = rows + i * s->dim;
+        for (uint32_t c = 0; c < s->dim; ++c) ss += static_cast<double>(v[c]) * v[c];
+        s->inv_norm[i] = ss > 0.0 ? static_cast<float>(1.0 / std::sqrt(ss)) : 0.f;
+        s->index_of.emplace(ids[i], static_cast<uint32_t>(i));
+    }
+    if (s->index_of.size() != n) {   // duplicate ids
+        s->level.clear(); s->upper_off.clear(); s->adj0.clear(); s->upper.clear(); s->vecs.clear();
+        s->inv_norm.clear(); s->deleted.clear(); s->id_of.clear(); s->index_of.clear();
+        return 2;
+    }
+    const size_t nc = n + n / 2 + 1024;
+    s->locks.reset(new std::atomic<uint8_t>[nc]);
+    for (size_t i = 0; i < nc; ++i) s->locks[i].store(0);
+    s->locks_cap = nc;
+    s->live = n;
+    s->max_level = hd.max_level;
+    s->entry = hd.entry;
+    s->rng_state = hd.rng_state;
+    s->dirty = s->dirty_full = s->deleted_dirty = true;
+    s->last_builder = 0;
+    return 0;
+}
+
 // device graph arrays for n nodes (capacity tracked in nodes / upper slots; grown geometrically)
 int hnsw_reserve_device(HnswState* s, size_t n) {
     if (n > s->d_n_cap) {
