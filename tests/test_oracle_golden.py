@@ -243,3 +243,39 @@ def test_bench_reference_arm_helpers_run_on_cpu(oracle_mod):
     for rec in h["sweep"].values():
         assert 0.0 <= rec["recall_at_10"] <= 1.0 and rec["qps_1_thread"] > 0 and rec["qps_2_threads"] > 0
     assert h["sweep"]["64"]["recall_at_10"] >= h["sweep"]["0"]["recall_at_10"]
+
+
+def test_hnsw_fast_functors_identical(oracle_mod):
+    """The restated insert evaluates the reference's u64 functors (hnsw.rs:113-174) through a guard-banded
+    vectorised form (oracle/vl_oracle_hnsw.cpp): whenever the pre-floor value is within 1e-6 of an integer the strict
+    left-to-right functor decides.  Whole graphs — every adjacency list of every layer — and the search results must
+    be identical to the strict evaluation (VLO_HNSW_STRICT=1), for all four metrics, f32- and f64-valued rows."""
+    import os
+    n, dim = 1500, 96
+    rows = oracle_mod.synth_rows(42, 0, n, dim, 16)
+    q = oracle_mod.synth_rows(43, 0, 20, dim, 16)
+    rng = np.random.default_rng(3)
+    rows64 = rows.astype(np.float64) + 1e-9 * rng.standard_normal(rows.shape)     # not f32-representable
+    for metric in (0, 1, 2, 3):
+        for data in (rows, rows64):
+            graphs = []
+            for strict in ("1", "0"):
+                os.environ["VLO_HNSW_STRICT"] = strict
+                try:
+                    h = oracle_mod.HNSW(dim, metric, 8, 16, 60)
+                finally:
+                    os.environ.pop("VLO_HNSW_STRICT", None)
+                if data.dtype == np.float32:
+                    assert h.add_batch(None, data) == 0
+                else:
+                    for i in range(n):
+                        assert h.add(i, data[i]) == 0
+                layers = [h.export_layer(l, 8) for l in range(1, h.num_layers() + 1)]
+                res = h.search_batch(q, 10, 24, nthreads=1)
+                graphs.append((h.export_zero(16), layers, res[1], res[2], h.strict_evals()))
+            a, b = graphs
+            assert a[4] == 0 and np.array_equal(a[0], b[0]), (metric, data.dtype)
+            assert len(a[1]) == len(b[1])
+            for la, lb in zip(a[1], b[1]):
+                assert all(np.array_equal(x, y) for x, y in zip(la, lb))
+            assert np.array_equal(a[2], b[2]) and np.array_equal(a[3].view(np.uint64), b[3].view(np.uint64))
