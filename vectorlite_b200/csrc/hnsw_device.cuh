@@ -9,7 +9,8 @@ namespace vl {
 constexpr int HN_THREADS = 128;
 constexpr int HN_WARPS = HN_THREADS / 32;
 constexpr int HN_MAX_DEG = 64;
-constexpr int HN_MAX_EXPAND = 4;                 // pool entries expanded per step
+constexpr int HN_MAX_EXPAND = 4;                 // pool entries expanded per step (throughput / construction kernels)
+constexpr int HN_MAX_EXPAND_WIDE = 8;            // 16-warp CTAs (a few queries in flight: latency): twice as many, half the steps
 constexpr int HN_MAX_CAND = HN_MAX_DEG * HN_MAX_EXPAND;
 constexpr int HN_EF_MAX = 2048;   // widest internal beam
 constexpr int HN_K_MAX = 256;
@@ -20,6 +21,7 @@ struct HnswParams {
     const float* rows;
     const float* queries;
     uint32_t pitch, dim, k, ef, vis_mask, beam_cap, cand_cap;
+    uint32_t expand = 1;                  // pool entries expanded per step on the beam level (<= the kernel's MAXE)
     uint32_t score_mode = 0;              // 0: exact flat similarity, 1: the reference's quantised score (hnsw.rs:478,51-75)
     uint64_t* out_ids;
     double* out_scores;

@@ -31,6 +31,10 @@ namespace vl {
 template <int METRIC, int NCH, bool BUILD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
     constexpr int THREADS = WARPS * 32;
+    // Entries expanded per step.  A step costs two dependent global round trips (adjacency rows, then the
+    // neighbours' vectors) whatever the number of entries, so a lone query's latency is steps x ~3 us: the wide
+    // CTA expands up to 8 entries at once (256 candidates = two rounds of gathers over its 16 warps).
+    constexpr int MAXE = WARPS >= 16 ? HN_MAX_EXPAND_WIDE : HN_MAX_EXPAND;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [q[pitch] f32 — only when the query is not register-resident (NCH == 0)] | beam[beam_cap] u64 |
     //         vis[vis_mask+1] u16 | candidate keys[cand_cap] u64 | candidate ids[cand_cap] u32
@@ -175,13 +179,13 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             // ---- warp 0: the `expand` closest unexpanded pool entries, then their unvisited neighbours
             if (warp == 0) {
                 const int size = s_size;
-                const int expand = ef >= 64u ? HN_MAX_EXPAND : (ef >= 32u ? 2 : 1);
+                const int expand = ef > 1u ? static_cast<int>(min(p.expand, static_cast<uint32_t>(MAXE))) : 1;
                 int nc = 0, picked = 0;
                 // pick first (shared memory only), then fetch: the adjacency rows of all picked entries are
                 // requested together, so a step waits for ONE global-memory round trip instead of `expand`
-                uint32_t node_e[HN_MAX_EXPAND];
+                uint32_t node_e[MAXE];
 #pragma unroll
-                for (int e = 0; e < HN_MAX_EXPAND; ++e) {
+                for (int e = 0; e < MAXE; ++e) {
                     node_e[e] = HNSW_NONE;
                     if (e >= expand || picked < e) continue;      // uniform
                     unsigned long long best = ~0ull;
@@ -197,26 +201,26 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
                     if (lane == 0) s_beam[bi] |= 1ull;
                     __syncwarp();
                 }
-                const uint32_t* adj_e[HN_MAX_EXPAND];
+                const uint32_t* adj_e[MAXE];
                 if (lvl == 0) {
 #pragma unroll
-                    for (int e = 0; e < HN_MAX_EXPAND; ++e)
+                    for (int e = 0; e < MAXE; ++e)
                         adj_e[e] = p.g.adj0 + static_cast<size_t>(node_e[e] != HNSW_NONE ? node_e[e] : 0u) * p.g.M0;
                 } else {
-                    uint32_t off_e[HN_MAX_EXPAND];
+                    uint32_t off_e[MAXE];
 #pragma unroll
-                    for (int e = 0; e < HN_MAX_EXPAND; ++e) off_e[e] = node_e[e] != HNSW_NONE ? __ldg(p.g.upper_off + node_e[e]) : 0u;
+                    for (int e = 0; e < MAXE; ++e) off_e[e] = node_e[e] != HNSW_NONE ? __ldg(p.g.upper_off + node_e[e]) : 0u;
 #pragma unroll
-                    for (int e = 0; e < HN_MAX_EXPAND; ++e) adj_e[e] = p.g.upper + (static_cast<size_t>(off_e[e]) + lvl - 1) * p.g.M;
+                    for (int e = 0; e < MAXE; ++e) adj_e[e] = p.g.upper + (static_cast<size_t>(off_e[e]) + lvl - 1) * p.g.M;
                 }
                 for (uint32_t j0 = 0; j0 < deg; j0 += 32) {
                     const uint32_t j = j0 + lane;
-                    uint32_t v_e[HN_MAX_EXPAND];
+                    uint32_t v_e[MAXE];
 #pragma unroll
-                    for (int e = 0; e < HN_MAX_EXPAND; ++e)
+                    for (int e = 0; e < MAXE; ++e)
                         v_e[e] = (node_e[e] != HNSW_NONE && j < deg) ? __ldg(adj_e[e] + j) : HNSW_NONE;
 #pragma unroll
-                    for (int e = 0; e < HN_MAX_EXPAND; ++e) {
+                    for (int e = 0; e < MAXE; ++e) {
                         if (node_e[e] == HNSW_NONE) continue;     // uniform
                         const uint32_t v = v_e[e];
                         bool fresh = false;
@@ -370,7 +374,8 @@ static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStre
 }
 
 // beam / visited-cache sizing shared by search and construction; returns the dynamic smem bytes
-static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg, uint32_t k, uint32_t pitch) {
+static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg, uint32_t k, uint32_t pitch,
+                        bool wide = false) {
     const bool query_in_smem = pitch != 384;   // launch_warps: pitch 384 runs the register-resident (NCH = 3) kernels
     p.ef = W;
     uint32_t bcap = 64;
@@ -387,7 +392,11 @@ static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg
     while (cap < want && cap < 32768) cap <<= 1;
     p.vis_mask = cap - 1;
     // candidates of one step: up to HN_MAX_EXPAND expanded entries x degree; the arrays also stage the results
-    const uint32_t expand = p.ef >= 64 ? HN_MAX_EXPAND : (p.ef >= 32 ? 2 : 1);
+    // throughput / construction: 1 / 2 / 4 entries per step; wide (latency) CTAs: ef/5 entries, at most 8
+    uint32_t expand = p.ef >= 64 ? HN_MAX_EXPAND : (p.ef >= 32 ? 2 : 1);
+    if (wide) expand = std::max(1u, std::min<uint32_t>(HN_MAX_EXPAND_WIDE, p.ef / 5));
+    if (const char* e = std::getenv("VL_HNSW_EXPAND")) expand = static_cast<uint32_t>(std::max(1, std::min(atoi(e), wide ? HN_MAX_EXPAND_WIDE : HN_MAX_EXPAND)));
+    p.expand = expand;
     uint32_t cc = expand * max_deg;
     if (cc < k) cc = k;
     if (cc < 8) cc = 8;
@@ -449,7 +458,8 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.out_counts = d_out_counts;
     p.visited = d_visited;
     p.score_mode = score_mode;
-    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch);
+    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch,
+                                  hnsw_cta_warps(static_cast<uint32_t>(W), nq) >= 16);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, false>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN, false>(p, nq, smem, stream);
