@@ -413,3 +413,24 @@ def test_duplicate_ids_inside_a_batch_are_rejected(vl, oracle_mod):
     with pytest.raises(ValueError):
         h.add_batch(np.array([20, 5], dtype=np.uint64), rows[:2])       # 5 is live
     assert h.len() == 10
+
+
+def test_k_larger_than_256(vl, oracle_mod):
+    """The reference accepts any k (ef = min(k, len), hnsw.rs:437); round 1 stopped at 256."""
+    n, dim = 4000, 32
+    rows = oracle_mod.synth_rows(42, 0, n, dim, clusters=8)
+    q = oracle_mod.synth_rows(43, 0, 3, dim, clusters=8)
+    h = vl.HNSWIndex(dim, vl.SimilarityMetric.Cosine, ef_construction=100)
+    h.add_batch(np.arange(n, dtype=np.uint64), rows)
+    for k in (300, 1000):
+        gi, gs, gc = h.search_batch(q, k, vl.SimilarityMetric.Cosine, 0)
+        assert np.all(gc == k)
+        assert np.all(np.diff(gs, axis=1) <= 0)
+        for j in range(3):
+            assert len(set(map(int, gi[j]))) == k
+        st, truth, _ = oracle_mod.flat_search_batch(rows, None, q, k, 0, nthreads=4)
+        assert _recall(gi, gc, truth) >= 0.9, k
+    small = vl.HNSWIndex(dim, vl.SimilarityMetric.Cosine)
+    small.add_batch(np.arange(20, dtype=np.uint64), rows[:20])
+    gi, gs, gc = small.search_batch(q[:1], 500, vl.SimilarityMetric.Cosine, 0)      # k > len → len results
+    assert int(gc[0]) == 20

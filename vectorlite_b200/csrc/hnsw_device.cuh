@@ -13,7 +13,7 @@ constexpr int HN_MAX_EXPAND = 4;                 // pool entries expanded per st
 constexpr int HN_MAX_EXPAND_WIDE = 8;            // 16-warp CTAs (a few queries in flight: latency): twice as many, half the steps
 constexpr int HN_MAX_CAND = HN_MAX_DEG * HN_MAX_EXPAND;
 constexpr int HN_EF_MAX = 2048;   // widest internal beam
-constexpr int HN_K_MAX = 256;
+constexpr int HN_K_MAX = 2048;      // the reference accepts any k (hnsw.rs:437: ef = min(k, len)); k <= widest beam here
 constexpr int HN_BEAM_MULT = 8;     // internal beam = 8 x nominal ef (see hnsw_launch_search)
 
 struct HnswParams {

@@ -388,8 +388,8 @@ static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg
     uint32_t vis_div = p.ef >= 256 ? 4 : 2;
     if (const char* e = std::getenv("VL_HNSW_VIS_DIV")) vis_div = static_cast<uint32_t>(std::max(1, atoi(e)));
     const uint32_t want = p.ef * M0 / vis_div;
-    uint32_t cap = 2048;   // >= HN_K_MAX·8 B: the quantised-score staging aliases the cache
-    while (cap < want && cap < 32768) cap <<= 1;
+    uint32_t cap = 2048;   // the quantised-score staging (k doubles) aliases the cache: >= 4·k tags of 2 bytes
+    while ((cap < want || cap < 4u * k) && cap < 32768) cap <<= 1;
     p.vis_mask = cap - 1;
     // candidates of one step: up to HN_MAX_EXPAND expanded entries x degree; the arrays also stage the results
     // throughput / construction: 1 / 2 / 4 entries per step; wide (latency) CTAs: ef/5 entries, at most 8
