@@ -1114,7 +1114,9 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
             BatchWork bw;
             // pipelined handles chain consecutive batches (PDL): alternate the scratch set the rescore kernel reads
             const uint32_t parity = h->pipelined ? (s.batch_parity++ & 1u) : 0u;
-            int st = slot_reserve_batch(s, m, &bw, parity);
+            int st = VL_OK;
+            if (h->pipelined) st = slot_reserve_batch(s, m, &bw, parity ^ 1u);   // both sets up front: no allocation in the 2nd batch
+            if (!st) st = slot_reserve_batch(s, m, &bw, parity);
             if (st) return st;
             const SearchOut out = out_at(q0);
             uint64_t nl = 0;
