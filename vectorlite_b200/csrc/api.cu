@@ -1049,8 +1049,19 @@ int vl_index_search(vl_index* h, const float* queries, uint32_t nq, uint32_t qdi
                         uint32_t* cnt) -> int {
             DeviceGuard dg(h->device);
             uint64_t visited = 0, launches = 0;
+            // The traversal gathers rows from the bf16 mirror where one applies (AUTO mode, 384-d; cosine: the
+            // pre-normalised mirror, so no 1/‖row‖ is fetched either): half the bytes per evaluated node.  The mirror
+            // is brought up to date lazily, like the flat scans do; the final k are re-scored in f64 from the fp32 rows.
+            const void* mirror = nullptr;
+            const float* sqn = nullptr;
+            static const bool fp32_gather = getenv("VL_HNSW_FP32_GATHER") != nullptr;
+            if (!fp32_gather && h->pitch == 384) {
+                const FlatView v = view_of(h);
+                int stm = single_query_mirror(h, v, h->hnsw_metric, h->mut_stream, &mirror, &sqn);
+                if (stm) return stm;
+            }
             // uploads a changed graph under its exclusive lock, then searches on a stream of its own
-            int st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, q, m, bk, bef, ids, sc, cnt, &visited, &launches);
+            int st = hnsw_search_host(h->hnsw.get(), h->d_rows, h->pitch, q, m, bk, bef, ids, sc, cnt, &visited, &launches, mirror);
             h->stats[ST_HNSW_VISITED] = visited;
             h->stats[ST_LAUNCHES] += launches;
             if (st) return fail(st, "hnsw search failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -49,8 +49,9 @@ int hnsw_import_graph(HnswState* s, const uint64_t* ids, const float* rows, uint
 int hnsw_upload(HnswState* s, cudaStream_t stream);
 // Re-entrant: uploads a changed graph under the exclusive graph lock, then searches under the shared lock on a
 // stream / scratch set of its own (pool of HnswState::MAX_CTX).
+// rows_bf16 (may be null): bf16 mirror of the rows for the traversal's gathers (cosine: pre-normalised rows)
 int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,
                      uint32_t k, uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
-                     uint64_t* visited, uint64_t* launches);
+                     uint64_t* visited, uint64_t* launches, const void* rows_bf16 = nullptr);
 
 }  // namespace vl

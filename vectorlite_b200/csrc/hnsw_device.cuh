@@ -13,15 +13,23 @@ constexpr int HN_MAX_EXPAND = 4;                 // pool entries expanded per st
 constexpr int HN_MAX_EXPAND_WIDE = 8;            // 16-warp CTAs (a few queries in flight: latency): twice as many, half the steps
 constexpr int HN_MAX_CAND = HN_MAX_DEG * HN_MAX_EXPAND;
 constexpr int HN_EF_MAX = 2048;   // widest internal beam
+constexpr int HN_REFINE_MAX = 1024;  // head of the beam refined in fp32 when the traversal gathers bf16 rows
 constexpr int HN_K_MAX = 2048;      // the reference accepts any k (hnsw.rs:437: ef = min(k, len)); k <= widest beam here
 constexpr int HN_BEAM_MULT = 8;     // internal beam = 8 x nominal ef (see hnsw_launch_search)
 
 struct HnswParams {
     HnswDeviceGraph g;
     const float* rows;
+    const void* rows_bf16 = nullptr;      // bf16 mirror of the rows ([n][pitch], cosine: pre-scaled by 1/‖row‖): the
+                                          // traversal gathers 768 B per evaluated node instead of 1.5 KB; the final k
+                                          // are re-scored in f64 from the fp32 rows either way
     const float* queries;
     uint32_t pitch, dim, k, ef, vis_mask, beam_cap, cand_cap;
     uint32_t expand = 1;                  // pool entries expanded per step on the beam level (<= the kernel's MAXE)
+    uint32_t refine = 0;                  // bf16 gathers: beam entries re-evaluated from the fp32 rows before k are taken
+    uint32_t rerank = 0;                  // beam entries re-scored in f64 before the top k are taken (>= k; = k when the
+                                          // traversal's distances are fp32; 4k..64+ when they come from the bf16 mirror,
+                                          // whose rounding (~1e-3 on a cosine) reorders near-ties among the best entries)
     uint32_t score_mode = 0;              // 0: exact flat similarity, 1: the reference's quantised score (hnsw.rs:478,51-75)
     uint64_t* out_ids;
     double* out_scores;
@@ -70,6 +78,14 @@ __device__ __forceinline__ float red8(const float (&a)[8], int lane) {
     return e;
 }
 
+// 4 bf16 elements (one 64-bit load) against 4 fp32 query elements; the same element order as the fp32 layout
+template <int METRIC>
+__device__ __forceinline__ float acc4_bf16(float acc, const uint2& v, const float4& q) {
+    const float x0 = __uint_as_float(v.x << 16), x1 = __uint_as_float(v.x & 0xFFFF0000u);
+    const float x2 = __uint_as_float(v.y << 16), x3 = __uint_as_float(v.y & 0xFFFF0000u);
+    return acc4<METRIC>(acc, make_float4(x0, x1, x2, x3), q);
+}
+
 // distance "lower is closer" from the raw accumulation
 template <int METRIC>
 __device__ __forceinline__ float to_dist(float acc, float invn, float invq) {
@@ -114,11 +130,12 @@ __device__ __forceinline__ void finish_query(const HnswParams& p, uint32_t qi, c
         if (tid == 0) p.out_counts[qi] = static_cast<uint32_t>(size);
         return;
     }
-    // ---- results: first k non-deleted beam entries (hnsw.rs:472-475), exact f64 re-score ------
+    // ---- results: first R >= k non-deleted beam entries (hnsw.rs:472-475), exact f64 re-score, best k of them ------
+    const int R = static_cast<int>(p.rerank > p.k ? p.rerank : p.k);
     if (warp == 0) {
         const int size = size_in;
         int cnt = 0;
-        for (int i0 = 0; i0 < size && cnt < static_cast<int>(p.k); i0 += 32) {
+        for (int i0 = 0; i0 < size && cnt < R; i0 += 32) {
             const int i = i0 + lane;
             uint32_t node = HNSW_NONE;
             bool ok = false;
@@ -128,13 +145,14 @@ __device__ __forceinline__ void finish_query(const HnswParams& p, uint32_t qi, c
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
             const int my = cnt + __popc(m & ((1u << lane) - 1));
-            if (ok && my < static_cast<int>(p.k) && my < HN_K_MAX) s_rid[my] = node;
+            if (ok && my < R && my < HN_K_MAX) s_rid[my] = node;
             cnt += __popc(m);
         }
-        if (lane == 0) s_rcount = min(min(cnt, static_cast<int>(p.k)), HN_K_MAX);
+        if (lane == 0) s_rcount = min(min(cnt, R), HN_K_MAX);
     }
     __syncthreads();
-    const int rc = s_rcount;
+    const int rc = s_rcount;                                  // entries re-scored
+    const int out_n = min(rc, static_cast<int>(p.k));         // entries returned
     for (int t = tid; t < rc; t += THREADS) {
         const uint32_t node = s_rid[t];
         const float* row = p.rows + static_cast<size_t>(node) * p.pitch;
@@ -204,17 +222,18 @@ __device__ __forceinline__ void finish_query(const HnswParams& p, uint32_t qi, c
         } else {
             for (int j = 0; j < rc; ++j) rank += (s_ex[j] > me) || (s_ex[j] == me && s_rid[j] < mn);
         }
+        if (rank >= out_n) continue;
         const size_t o = static_cast<size_t>(qi) * p.k + rank;
         p.out_ids[o] = p.g.ids[mn];
         p.out_scores[o] = p.score_mode == 1 ? s_qs[t] : me;
     }
-    for (int i = rc + tid; i < static_cast<int>(p.k); i += THREADS) {
+    for (int i = out_n + tid; i < static_cast<int>(p.k); i += THREADS) {
         const size_t o = static_cast<size_t>(qi) * p.k + i;
         p.out_ids[o] = ~0ull;
         p.out_scores[o] = 0.0;
     }
     if (tid == 0) {
-        p.out_counts[qi] = static_cast<uint32_t>(rc);
+        p.out_counts[qi] = static_cast<uint32_t>(out_n);
         if (p.visited) atomicAdd(p.visited, n_eval);
     }
 }

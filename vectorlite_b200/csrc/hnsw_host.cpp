@@ -676,7 +676,7 @@ static void release_ctx(HnswState* s, HnswState::SearchCtx* c) {
 
 int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const float* queries, uint32_t nq,
                      uint32_t k, uint32_t ef, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
-                     uint64_t* visited, uint64_t* launches) {
+                     uint64_t* visited, uint64_t* launches, const void* rows_bf16) {
     HnswState::SearchCtx* c = acquire_ctx(s);
     if (!c) return 6;
     struct Rel { HnswState* s; HnswState::SearchCtx* c; ~Rel() { release_ctx(s, c); } } rel{s, c};
@@ -729,7 +729,7 @@ int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const fl
                           nq, cudaMemcpyHostToDevice, stream);
     }
     int st = hnsw_launch_search(g, d_rows, pitch, s->dim, s->metric, c->d_q, nq, k, ef_search, d_ids, d_scores,
-                                d_counts, c->d_visited, stream, s->score_mode, s->beam_mult);
+                                d_counts, c->d_visited, stream, s->score_mode, s->beam_mult, rows_bf16);
     if (st) return st;
     cudaMemcpyAsync(c->h_out, c->d_out, need, cudaMemcpyDeviceToHost, stream);
     cudaMemcpyAsync(c->h_visited, c->d_visited, 8, cudaMemcpyDeviceToHost, stream);

@@ -23,13 +23,15 @@
 // QPS, visited nodes per query (d_visited), recall@10 vs exact flat.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "hnsw_device.cuh"
 
 namespace vl {
 
-template <int METRIC, int NCH, bool BUILD, int WARPS>
+template <int METRIC, int NCH, bool BUILD, int WARPS, bool BF16>
 __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
+    static_assert(!BF16 || (NCH > 0 && !BUILD), "bf16 gathers: register-resident query, search mode only");
     constexpr int THREADS = WARPS * 32;
     // Entries expanded per step.  A step costs two dependent global round trips (adjacency rows, then the
     // neighbours' vectors) whatever the number of entries, so a lone query's latency is steps x ~3 us: the wide
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
     const float invq = METRIC == COSINE ? s_invq : 1.f;
 
     // scores up to 8 nodes ids[0..cnt) → keys out[0..cnt)  (one warp)
-    auto score8 = [&](const uint32_t* ids, int cnt, unsigned long long* out) {
+    auto score8_from = [&](auto bf16_tag, const uint32_t* ids, int cnt, unsigned long long* out) {
+        constexpr bool FROM_BF16 = decltype(bf16_tag)::value;
         float acc[8];
         uint32_t nid[8];
 #pragma unroll
@@ -108,8 +111,20 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
         const int own_r = lane >> 2;
         const bool own = (lane & 3) == 0 && own_r < cnt;
         const uint32_t own_id = own ? ids[own_r] : 0u;
-        const float invn = (METRIC == COSINE && own) ? __ldg(p.g.inv_norm + own_id) : 1.f;
-        if (NCH > 0) {
+        const float invn = (METRIC == COSINE && own && !FROM_BF16) ? __ldg(p.g.inv_norm + own_id) : 1.f;   // mirror: pre-scaled
+        if (FROM_BF16) {
+            const uint2* rows2 = reinterpret_cast<const uint2*>(p.rows_bf16);
+#pragma unroll
+            for (int c = 0; c < (NCH > 0 ? NCH : 1); ++c) {
+                uint2 v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    v[r] = nid[r] != HNSW_NONE ? __ldg(rows2 + static_cast<size_t>(nid[r]) * pitch4 + c * 32 + lane)
+                                               : make_uint2(0u, 0u);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = acc4_bf16<METRIC>(acc[r], v[r], qreg[c]);
+            }
+        } else if (NCH > 0) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 float4 v[8];
@@ -134,6 +149,9 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
         }
         const float s = red8(acc, lane);
         if (own) out[own_r] = beam_key(to_dist<METRIC>(s, invn, invq), own_id);
+    };
+    auto score8 = [&](const uint32_t* ids, int cnt, unsigned long long* out) {   // the traversal's gathers
+        score8_from(std::integral_constant<bool, BF16>{}, ids, cnt, out);
     };
 
     // ---- entry point ---------------------------------------------------------------------
@@ -327,17 +345,44 @@ __global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
             }
     }
 
+    // ---- bf16 gathers: refine the head of the beam in fp32 before the top k are taken ------------------------------
+    // The mirror's rounding (~1e-3 on a cosine) reorders near-ties among the best entries (1M clustered rows, beam 80:
+    // recall 0.933 when the first k by bf16 distance are returned, 0.980 with fp32 gathers).  The first `refine` beam
+    // entries are re-evaluated from the fp32 rows — warp-cooperative, coalesced, 64 rows against the ~1200 the
+    // traversal gathered — and re-ordered; the f64 re-score below still only touches k rows.
+    if (BF16) {
+        const int R = min(s_size, static_cast<int>(p.refine));
+        __syncthreads();
+        for (int i = tid; i < R; i += THREADS) s_cid[i] = static_cast<uint32_t>(s_beam[i] >> 1) & 0x7FFFFFFFu;
+        __syncthreads();
+        for (int g0 = warp * 8; g0 < R; g0 += WARPS * 8)
+            score8_from(std::false_type{}, s_cid + g0, min(8, R - g0), s_ck + g0);
+        __syncthreads();
+        // re-order the head: ranks are a permutation of [0, R) (keys are unique: they embed the node) and nothing reads
+        // s_beam[0, R) any more (nodes sit in s_cid, keys in s_ck), so every key goes straight to its place
+        for (int t = tid; t < R; t += THREADS) {
+            const unsigned long long key = s_ck[t];
+            int r = 0;
+            for (int j = 0; j < R; ++j) r += s_ck[j] < key;
+            s_beam[r] = key;
+        }
+        __syncthreads();
+    }
     finish_query<METRIC, BUILD, THREADS>(p, qi, s_beam, s_size, reinterpret_cast<const float*>(q4), s_ex, s_rid, s_qs, n_eval);
 }
 
 template <int METRIC, bool BUILD, int WARPS>
 static int launch_warps(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
-    if (p.pitch == 384) {
-        auto k = hnsw_search_kernel<METRIC, 3, BUILD, WARPS>;
+    if (p.pitch == 384 && p.rows_bf16 && !BUILD) {
+        auto k = hnsw_search_kernel<METRIC, 3, false, WARPS, true>;
+        if (smem > 40 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        k<<<nq, WARPS * 32, smem, s>>>(p);
+    } else if (p.pitch == 384) {
+        auto k = hnsw_search_kernel<METRIC, 3, BUILD, WARPS, false>;
         if (smem > 40 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         k<<<nq, WARPS * 32, smem, s>>>(p);
     } else {
-        auto k = hnsw_search_kernel<METRIC, 0, BUILD, WARPS>;
+        auto k = hnsw_search_kernel<METRIC, 0, BUILD, WARPS, false>;
         if (smem > 40 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         k<<<nq, WARPS * 32, smem, s>>>(p);
     }
@@ -389,7 +434,7 @@ static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg
     if (const char* e = std::getenv("VL_HNSW_VIS_DIV")) vis_div = static_cast<uint32_t>(std::max(1, atoi(e)));
     const uint32_t want = p.ef * M0 / vis_div;
     uint32_t cap = 2048;   // the quantised-score staging (k doubles) aliases the cache: >= 4·k tags of 2 bytes
-    while ((cap < want || cap < 4u * k) && cap < 32768) cap <<= 1;
+    while ((cap < want || cap < 4u * std::max(k, p.rerank)) && cap < 32768) cap <<= 1;
     p.vis_mask = cap - 1;
     // candidates of one step: up to HN_MAX_EXPAND expanded entries x degree; the arrays also stage the results
     // throughput / construction: 1 / 2 / 4 entries per step; wide (latency) CTAs: ef/5 entries, at most 8
@@ -399,6 +444,8 @@ static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg
     p.expand = expand;
     uint32_t cc = expand * max_deg;
     if (cc < k) cc = k;
+    if (cc < p.rerank) cc = p.rerank;    // the result staging (exact scores, nodes) aliases the candidate arrays
+    if (cc < p.refine) cc = p.refine;    // ... and so does the fp32 refinement of the beam's head
     if (cc < 8) cc = 8;
     p.cand_cap = (cc + 7u) & ~7u;
     return (query_in_smem ? static_cast<size_t>(pitch) * 4 : 0) + static_cast<size_t>(bcap) * 8 +
@@ -436,11 +483,12 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
-                       cudaStream_t stream, uint32_t score_mode, uint32_t beam_mult) {
+                       cudaStream_t stream, uint32_t score_mode, uint32_t beam_mult, const void* rows_bf16) {
     if (k > HN_K_MAX) return 9;
     HnswParams p;
     p.g = g;
     p.rows = d_rows;
+    p.rows_bf16 = rows_bf16;
     p.queries = d_queries;
     p.pitch = pitch;
     p.dim = dim;
@@ -458,6 +506,11 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.out_counts = d_out_counts;
     p.visited = d_visited;
     p.score_mode = score_mode;
+    // bf16 gathers: the best 4k (at least 64) beam entries are refined in fp32 before k are taken (see the kernel)
+    p.rerank = k;
+    p.refine = 0;
+    if (rows_bf16 && pitch == 384)
+        p.refine = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(4ull * k, 64), std::min<uint64_t>(W, HN_REFINE_MAX)));
     const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch,
                                   hnsw_cta_warps(static_cast<uint32_t>(W), nq) >= 16);
     switch (metric) {
