@@ -150,6 +150,26 @@ public:
     }
     SimilarityMetric metric() const { return static_cast<SimilarityMetric>(vl_index_metric(h_)); }
     IndexType index_type() const { return IndexType::HNSW; }
+    // device beam = factor x ef, ef = the reference's min(k, len) (hnsw.rs:437); 1 = equal ef, default 8
+    void set_beam_factor(uint32_t factor) {
+        if (vl_hnsw_set_beam_factor(h_, factor) != VL_OK) throw VectorLiteError(VL_ERR_INVALID, err());
+    }
+    // Graph persistence: what `#[serde(skip)] index_internal` (hnsw.rs:199-200) leaves out.  export_graph() throws
+    // (VL_ERR_UNSUPPORTED) when the graph holds soft-deleted nodes; import_graph() needs an EMPTY index and the rows
+    // in the order they were exported (vl_index_export).
+    std::vector<unsigned char> export_graph() const {
+        uint64_t nb = 0, w = 0;
+        if (vl_hnsw_graph_bytes(h_, &nb) != VL_OK) throw VectorLiteError(VL_ERR_INVALID, err());
+        std::vector<unsigned char> blob(nb);
+        const int st = vl_hnsw_export_graph(h_, blob.data(), nb, &w);
+        if (st != VL_OK) throw VectorLiteError(st, err());
+        blob.resize(w);
+        return blob;
+    }
+    void import_graph(const std::vector<uint64_t>& ids, const std::vector<float>& rows, const std::vector<unsigned char>& blob) {
+        const int st = vl_hnsw_import_graph(h_, ids.data(), rows.data(), ids.size(), blob.data(), blob.size());
+        if (st != VL_OK) throw VectorLiteError(st, err());
+    }
 };
 
 // A flat store row-sharded over several devices of ONE process behind the same trait: shard g holds

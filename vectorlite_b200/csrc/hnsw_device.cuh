@@ -35,6 +35,7 @@ struct HnswParams {
     double* out_scores;
     uint32_t* out_counts;
     unsigned long long* visited;
+    uint32_t* visited_per_query = nullptr;   // when set (results written straight to pinned host memory): no atomics
     // ---- construction mode (hnsw_build.cu): the queries are rows of the arena -------------------------
     const uint32_t* order = nullptr;      // [nq] node whose row is query qi
     int stop_level = 0;                   // beam search on this level; greedy descent above it
@@ -234,7 +235,8 @@ __device__ __forceinline__ void finish_query(const HnswParams& p, uint32_t qi, c
     }
     if (tid == 0) {
         p.out_counts[qi] = static_cast<uint32_t>(out_n);
-        if (p.visited) atomicAdd(p.visited, n_eval);
+        if (p.visited_per_query) p.visited_per_query[qi] = static_cast<uint32_t>(n_eval);
+        else if (p.visited) atomicAdd(p.visited, n_eval);
     }
 }
 

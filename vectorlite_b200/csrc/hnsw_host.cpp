@@ -702,7 +702,10 @@ int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const fl
         c->q_cap = qf;
     }
     const size_t on = static_cast<size_t>(nq) * k;
-    const size_t need = on * 16 + static_cast<size_t>(nq) * 4;
+    const size_t need = on * 16 + static_cast<size_t>(nq) * 8;   // ids | scores | counts | visited (per query)
+    // a few queries: the kernel writes its (tiny) results straight into the pinned host block (UVA zero-copy), which
+    // takes the memset and the two device-to-host copies off the latency path
+    const bool zero_copy = nq <= 16;
     if (need > c->out_cap) {
         cudaFree(c->d_out); cudaFreeHost(c->h_out);
         c->d_out = nullptr; c->h_out = nullptr; c->out_cap = 0;
@@ -710,15 +713,17 @@ int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const fl
         if (cudaMallocHost(&c->h_out, need) != cudaSuccess) return 7;
         c->out_cap = need;
     }
-    cudaMemsetAsync(c->d_visited, 0, 8, stream);
+    if (!zero_copy) cudaMemsetAsync(c->d_visited, 0, 8, stream);
     HnswDeviceGraph g;
     g.adj0 = s->d_adj0; g.upper_off = s->d_upper_off; g.upper = s->d_upper; g.level = s->d_level;
     g.deleted = s->d_deleted; g.ids = s->d_ids; g.inv_norm = s->d_inv_norm;
     g.n = static_cast<uint32_t>(s->level.size()); g.M = s->M; g.M0 = s->M0; g.entry = s->entry;
     g.max_level = s->max_level;
-    uint64_t* d_ids = reinterpret_cast<uint64_t*>(c->d_out);
-    double* d_scores = reinterpret_cast<double*>(c->d_out + on * 8);
-    uint32_t* d_counts = reinterpret_cast<uint32_t*>(c->d_out + on * 16);
+    unsigned char* ob = zero_copy ? c->h_out : c->d_out;
+    uint64_t* d_ids = reinterpret_cast<uint64_t*>(ob);
+    double* d_scores = reinterpret_cast<double*>(ob + on * 8);
+    uint32_t* d_counts = reinterpret_cast<uint32_t*>(ob + on * 16);
+    uint32_t* d_vis_q = zero_copy ? d_counts + nq : nullptr;
     // One launch for the whole batch: splitting it into wave-sized chunks (to overlap the query upload with the
     // search) was measured 25 % SLOWER — every launch pays its own tail of slow queries.
     if (pitch == s->dim) {
@@ -729,11 +734,19 @@ int hnsw_search_host(HnswState* s, const float* d_rows, uint32_t pitch, const fl
                           nq, cudaMemcpyHostToDevice, stream);
     }
     int st = hnsw_launch_search(g, d_rows, pitch, s->dim, s->metric, c->d_q, nq, k, ef_search, d_ids, d_scores,
-                                d_counts, c->d_visited, stream, s->score_mode, s->beam_mult, rows_bf16);
+                                d_counts, c->d_visited, stream, s->score_mode, s->beam_mult, rows_bf16, d_vis_q);
     if (st) return st;
-    cudaMemcpyAsync(c->h_out, c->d_out, need, cudaMemcpyDeviceToHost, stream);
-    cudaMemcpyAsync(c->h_visited, c->d_visited, 8, cudaMemcpyDeviceToHost, stream);
+    if (!zero_copy) {
+        cudaMemcpyAsync(c->h_out, c->d_out, need, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(c->h_visited, c->d_visited, 8, cudaMemcpyDeviceToHost, stream);
+    }
     if (cudaStreamSynchronize(stream) != cudaSuccess) return 6;
+    if (zero_copy) {
+        unsigned long long tot = 0;
+        const uint32_t* vq = reinterpret_cast<const uint32_t*>(c->h_out + on * 16) + nq;
+        for (uint32_t i = 0; i < nq; ++i) tot += vq[i];
+        *c->h_visited = tot;
+    }
     memcpy(out_ids, c->h_out, on * 8);
     memcpy(out_scores, c->h_out + on * 8, on * 8);
     memcpy(out_counts, c->h_out + on * 16, static_cast<size_t>(nq) * 4);

@@ -483,7 +483,8 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
 int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
-                       cudaStream_t stream, uint32_t score_mode, uint32_t beam_mult, const void* rows_bf16) {
+                       cudaStream_t stream, uint32_t score_mode, uint32_t beam_mult, const void* rows_bf16,
+                       uint32_t* visited_per_query) {
     if (k > HN_K_MAX) return 9;
     HnswParams p;
     p.g = g;
@@ -505,6 +506,7 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.out_scores = d_out_scores;
     p.out_counts = d_out_counts;
     p.visited = d_visited;
+    p.visited_per_query = visited_per_query;
     p.score_mode = score_mode;
     // bf16 gathers: the best 4k (at least 64) beam entries are refined in fp32 before k are taken (see the kernel)
     p.rerank = k;

@@ -91,7 +91,7 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
                        const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                        double* d_out_scores, uint32_t* d_out_counts, unsigned long long* d_visited,
                        cudaStream_t stream, uint32_t score_mode = 0, uint32_t beam_mult = 1,
-                       const void* rows_bf16 = nullptr);
+                       const void* rows_bf16 = nullptr, uint32_t* visited_per_query = nullptr);
 
 // hnsw_search.cu, construction mode: node d_order[i]'s row is query i; beam of `ef` on `level`
 int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t pitch, uint32_t dim, int metric,
