@@ -443,6 +443,9 @@ def main():
     ap.add_argument("--config5-rows", type=int, default=100_000_000,
                     help="BASELINE config 5 leg: total rows of the sharded B=1024, k=100 batch search (0 = skip); at "
                          "N = 1 one shard of the 8-GPU configuration (rows/8) is measured")
+    ap.add_argument("--config4-rows", type=int, default=1_000_000,
+                    help="BASELINE config 4 leg: HNSW memory-optimized / high-accuracy profiles, one replica per GPU, "
+                         "4096 queries per replica (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -891,6 +894,48 @@ def main():
             i5.local.close()
         except Exception as e:  # noqa: BLE001
             e2e_extra["config5"] = {"error": repr(e)}
+
+    # ---- BASELINE config 4: HNSW profiles 8/16 and 32/64, ONE REPLICA PER GPU, queries split across the replicas ----
+    if args.config4_rows > 0:
+        try:
+            n4, B4 = args.config4_rows, 4096
+            cos = vl.SimilarityMetric.Cosine
+            flat4 = vl.FlatIndex(DIM, device=local_rank)
+            flat4.fill_synthetic(42, n4, clusters=1024)
+            q4 = device_synth_rows(vl, 43, rank * B4, B4, local_rank, clusters=1024)     # this replica's share of the queries
+            truth4, _, _ = flat4.search_batch(q4, k, cos)                                  # exact (certified) flat
+            ids4, rows4 = flat4.export()
+            flat4.close()
+            c4 = {"rows": n4, "dim": DIM, "data": "synthetic 1024-centre mixture, unit norm", "ef_construction": args.hnsw_efc,
+                  "k": k, "queries_per_replica": B4, "replicas": world, "ef": "k (the reference's setting), device beam = 8 x ef",
+                  "parallelism": "replicas only: one full graph per GPU, queries split, no collective"}
+            for prof, (M4, M04) in (("memory-optimized", (8, 16)), ("high-accuracy", (32, 64))):
+                h4 = vl.HNSWIndex(DIM, cos, M=M4, M0=M04, ef_construction=args.hnsw_efc, device=local_rank)
+                t0 = time.perf_counter()
+                h4.add_batch(ids4, rows4)
+                h4.build()
+                build_s = time.perf_counter() - t0
+                h4.search_batch(q4, k, cos, 0)
+                host_barrier()
+                t0 = time.perf_counter()
+                reps4 = 3
+                for _ in range(reps4):
+                    gi4, _, gc4 = h4.search_batch(q4, k, cos, 0)
+                dt4 = (time.perf_counter() - t0) / reps4
+                hit4 = sum(len(set(map(int, gi4[i, :gc4[i]])) & set(map(int, truth4[i]))) for i in range(B4)) / (B4 * k)
+                vis4 = h4.stats()["hnsw_visited"] / B4
+                h4.close()
+                if world > 1:
+                    t = torch.tensor([dt4, -hit4, build_s], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    dt4, hit4, build_s = float(t[0]), -float(t[1]), float(t[2])
+                c4[prof] = {"M": M4, "M0": M04, "qps_e2e_all_replicas": world * B4 / dt4, "qps_e2e_per_replica": B4 / dt4,
+                            "recall_at_10_min_over_replicas": hit4, "visited_per_query": vis4,
+                            "build_seconds_max_over_replicas": build_s}
+            del rows4
+            e2e_extra["config4_hnsw_replicas"] = c4
+        except Exception as e:  # noqa: BLE001
+            e2e_extra["config4_hnsw_replicas"] = {"error": repr(e)}
 
     # ---- CPU baseline + oracle comparison of the timed path ------------------------------------------------
     cpu = None
