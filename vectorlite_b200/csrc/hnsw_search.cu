@@ -30,7 +30,7 @@
 namespace vl {
 
 template <int METRIC, int NCH, bool BUILD, int WARPS, bool BF16>
-__global__ void __launch_bounds__(WARPS * 32) hnsw_search_kernel(HnswParams p) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_kernel(HnswParams p) {
     static_assert(!BF16 || (NCH > 0 && !BUILD), "bf16 gathers: register-resident query, search mode only");
     constexpr int THREADS = WARPS * 32;
     // Entries expanded per step.  A step costs two dependent global round trips (adjacency rows, then the
