@@ -671,6 +671,13 @@ def main():
             # a lone native caller: the C-ABI latency without the Python wrapper's allocations
             e2e_single_python = e2e_single
             e2e_single = native_callers(idx.local, queries, k, metric, 0, 1, 4 * QUERIES_PER_STEP)[0]
+            # more requests in flight than host cores (a server's worker pool): the combined batches grow with the
+            # number of waiting callers, the device-side cost of a batch barely does (0.16 ms for 2 ... 128 queries)
+            more = {}
+            for nthreads in (64, 128):
+                r_ = native_callers(idx.local, queries, k, metric, 0, nthreads, 2 * conc_total)
+                more[str(nthreads)] = r_[0]
+            e2e_extra["value_by_callers"] = {"16": e2e_qps, **more, "host_cores": cpu_threads()}
     else:
         e2e_extra["exchange_one_caller_per_rank"] = {
             "value": e2e_single, "unit": "queries/s x 1M-row shards",
