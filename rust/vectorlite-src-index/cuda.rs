@@ -40,6 +40,33 @@ impl CudaIndex {
         Ok(Self { h, dim, meta: HashMap::new(), metric: Some(metric) })
     }
     pub fn metric(&self) -> Option<SimilarityMetric> { self.metric }
+    /// Device beam = factor x ef, ef = min(k, len) as at hnsw.rs:437; 1 = equal ef, default 8.
+    pub fn set_beam_factor(&mut self, factor: u32) -> Result<(), String> {
+        if unsafe { sys::vl_hnsw_set_beam_factor(self.h, factor) } != sys::VL_OK { return Err(last_error()); }
+        Ok(())
+    }
+    /// What `#[serde(skip)] index_internal` (hnsw.rs:199-200) leaves out of the .vlc: levels + adjacency of the
+    /// graph.  `Collection::save_to_file` writes it to `<file>.graph` next to the JSON; the custom `Deserialize`
+    /// (hnsw.rs:272-360) calls `restore_graph` instead of re-inserting every vector when that file is present and
+    /// valid.  Err when the graph holds soft-deleted nodes (rebuild on load then, as the reference does).
+    pub fn graph_blob(&self) -> Result<Vec<u8>, String> {
+        let mut n = 0u64;
+        if unsafe { sys::vl_hnsw_graph_bytes(self.h, &mut n) } != sys::VL_OK { return Err(last_error()); }
+        let (mut buf, mut written) = (vec![0u8; n as usize], 0u64);
+        if unsafe { sys::vl_hnsw_export_graph(self.h, buf.as_mut_ptr().cast(), n, &mut written) } != sys::VL_OK {
+            return Err(last_error());
+        }
+        buf.truncate(written as usize);
+        Ok(buf)
+    }
+    /// `ids` / `rows` in the insertion order the blob was exported with (vl_index_export); the index must be empty.
+    pub fn restore_graph(&mut self, ids: &[u64], rows: &[f32], blob: &[u8]) -> Result<(), String> {
+        match unsafe { sys::vl_hnsw_import_graph(self.h, ids.as_ptr(), rows.as_ptr(), ids.len() as u64,
+                                                 blob.as_ptr().cast(), blob.len() as u64) } {
+            sys::VL_OK => Ok(()),
+            _ => Err(last_error()),
+        }
+    }
     pub fn max_id(&self) -> Option<u64> {                       // flat.rs:76-78, hnsw.rs:267-269
         let mut id = 0u64;
         (unsafe { sys::vl_index_max_id(self.h, &mut id) } == sys::VL_OK).then_some(id)
