@@ -75,6 +75,34 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
+// ---- CTA pair (cta_group::2): one MMA over two SMs, M = 256 (128 queries per CTA), the B tile split across the pair ----
+// Same offset in the pair's LEADER (even) CTA: inside a CTA pair the shared::cluster window of the two CTAs differs
+// in address bit 24 only, so clearing it names the leader's copy from either CTA (what CUTLASS's 2-SM TMA atoms do).
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local_smem_addr) { return local_smem_addr & 0xFEFFFFFFu; }
+// TMA load into THIS CTA's shared memory whose bytes are credited to a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster_addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+// Arrive on a barrier of the pair's other CTA.  Default (cta-scope) semantics on purpose: `.release.cluster` compiles
+// to MEMBAR.ALL.GPU + ERRBAR in front of the arrive (30 % of the pair kernel's stall samples, profiles/
+// r02_batch_tc_pair_full.txt); what the arrive orders here are tcgen05.ld reads of tensor memory, which
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+constexpr int NSTAGE_PAIR = 6;                           // half tiles: twice the ring depth in the same 96 KB
+constexpr uint32_t B_STAGE_BYTES_PAIR = (BN / 2) * BK * 2;   // 16 KB
+constexpr uint32_t IDESC_PAIR_BITS = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | (((2 * BM) >> 4) << 24);
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -84,6 +112,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
+}
+// max(a, b, c), NaN if any operand is NaN (one FMNMX3.NAN)
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // v[i] for a runtime i without spilling v to local memory (31 selects; survivors are rare)
@@ -131,19 +165,28 @@ struct Params {
     uint32_t pdl_first;     // first kernel of the batch's PDL chain: EVERY warp waits for the query conversion
 };
 
-template <int METRIC, int CS>
+// PAIR (CS == 2 only): the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 per K step — M = 256 (each CTA's
+// 128 queries), N = 256 rows of which each CTA stages HALF (16 KB per K-chunk instead of 32 KB: half the L2 → SM
+// traffic, half the shared-memory writes, the B operand read once per pair, a 6-deep ring in the same 96 KB).  Only
+// the leader CTA (rank 0) issues MMAs; both issue TMA, whose bytes are credited to the LEADER's barriers; commits
+// arrive on the barriers of both CTAs; each CTA's epilogue reads its own TMEM half and releases the accumulator
+// buffer on the leader's barrier.
+template <int METRIC, int CS, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q, Params p) {
+    static_assert(!PAIR || CS == 2, "a CTA pair is a cluster of two");
+    constexpr int NST = PAIR ? NSTAGE_PAIR : NSTAGE;
+    constexpr uint32_t BSTAGE = PAIR ? B_STAGE_BYTES_PAIR : B_STAGE_BYTES;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* s_a = base;
     unsigned char* s_b = base + SMEM_A;
     // (SMEM_XN bytes after the B ring are reserved: the L2 epilogue keeps its squared norms in registers)
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SMEM_A + SMEM_B + SMEM_XN);
-    // bars: [0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, then a_full, tmem_full[2], tmem_empty[2]
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE), bar_a = smem_u32(bars + 2 * NSTAGE);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE + 1), bar_tempty = smem_u32(bars + 2 * NSTAGE + 3);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+    // bars: [0..NST) full, [NST..2NST) empty, then a_full, tmem_full[2], tmem_empty[2]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NST), bar_a = smem_u32(bars + 2 * NST);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * NST + 1), bar_tempty = smem_u32(bars + 2 * NST + 3);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
     unsigned long long* s_pq = reinterpret_cast<unsigned long long*>(base + SMEM_A + SMEM_B + SMEM_XN + SMEM_BAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,20 +198,25 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t qblock = qg * CS + rank;   // may be >= qblocks (padding CTA of the last group): scores ignored
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) {
+        for (int i = 0; i < NST; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, CS);   // one tcgen05.commit arrival from every CTA of the cluster
+            mbar_init(bar_empty + 8 * i, PAIR ? 1 : CS);   // one tcgen05.commit arrival from every MMA-issuing CTA
         }
         mbar_init(bar_a, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, EPI_WARPS);   // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * i, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp (pair: of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {   // the same warp of both CTAs allocates the pair's tensor memory
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     if (CS > 1) cluster_sync_all(); else __syncthreads();
@@ -188,7 +236,25 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && active) {
+        if (PAIR) {
+            if (lane == 0 && active) {
+                // every byte of the pair (both A blocks, both halves of every B stage) is credited to the LEADER's barriers
+                const uint32_t lead_a = leader_addr(bar_a);
+                if (rank == 0) mbar_expect_tx(bar_a, 2 * p.kch * A_CHUNK_BYTES);
+                for (uint32_t kc = 0; kc < p.kch; ++kc)
+                    tma_load_2d_pair(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, lead_a, kc * BK, qblock * BM);
+                uint32_t stage = 0, phase = 0;
+                for (uint32_t t = t0; t < p.tiles; t += tstride) {
+                    const int row = static_cast<int>(p.row_lo + t * BN + rank * (BN / 2));   // this CTA's half of the tile
+                    for (uint32_t kc = 0; kc < p.kch; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // own barrier: the commit arrives on both CTAs
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * BSTAGE);
+                        tma_load_2d_pair(smem_u32(s_b + stage * BSTAGE), &map_x, leader_addr(bar_full + 8 * stage), kc * BK, row);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (lane == 0 && active) {
             mbar_expect_tx(bar_a, p.kch * A_CHUNK_BYTES);
             for (uint32_t kc = 0; kc < p.kch; ++kc)
                 tma_load_2d(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, bar_a, kc * BK, qblock * BM);
@@ -215,7 +281,37 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // The whole warp runs the loop (warp-uniform control flow and descriptors stay in uniform
         // registers); one elected lane issues the MMAs and their commits.  Descriptors are advanced
         // by adding to the encoded 16-byte address field instead of being rebuilt per instruction.
-        if (active) {
+        if (PAIR) {
+            if (active && rank == 0) {   // the leader issues for the pair; its barriers see both CTAs' bytes / epilogues
+                mbar_wait(bar_a, 0);
+                tc_fence_after();
+                const uint64_t adesc0 = make_desc(smem_u32(s_a)), bdesc0 = make_desc(smem_u32(s_b));
+                uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
+                for (uint32_t t = t0; t < p.tiles; t += tstride) {
+                    mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + buf * TMEM_BUF_COLS;
+                    for (uint32_t kc = 0; kc < p.kch; ++kc) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t ad = adesc0 + static_cast<uint64_t>(kc * (A_CHUNK_BYTES >> 4));
+                            const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (BSTAGE >> 4));
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j)
+                                umma_bf16_pair(d, ad + 2 * j, bd + 2 * j, IDESC_PAIR_BITS, (kc | j) != 0 ? 1u : 0u);
+                            umma_commit_pair(bar_empty + 8 * stage);    // frees the stage in both CTAs
+                        }
+                        __syncwarp();
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                    if (elect_one()) umma_commit_pair(bar_tfull + 8 * buf);   // both CTAs' epilogues
+                    __syncwarp();
+                    buf ^= 1;
+                    if (buf == 0) tphase ^= 1;
+                }
+            }
+        } else if (active) {
             mbar_wait(bar_a, 0);
             tc_fence_after();
             const uint64_t adesc0 = make_desc(smem_u32(s_a)), bdesc0 = make_desc(smem_u32(s_b));
@@ -356,6 +452,18 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         const float xm = __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, __float_as_uint(xn_lane)));
                         thr = 0.5f * (tau + xm) - (4e-7f * (fabsf(tau) + xm) + 1e-30f);
                     }
+                    // Fast reject: the chunk's NaN-propagating maximum (16 three-input FMNMX3 for 32 scores, two
+                    // independent chains) against the threshold.  Only when some lane of the warp has a candidate (or a
+                    // NaN) does the warp build the per-score masks — in the main stage that is about one chunk in four.
+                    float mxa = fmax3_nan(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+                    float mxb = fmax3_nan(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+#pragma unroll
+                    for (int i = 6; i < 30; i += 4) {
+                        mxa = fmax3_nan(mxa, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                        mxb = fmax3_nan(mxb, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                    }
+                    mxa = fmax3_nan(mxa, __uint_as_float(v[30]), __uint_as_float(v[31]));
+                    if (!__any_sync(0xFFFFFFFFu, !(fmax3_nan(mxa, mxb, mxb) < thr))) return;
                     uint32_t m4[4] = {0u, 0u, 0u, 0u};   // independent partial masks: no 32-long dependent chain
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
@@ -397,7 +505,10 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(leader_addr(bar_tempty + 8 * buf));   // the leader's barrier counts both CTAs
+                    else mbar_arrive(bar_tempty + 8 * buf);
+                }
                 buf ^= 1;
                 if (buf == 0) tphase ^= 1;
             }
@@ -410,7 +521,8 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (CS > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -526,6 +638,17 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t K
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// CTA pairs (tcgen05 cta_group::2) are the default whenever the batch has an even number of 128-query blocks
+// (an odd count would leave one CTA of a pair scanning for nobody); VL_TC_PAIR=0 turns them off, VL_TC_PAIR=1 forces
+// them, VL_TC_CLUSTER=2|4 selects the multicast clusters of independent CTAs instead.
+static int tc_pair_mode() {   // -1 = by batch shape, 0 = never, 1 = always
+    static const int mode = [] {
+        const char* e = std::getenv("VL_TC_PAIR");
+        return !e ? -1 : (e[0] == '1' ? 1 : 0);
+    }();
+    return mode;
+}
+
 int tc_cluster_size() {
     static int cs = -1;
     if (cs < 0) {
@@ -534,6 +657,12 @@ int tc_cluster_size() {
         if (cs != 1 && cs != 2 && cs != 4) cs = 1;
     }
     return cs;
+}
+
+static bool tc_use_pair(uint32_t qblocks) {
+    const int mode = tc_pair_mode();
+    if (mode >= 0) return mode == 1;
+    return tc_cluster_size() == 1 && qblocks % 2 == 0;
 }
 
 void tc_state_free(TcState* t) {
@@ -592,9 +721,9 @@ cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int me
     return cudaGetLastError();
 }
 
-template <int METRIC, int CS>
+template <int METRIC, int CS, bool PAIR = false>
 static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mq, const tc::Params& p, int grid, cudaStream_t s) {
-    auto kern = tc::batch_scan_tc_kernel<METRIC, CS>;
+    auto kern = tc::batch_scan_tc_kernel<METRIC, CS, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -620,7 +749,8 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     if (!t || !t->usable) return cudaErrorNotSupported;
     const uint32_t KP = t->KP;
     const uint32_t nq_pad = (nq + tc::BM - 1) / tc::BM * tc::BM;
-    const int CS = tc_cluster_size();
+    const bool pair = tc_use_pair(nq_pad / tc::BM);
+    const int CS = pair ? 2 : tc_cluster_size();
     if (first) {  // first scan of a batch: convert the queries, (re)encode the maps
         {
             cudaLaunchConfig_t cfg = {};
@@ -671,7 +801,9 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     const int grid = static_cast<int>(per_group * qgroups * CS);
 #define VL_TC_LAUNCH(M)                                                          \
     (CS == 1 ? launch_tc<M, 1>(t->map_x, t->map_q, p, grid, s)                  \
-             : CS == 2 ? launch_tc<M, 2>(t->map_x, t->map_q, p, grid, s) : launch_tc<M, 4>(t->map_x, t->map_q, p, grid, s))
+             : CS == 2 ? (pair ? launch_tc<M, 2, true>(t->map_x, t->map_q, p, grid, s)  \
+                                    : launch_tc<M, 2>(t->map_x, t->map_q, p, grid, s))       \
+                       : launch_tc<M, 4>(t->map_x, t->map_q, p, grid, s))
     switch (metric) {
         case COSINE: return VL_TC_LAUNCH(COSINE);
         case EUCLIDEAN: return VL_TC_LAUNCH(EUCLIDEAN);
