@@ -805,6 +805,7 @@ def main():
                 rec.update({"lane_ops_per_s": 2.0 * B * n_shard * DIM / (t_ms * 1e-3)})
             extras[f"flat_b1024_{name}"] = rec
         extras["tc_cluster"] = int(os.environ.get("VL_TC_CLUSTER", "1"))
+        extras["tc_cta_pairs"] = os.environ.get("VL_TC_PAIR", "default: cta_group::2 for even 128-query block counts")
         bt = extras.get(f"flat_b1024_{args.metric}")
         if bt and "tflops_whole_pipeline" in bt:
             roofline["batched_tensor"] = {"bound": "tensor", "workload": f"B=1024 x {n_shard} rows, {args.metric}, k={k}: whole pipeline "

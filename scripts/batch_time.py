@@ -1,5 +1,5 @@
 """Times the batched (B=1024) flat pipeline on a 1M x 384 synthetic index: CUDA events over REPS batches.
-Env: N (rows), METRICS (comma list of metric ids), K, REPS, VL_TC_CLUSTER (cluster size of the tensor-core kernel)."""
+Env: N (rows), METRICS (comma list of metric ids), K, REPS, VL_TC_CLUSTER (multicast cluster size of the tensor-core kernel), VL_TC_PAIR (0 = no CTA pairs)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,4 +26,4 @@ for m in [vl.SimilarityMetric(int(x)) for x in os.environ.get("METRICS", "0").sp
     ms = e0.elapsed_time(e1) / reps
     out[m.name] = {"ms_per_batch": round(ms, 4), "qps": round(B / ms * 1e3), "tflops": round(2.0 * B * n * 384 / ms / 1e9, 1),
                    "cert_failed": failed}
-print(json.dumps({"n": n, "B": B, "k": k, "cluster": os.environ.get("VL_TC_CLUSTER", "1"), **out}))
+print(json.dumps({"n": n, "B": B, "k": k, "cluster": os.environ.get("VL_TC_CLUSTER", "1"), "pair": os.environ.get("VL_TC_PAIR", "default"), **out}))

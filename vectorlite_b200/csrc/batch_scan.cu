@@ -488,6 +488,9 @@ cudaError_t batch_scan_cuda_cores(const FlatView& v, const float* d_q, uint32_t 
     }
 }
 
+// probability that one row beats the Kp-th largest of G group maxima (groups of 32 rows)
+static double p_row_of(int Kp, uint32_t G) { return 1.0 - pow(1.0 - static_cast<double>(Kp) / G, 1.0 / 32.0); }
+
 cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_t nq, uint32_t k, int metric,
                               int Kp, const BatchWork& w, const SearchOut& out, const BatchTensor* tc,
                               uint64_t* launches, cudaStream_t s, int kp_base) {
@@ -524,6 +527,7 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
     static const bool no_estimate = getenv("VL_BATCH_NO_ESTIMATE") != nullptr;
     const uint32_t G = Kp <= 256 ? 512u : GMAX_STRIDE;
     const uint32_t S0 = G * 32u;
+    double balanced = 0.0;   // > 0: the common ratio of the balanced schedule (estimation path only)
     const bool estimate = use_tc && w.gmax && !no_estimate && v.n >= 4ull * S0 && static_cast<uint32_t>(Kp) * 2u <= G;
     if (estimate) {
         if ((e = batch_scan_tensor(v, *tc, d_queries, nq, metric, 0, S0, w, s, true, SCAN_GROUPMAX)) != cudaSuccess) return e;
@@ -539,8 +543,15 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
         if ((e = cudaLaunchKernelEx(&cfg, batch_tau_kernel, static_cast<const float*>(w.gmax), G, Kp, w.tau, nq)) != cudaSuccess)
             return e;
         nl += 2;
-        const double p_row = 1.0 - pow(1.0 - static_cast<double>(Kp) / G, 1.0 / 32.0);
-        hi64 = static_cast<uint64_t>(static_cast<double>(Kp) / p_row) * ratio;
+        // VL_BATCH_STAGES=m (experiments): balanced schedule — the filtered stages end at S_eq·r, S_eq·r², … n with the
+        // same ratio r = (n / S_eq)^(1/m).  Measured at 1M × 384, B = 1024 (profiles/r02_batch_schedule_sweeps.txt):
+        // m = 2 (r = 8) 0.633 ms, m = 3 (r = 4) 0.618 ms, the default geometric ratio 16 below 0.622 ms — back to back
+        // the batch time follows the energy of the MMA stage, not the stage structure.
+        const double s_eq = static_cast<double>(Kp) / p_row_of(Kp, G);
+        static const int forced_stages = [] { const char* e = getenv("VL_BATCH_STAGES"); return e ? atoi(e) : 0; }();
+        if (forced_stages > 0 && static_cast<double>(v.n) > s_eq)
+            balanced = std::max(2.0, pow(static_cast<double>(v.n) / s_eq, 1.0 / forced_stages) * 1.0001);
+        hi64 = static_cast<uint64_t>(s_eq * (balanced > 0.0 ? balanced : static_cast<double>(ratio)));
     }
     bool first = !estimate;
     while (lo < v.n) {
@@ -568,7 +579,8 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
         }
         nl += 2;
         lo = hi;
-        hi64 = static_cast<uint64_t>(hi) * ratio;
+        hi64 = balanced > 0.0 ? static_cast<uint64_t>(static_cast<double>(hi) * balanced) : static_cast<uint64_t>(hi) * ratio;
+        if (balanced > 0.0 && hi64 < v.n && v.n - hi64 < 4096u) hi64 = v.n;   // no sliver stage from rounding
     }
     // rescore + certify
     const size_t budget = 180 * 1024;

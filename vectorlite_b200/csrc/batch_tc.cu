@@ -1,15 +1,23 @@
 // batch_tc.cu — batched cosine / L2 / dot scan on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
 //
-// S = Q · Xᵀ as a tile contraction: the query block is the A operand (M = 128 queries, K-major,
+// S = Q · Xᵀ as a tile contraction: the query block is the A operand (M = 128 queries per CTA, K-major,
 // resident in shared memory for the CTA's whole life), database row tiles are the B operand
-// (N = 256 rows per tile, K-major, streamed by TMA through a 3-stage ring, optionally multicast
-// across a cluster of CTAs that work on different query blocks of the same row tiles), and the
-// 128×256 fp32 accumulator lives in TMEM, double buffered (2 × 256 of the 512 columns) so the
-// epilogue of tile t overlaps the MMAs of tile t+1.
+// (N = 256 rows per tile, K-major, streamed by TMA through a ring), and the 128×256 fp32 accumulator
+// lives in TMEM, double buffered (2 × 256 of the 512 columns) so the epilogue of tile t overlaps the
+// MMAs of tile t+1.
 //
-// TMEM lane == query: every epilogue thread owns one query, keeps that query's running threshold
-// in a register, reads its 256 scores with tcgen05.ld (32x32b.x32) and pushes the rare survivors
-// (score >= τ) to the per-query candidate buffer — the B×N score matrix never reaches memory.
+// Default: CTA PAIRS (tcgen05 cta_group::2).  The two CTAs of a cluster hold two different query blocks
+// and issue ONE M = 256 MMA per K step; each CTA stages only HALF of every row tile (16 KB per K-chunk,
+// 6-deep ring), so the bytes pulled from L2 per flop halve — the single-CTA form needs 64 B/clk/SM at
+// full tensor rate, more than the ~6300 B/clk the L2 slices deliver to 148 SMs (it ran at 76 % tensor-pipe
+// activity, the pair at 90 %; profiles/r02_batch_tc_pair_full.txt).  Batches with an odd number of
+// 128-query blocks run single CTAs (optionally multicast clusters, VL_TC_CLUSTER).
+//
+// TMEM lane == query: every epilogue thread owns one query, keeps that query's running threshold in a
+// register, reads its scores with tcgen05.ld (32x32b.x32), rejects a 32-score chunk with its
+// NaN-propagating maximum (16 FMNMX3) and pushes the rare survivors (score >= τ) to the per-query
+// candidate buffer — the B×N score matrix never reaches memory.  16 epilogue warps (four per TMEM lane
+// quarter, 64 columns each) keep the survivor-heavy first filtered stage off the MMA's critical path.
 // Inputs are a bf16 mirror of the arena (rows pre-scaled by 1/‖row‖ for cosine); the selected
 // candidates are re-scored in f64 from the fp32 arena by the shared rescore/certify kernel, whose
 // certificate uses the bf16 error bound (FinalizeParams::eps_scale / tc_abs).
@@ -25,7 +33,12 @@ namespace vl {
 
 namespace tc {
 constexpr int BM = 128, BN = 256, BK = 64, NSTAGE = 3, KCH_MAX = 6;
-constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, half of the tile's columns each
+#ifndef VL_TC_EPI_WARPS
+#define VL_TC_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = VL_TC_EPI_WARPS;   // EPI_WARPS / 4 warps per TMEM lane quarter, an equal share of the tile's columns each
+constexpr int CW = BN / (EPI_WARPS / 4);     // columns of a tile owned by one epilogue warp (64 with 16 warps)
+static_assert(EPI_WARPS % 4 == 0 && CW % 32 == 0, "whole 32-column chunks per warp");
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 64 + EPI_THREADS;    // warp 0 = TMA producer, warp 1 = MMA issuer
 constexpr int TMEM_BUF_COLS = 256;   // accumulator buffers sit 256 TMEM columns apart (2 × 256 = all 512)
@@ -33,7 +46,7 @@ constexpr uint32_t A_CHUNK_BYTES = BM * BK * 2;   // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr uint32_t SMEM_A = KCH_MAX * A_CHUNK_BYTES;          // 96 KB
 constexpr uint32_t SMEM_B = NSTAGE * B_STAGE_BYTES;           // 96 KB
-constexpr uint32_t SMEM_XN = 2 * BN * 4;                      // 2 KB
+constexpr uint32_t SMEM_XN = 0;                               // (the L2 epilogue keeps its squared norms in registers)
 constexpr uint32_t SMEM_BAR = 256;
 constexpr int QCAP = 8;                                       // survivor queue entries per epilogue thread
 constexpr uint32_t SMEM_PQ = QCAP * EPI_THREADS * 8;          // 16 KB, interleaved [QCAP][EPI_THREADS]
@@ -181,7 +194,6 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* s_a = base;
     unsigned char* s_b = base + SMEM_A;
-    // (SMEM_XN bytes after the B ring are reserved: the L2 epilogue keeps its squared norms in registers)
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SMEM_A + SMEM_B + SMEM_XN);
     // bars: [0..NST) full, [NST..2NST) empty, then a_full, tmem_full[2], tmem_empty[2]
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NST), bar_a = smem_u32(bars + 2 * NST);
@@ -345,7 +357,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // ================= epilogue: TMEM lane == query =================
         const int quarter = warp & 3;                       // TMEM lanes [32q, 32q+32) belong to this warp
         const int etid = (warp - 2) * 32 + lane;            // 0..255 among the epilogue threads
-        const int cbase = ((warp - 2) >> 2) * (BN / 2);     // this warp's half of the tile's columns
+        const int cbase = ((warp - 2) >> 2) * CW;           // this warp's share of the tile's columns
         const uint32_t q = qblock * BM + quarter * 32 + lane;
         const bool qvalid = qblock < p.qblocks && q < p.nq;
         if (!p.pdl_first) {
@@ -375,12 +387,13 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         };
         if (active) {
             uint32_t buf = 0, tphase = 0;
-            // L2: every warp keeps the ‖x‖² of its 128 columns in registers (lane l holds columns cbase + 32j + l,
-            // j = 0..3), loaded one tile ahead — no shared-memory staging and no barrier between epilogue warps
-            float xr[4] = {0.f, 0.f, 0.f, 0.f}, xp[4] = {0.f, 0.f, 0.f, 0.f};
-            auto load_xn = [&](uint32_t tile, float (&dst)[4]) {
+            // L2: every warp keeps the ‖x‖² of its CW columns in registers (lane l holds columns cbase + 32j + l),
+            // loaded one tile ahead — no shared-memory staging and no barrier between epilogue warps
+            constexpr int NXR = CW / 32;
+            float xr[NXR] = {}, xp[NXR] = {};
+            auto load_xn = [&](uint32_t tile, float (&dst)[NXR]) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NXR; ++j) {
                     const uint32_t r = p.row_lo + tile * BN + cbase + 32 * j + lane;
                     dst[j] = (tile < p.tiles && r < p.row_hi) ? __ldg(p.sq_norm + r) : 0.f;
                 }
@@ -390,7 +403,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const uint32_t row0 = p.row_lo + t * BN;
                 if (METRIC == EUCLIDEAN) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) xr[j] = xp[j];
+                    for (int j = 0; j < NXR; ++j) xr[j] = xp[j];
                     load_xn(t + tstride, xp);
                 }
                 mbar_wait(bar_tfull + 8 * buf, tphase);
@@ -493,15 +506,15 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 uint32_t va[32], vb[32];
                 tmem_ld32(tbase + cbase, va);
                 tmem_ld_wait();
-#pragma unroll 1
-                for (int c0 = cbase; c0 < cbase + BN / 2; c0 += 64) {   // two chunks per iteration, loads double buffered
-                    const bool first = c0 == cbase;
+#pragma unroll
+                for (int j = 0; j < NXR; j += 2) {   // two chunks per iteration, loads double buffered
+                    const int c0 = cbase + 32 * j;
                     tmem_ld32(tbase + c0 + 32, vb);
-                    process(va, c0, first ? xr[0] : xr[2]);
+                    process(va, c0, xr[j]);
                     tmem_ld_wait();
-                    if (c0 + 64 < cbase + BN / 2) tmem_ld32(tbase + c0 + 64, va);
-                    process(vb, c0 + 32, first ? xr[1] : xr[3]);
-                    tmem_ld_wait();
+                    if (j + 2 < NXR) tmem_ld32(tbase + c0 + 64, va);
+                    process(vb, c0 + 32, xr[j + 1]);
+                    if (j + 2 < NXR) tmem_ld_wait();
                 }
                 tc_fence_before();
                 __syncwarp();
