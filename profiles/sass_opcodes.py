@@ -11,7 +11,7 @@ import sys
 so = sys.argv[1] if len(sys.argv) > 1 else "vectorlite_b200/libvectorlite_cuda.so"
 WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMAPF", "SYNCS", "LDGSTS", "LDG.E.128", "LDG.E.64",
          "LDG.E", "STG.E", "ATOMG", "RED.E", "REDUX", "SHFL", "DADD", "DMUL", "DFMA", "FFMA", "FADD", "HMMA", "BAR.SYNC",
-         "ACQBULK", "ERRBAR", "MEMBAR", "CCTL", "ELECT"]
+         "ACQBULK", "ERRBAR", "MEMBAR", "CCTL", "ELECT", "FMNMX3"]
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 demangle = {}
 names = re.findall(r"Function : (\S+)", out)
