@@ -244,7 +244,8 @@ int vl_index_set_pos_base(vl_index* h, uint64_t base);
  * [8] queries whose certificate did not hold after a bf16 scan (mirror / tensor cores) and that were re-run at the
  *     next level (larger over-selection K', then the fp32 arena, then the exact path),
  * [9] queries re-run on the fp32 arena, [10] queries served at the boosted over-selection from the start (the
- *     handle remembers data whose top-k gaps are below the bf16 bound). */
+ *     handle remembers data whose top-k gaps are below the bf16 bound), [11] queries whose batched scan ran on the
+ *     tensor cores (tcgen05 kernel over the bf16 mirror; rows up to 2048 elements wide). */
 int vl_index_stats(const vl_index* h, uint64_t* out, uint32_t n);
 /* Pipelined device searches (flat, vl_index_search_device only).  When enabled, consecutive searches
  * enqueued on one stream overlap through programmatic dependent launch: the scan of search i+1

@@ -468,6 +468,7 @@ def test_tensor_core_batched_path(vl, oracle_mod):
         assert np.array_equal(gs.view(np.uint64), os_.view(np.uint64)), metric
         certified = after["fast_queries"] - before["fast_queries"]
         assert certified >= 0.9 * nq, (metric, certified)
+        assert after["tensor_queries"] - before["tensor_queries"] >= nq, metric
     # k = 100 and a ragged query count (not a multiple of the 128-query MMA tile)
     gi, gs, gc = idx.search_batch(queries[:77], 100, vl.SimilarityMetric.Cosine)
     st, oi, os_ = oracle_mod.flat_search_batch(rows, None, queries[:77], 100, 0, nthreads=8)
@@ -476,6 +477,31 @@ def test_tensor_core_batched_path(vl, oracle_mod):
     idx.set_mode(vl.Mode.Fp32)
     gi2, gs2, _ = idx.search_batch(queries[:77], 100, vl.SimilarityMetric.Cosine)
     assert np.array_equal(gi2, oi) and np.array_equal(gs2.view(np.uint64), os_.view(np.uint64))
+
+
+@pytest.mark.parametrize("dim", [768, 1000, 1536])
+def test_tensor_core_batched_path_wide_rows(vl, oracle_mod, dim):
+    """Rows wider than 384 elements (768 / 1024 / 1536-d embedding models; 1000 exercises the K padding): the query
+    block no longer fits in shared memory beside the row ring, its K-chunks are streamed through the ring with the
+    row chunks (batch_tc.cu, STREAM_A).  Same bar as 384-d: ids and f64 scores bit-identical to the oracle, the batch
+    served by the tcgen05 kernel and certified there.  256 queries run as CTA pairs, 77 as single CTAs."""
+    n, k = 30000, 10
+    rows = oracle_mod.synth_rows(42, 0, n, dim)
+    queries = oracle_mod.synth_rows(43, 0, 256, dim)
+    idx = vl.FlatIndex(dim)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    for metric in (vl.SimilarityMetric.Cosine, vl.SimilarityMetric.DotProduct, vl.SimilarityMetric.Euclidean):
+        for nq in (256, 77):
+            before = idx.stats()
+            gi, gs, gc = idx.search_batch(queries[:nq], k, metric)
+            after = idx.stats()
+            st, oi, os_ = oracle_mod.flat_search_batch(rows, None, queries[:nq], k, int(metric), nthreads=8)
+            assert st == 0 and np.all(gc == k)
+            assert np.array_equal(gi, oi), (metric, nq)
+            assert np.array_equal(gs.view(np.uint64), os_.view(np.uint64)), (metric, nq)
+            assert after["tensor_queries"] - before["tensor_queries"] >= nq, (metric, nq)
+            assert after["fast_queries"] - before["fast_queries"] >= 0.9 * nq, (metric, nq)
+            assert after["exact_queries"] == before["exact_queries"], (metric, nq)
 
 
 def test_bf16_mirror_single_query_scan(vl, oracle_mod):

@@ -314,10 +314,10 @@ class _CudaIndex:
         return ids[:got.value], rows[:got.value]
 
     def stats(self) -> dict:
-        out = np.zeros(11, dtype=np.uint64)
-        self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 11)
+        out = np.zeros(12, dtype=np.uint64)
+        self._L.vl_index_stats(self._h, _ptr(out, C.c_uint64), 12)
         keys = ["launches", "fast_queries", "exact_queries", "h2d_bytes", "d2h_bytes", "hnsw_visited", "bf16_scans",
-                "combined_queries", "bf16_retries", "fp32_retries", "boosted_queries"]
+                "combined_queries", "bf16_retries", "fp32_retries", "boosted_queries", "tensor_queries"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def set_mode(self, mode: Mode) -> None:

@@ -47,7 +47,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 enum { ST_LAUNCHES = 0, ST_FAST = 1, ST_EXACT = 2, ST_H2D = 3, ST_D2H = 4, ST_HNSW_VISITED = 5, ST_BF16_SCANS = 6, ST_COMBINED = 7,
-       ST_BF16_RETRY = 8, ST_FP32_RETRY = 9, ST_BOOSTED = 10, ST_N = 11 };
+       ST_BF16_RETRY = 8, ST_FP32_RETRY = 9, ST_BOOSTED = 10, ST_TENSOR = 11, ST_N = 12 };
 
 namespace {
 
@@ -562,7 +562,7 @@ struct PassCfg {
 
 static bool pass_is_batched(const vl_index* h, uint32_t m, int metric, bool use_bf16, bool exact) {
     const bool tc_ok = use_bf16 && h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
-    return !exact && m >= batch_min_for(tc_ok && h->dim <= 384, use_bf16 && mirror_scans_apply(h));
+    return !exact && m >= batch_min_for(tc_ok && h->dim <= TC_MAX_DIM, use_bf16 && mirror_scans_apply(h));
 }
 
 // one pass over m staged host queries; leaves ids / scores / counts / flags of the m queries in the slot's pinned
@@ -601,6 +601,7 @@ static int run_pass(vl_index* h, Slot& s, const FlatView& v, const float* querie
             bt.usable = h->tc.usable;
             bt.scratch = &h->tc;
             *bf16_used = bt.usable;
+            if (bt.usable) h->stats[ST_TENSOR] += m;
             CU(launch_batch_flat(v, s.d_q, m, k, metric, cfg.Kp, bw, out, &bt, &nl, s.stream, cfg.kp_base));
             CU(cudaStreamSynchronize(s.stream));
         } else {
@@ -722,7 +723,7 @@ static int flat_search_impl(vl_index* h, const float* queries, uint32_t nq, uint
     struct Rel { vl_index* h; Slot* s; ~Rel() { release_slot(h, s); } } rel{h, sp};
 
     const FlatView v = view_of(h);
-    const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
+    const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= TC_MAX_DIM && !getenv("VL_DISABLE_TC");
     const bool batched = h->mode != VL_MODE_EXACT && k <= 256 && nq >= batch_min_for(tensor_path, mirror_scans_apply(h));
     const uint32_t chunk = batched ? BATCH_CHUNK : NQ_CHUNK;
     bool nan = false;
@@ -1117,7 +1118,7 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
         out.peers.q_off = o.peers.q_off + q0;
         return out;
     };
-    const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= 384 && !getenv("VL_DISABLE_TC");
+    const bool tensor_path = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && h->dim <= TC_MAX_DIM && !getenv("VL_DISABLE_TC");
     if (nq >= batch_min_for(tensor_path, mirror_scans_apply(h))) {
         const bool want_tc = h->mode == VL_MODE_AUTO && metric != VL_METRIC_MANHATTAN && !getenv("VL_DISABLE_TC");
         for (uint32_t q0 = 0; q0 < nq; q0 += BATCH_CHUNK) {
@@ -1138,6 +1139,7 @@ static int search_device_impl(vl_index* h, const float* d_queries, uint32_t nq, 
                 bt.scratch = &h->tc;
                 bt.chain_batches = h->pipelined;
                 bt.parity = parity;
+                if (bt.usable) h->stats[ST_TENSOR] += m;
             }
             CU(launch_batch_flat(v, d_queries + static_cast<size_t>(q0) * h->pitch, m, k, metric, Kp, bw, out,
                                  want_tc ? &bt : nullptr, &nl, stream));

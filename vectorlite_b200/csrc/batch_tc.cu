@@ -184,16 +184,27 @@ struct Params {
 // the leader CTA (rank 0) issues MMAs; both issue TMA, whose bytes are credited to the LEADER's barriers; commits
 // arrive on the barriers of both CTAs; each CTA's epilogue reads its own TMEM half and releases the accumulator
 // buffer on the leader's barrier.
-template <int METRIC, int CS, bool PAIR = false>
+//
+// STREAM_A (rows wider than KCH_MAX·64 = 384 elements, e.g. 768 / 1024 / 1536-d embeddings): the query block no longer
+// fits in shared memory next to the row ring, so its K-chunks travel through the ring WITH the row chunks — one stage =
+// the 16 KB query chunk + the row chunk of the same K range, the whole 192 KB as ring (6 stages of 32 KB for a pair,
+// 4 of 48 KB for a single CTA).  The query chunks are re-read from L2 for every row tile: 32 KB per K-chunk per CTA
+// of a pair, the L2 → SM rate of the single-CTA kernel at 384-d.
+template <int METRIC, int CS, bool PAIR = false, bool STREAM_A = false>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_q, Params p) {
     static_assert(!PAIR || CS == 2, "a CTA pair is a cluster of two");
-    constexpr int NST = PAIR ? NSTAGE_PAIR : NSTAGE;
+    static_assert(!STREAM_A || PAIR || CS == 1, "streamed query chunks: single CTAs or CTA pairs only");
     constexpr uint32_t BSTAGE = PAIR ? B_STAGE_BYTES_PAIR : B_STAGE_BYTES;
+    constexpr uint32_t STRIDE = STREAM_A ? A_CHUNK_BYTES + BSTAGE : BSTAGE;      // bytes from one ring stage to the next
+    constexpr uint32_t B_OFF = STREAM_A ? A_CHUNK_BYTES : 0u;                     // row chunk inside a stage
+    constexpr int NST = STREAM_A ? static_cast<int>((SMEM_A + SMEM_B) / STRIDE) : (PAIR ? NSTAGE_PAIR : NSTAGE);
+    constexpr uint32_t STAGE_TX = BSTAGE + (STREAM_A ? A_CHUNK_BYTES : 0u);      // bytes one CTA loads per stage
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned char* s_a = base;
-    unsigned char* s_b = base + SMEM_A;
+    unsigned char* s_a = base;                                  // resident query block (!STREAM_A)
+    unsigned char* s_ring = STREAM_A ? base : base + SMEM_A;    // stage i: [query chunk (STREAM_A)] [row chunk]
+    unsigned char* s_b = s_ring + B_OFF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SMEM_A + SMEM_B + SMEM_XN);
     // bars: [0..NST) full, [NST..2NST) empty, then a_full, tmem_full[2], tmem_empty[2]
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NST), bar_a = smem_u32(bars + 2 * NST);
@@ -251,40 +262,47 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (PAIR) {
             if (lane == 0 && active) {
                 // every byte of the pair (both A blocks, both halves of every B stage) is credited to the LEADER's barriers
-                const uint32_t lead_a = leader_addr(bar_a);
-                if (rank == 0) mbar_expect_tx(bar_a, 2 * p.kch * A_CHUNK_BYTES);
-                for (uint32_t kc = 0; kc < p.kch; ++kc)
-                    tma_load_2d_pair(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, lead_a, kc * BK, qblock * BM);
+                if (!STREAM_A) {
+                    const uint32_t lead_a = leader_addr(bar_a);
+                    if (rank == 0) mbar_expect_tx(bar_a, 2 * p.kch * A_CHUNK_BYTES);
+                    for (uint32_t kc = 0; kc < p.kch; ++kc)
+                        tma_load_2d_pair(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, lead_a, kc * BK, qblock * BM);
+                }
                 uint32_t stage = 0, phase = 0;
                 for (uint32_t t = t0; t < p.tiles; t += tstride) {
                     const int row = static_cast<int>(p.row_lo + t * BN + rank * (BN / 2));   // this CTA's half of the tile
                     for (uint32_t kc = 0; kc < p.kch; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // own barrier: the commit arrives on both CTAs
-                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * BSTAGE);
-                        tma_load_2d_pair(smem_u32(s_b + stage * BSTAGE), &map_x, leader_addr(bar_full + 8 * stage), kc * BK, row);
+                        const uint32_t lead_full = leader_addr(bar_full + 8 * stage);
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * STAGE_TX);
+                        if (STREAM_A) tma_load_2d_pair(smem_u32(s_ring + stage * STRIDE), &map_q, lead_full, kc * BK, qblock * BM);
+                        tma_load_2d_pair(smem_u32(s_b + stage * STRIDE), &map_x, lead_full, kc * BK, row);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         } else if (lane == 0 && active) {
-            mbar_expect_tx(bar_a, p.kch * A_CHUNK_BYTES);
-            for (uint32_t kc = 0; kc < p.kch; ++kc)
-                tma_load_2d(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, bar_a, kc * BK, qblock * BM);
+            if (!STREAM_A) {
+                mbar_expect_tx(bar_a, p.kch * A_CHUNK_BYTES);
+                for (uint32_t kc = 0; kc < p.kch; ++kc)
+                    tma_load_2d(smem_u32(s_a + kc * A_CHUNK_BYTES), &map_q, bar_a, kc * BK, qblock * BM);
+            }
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
                 const int row = static_cast<int>(p.row_lo + t * BN);
                 for (uint32_t kc = 0; kc < p.kch; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, B_STAGE_BYTES);
+                    mbar_expect_tx(bar_full + 8 * stage, STAGE_TX);
+                    if (STREAM_A) tma_load_2d(smem_u32(s_ring + stage * STRIDE), &map_q, bar_full + 8 * stage, kc * BK, qblock * BM);
                     if (CS == 1) {
-                        tma_load_2d(smem_u32(s_b + stage * B_STAGE_BYTES), &map_x, bar_full + 8 * stage, kc * BK, row);
+                        tma_load_2d(smem_u32(s_b + stage * STRIDE), &map_x, bar_full + 8 * stage, kc * BK, row);
                     } else {
                         constexpr uint32_t SLICE = BN / CS;  // rows loaded by this CTA, multicast to all
-                        tma_load_2d_mc(smem_u32(s_b + stage * B_STAGE_BYTES + rank * SLICE * 128), &map_x,
+                        tma_load_2d_mc(smem_u32(s_b + stage * STRIDE + rank * SLICE * 128), &map_x,
                                        bar_full + 8 * stage, kc * BK, row + rank * SLICE,
                                        static_cast<uint16_t>((1u << CS) - 1));
                     }
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -295,9 +313,9 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // by adding to the encoded 16-byte address field instead of being rebuilt per instruction.
         if (PAIR) {
             if (active && rank == 0) {   // the leader issues for the pair; its barriers see both CTAs' bytes / epilogues
-                mbar_wait(bar_a, 0);
+                if (!STREAM_A) mbar_wait(bar_a, 0);
                 tc_fence_after();
-                const uint64_t adesc0 = make_desc(smem_u32(s_a)), bdesc0 = make_desc(smem_u32(s_b));
+                const uint64_t adesc0 = make_desc(smem_u32(STREAM_A ? s_ring : s_a)), bdesc0 = make_desc(smem_u32(s_b));
                 uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
                 for (uint32_t t = t0; t < p.tiles; t += tstride) {
                     mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);
@@ -307,8 +325,8 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t ad = adesc0 + static_cast<uint64_t>(kc * (A_CHUNK_BYTES >> 4));
-                            const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (BSTAGE >> 4));
+                            const uint64_t ad = adesc0 + static_cast<uint64_t>(STREAM_A ? stage * (STRIDE >> 4) : kc * (A_CHUNK_BYTES >> 4));
+                            const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (STRIDE >> 4));
 #pragma unroll
                             for (int j = 0; j < BK / 16; ++j)
                                 umma_bf16_pair(d, ad + 2 * j, bd + 2 * j, IDESC_PAIR_BITS, (kc | j) != 0 ? 1u : 0u);
@@ -324,9 +342,9 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 }
             }
         } else if (active) {
-            mbar_wait(bar_a, 0);
+            if (!STREAM_A) mbar_wait(bar_a, 0);
             tc_fence_after();
-            const uint64_t adesc0 = make_desc(smem_u32(s_a)), bdesc0 = make_desc(smem_u32(s_b));
+            const uint64_t adesc0 = make_desc(smem_u32(STREAM_A ? s_ring : s_a)), bdesc0 = make_desc(smem_u32(s_b));
             uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
             for (uint32_t t = t0; t < p.tiles; t += tstride) {
                 mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);
@@ -336,8 +354,8 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t ad = adesc0 + static_cast<uint64_t>(kc * (A_CHUNK_BYTES >> 4));
-                        const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (B_STAGE_BYTES >> 4));
+                        const uint64_t ad = adesc0 + static_cast<uint64_t>(STREAM_A ? stage * (STRIDE >> 4) : kc * (A_CHUNK_BYTES >> 4));
+                        const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (STRIDE >> 4));
 #pragma unroll
                         for (int j = 0; j < BK / 16; ++j)
                             umma_bf16(d, ad + 2 * j, bd + 2 * j, IDESC, (kc | j) != 0 ? 1u : 0u);
@@ -345,7 +363,7 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         else umma_commit_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << CS) - 1));
                     }
                     __syncwarp();
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
                 if (elect_one()) umma_commit(bar_tfull + 8 * buf);
                 __syncwarp();
@@ -687,7 +705,7 @@ void tc_state_free(TcState* t) {
 
 // bring the bf16 mirror(s) needed by `metric` up to date with the arena (rows [0, n))
 cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int metric, uint32_t nq, cudaStream_t s) {
-    if (v.dim > tc::KCH_MAX * tc::BK || !encode_fn()) { t->usable = false; return cudaSuccess; }
+    if (v.dim > TC_MAX_DIM || !encode_fn()) { t->usable = false; return cudaSuccess; }
     const uint32_t KP = (v.dim + tc::BK - 1) / tc::BK * tc::BK;
     cudaError_t e;
     if (t->cap < arena_cap || t->KP != KP) {  // (re)allocate lazily per mirror below
@@ -734,9 +752,9 @@ cudaError_t tc_prepare(TcState* t, const FlatView& v, uint64_t arena_cap, int me
     return cudaGetLastError();
 }
 
-template <int METRIC, int CS, bool PAIR = false>
+template <int METRIC, int CS, bool PAIR = false, bool STREAM_A = false>
 static cudaError_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mq, const tc::Params& p, int grid, cudaStream_t s) {
-    auto kern = tc::batch_scan_tc_kernel<METRIC, CS, PAIR>;
+    auto kern = tc::batch_scan_tc_kernel<METRIC, CS, PAIR, STREAM_A>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -763,7 +781,8 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     const uint32_t KP = t->KP;
     const uint32_t nq_pad = (nq + tc::BM - 1) / tc::BM * tc::BM;
     const bool pair = tc_use_pair(nq_pad / tc::BM);
-    const int CS = pair ? 2 : tc_cluster_size();
+    const bool stream_a = KP > tc::KCH_MAX * tc::BK;   // wide rows: the query block's K-chunks go through the ring
+    const int CS = pair ? 2 : (stream_a ? 1 : tc_cluster_size());
     if (first) {  // first scan of a batch: convert the queries, (re)encode the maps
         {
             cudaLaunchConfig_t cfg = {};
@@ -812,11 +831,13 @@ cudaError_t batch_scan_tensor(const FlatView& v, const BatchTensor& bt, const fl
     uint32_t per_group = std::max<uint32_t>(1, max_clusters / qgroups);
     per_group = std::min<uint32_t>(per_group, p.tiles);
     const int grid = static_cast<int>(per_group * qgroups * CS);
-#define VL_TC_LAUNCH(M)                                                          \
-    (CS == 1 ? launch_tc<M, 1>(t->map_x, t->map_q, p, grid, s)                  \
-             : CS == 2 ? (pair ? launch_tc<M, 2, true>(t->map_x, t->map_q, p, grid, s)  \
-                                    : launch_tc<M, 2>(t->map_x, t->map_q, p, grid, s))       \
-                       : launch_tc<M, 4>(t->map_x, t->map_q, p, grid, s))
+#define VL_TC_LAUNCH(M)                                                                            \
+    (stream_a ? (pair ? launch_tc<M, 2, true, true>(t->map_x, t->map_q, p, grid, s)               \
+                      : launch_tc<M, 1, false, true>(t->map_x, t->map_q, p, grid, s))             \
+     : CS == 1 ? launch_tc<M, 1>(t->map_x, t->map_q, p, grid, s)                                  \
+     : CS == 2 ? (pair ? launch_tc<M, 2, true>(t->map_x, t->map_q, p, grid, s)                    \
+                       : launch_tc<M, 2>(t->map_x, t->map_q, p, grid, s))                         \
+               : launch_tc<M, 4>(t->map_x, t->map_q, p, grid, s))
     switch (metric) {
         case COSINE: return VL_TC_LAUNCH(COSINE);
         case EUCLIDEAN: return VL_TC_LAUNCH(EUCLIDEAN);

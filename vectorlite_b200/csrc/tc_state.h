@@ -8,6 +8,10 @@
 
 namespace vl {
 
+// widest rows the tensor-core batched path takes (bf16 mirror, K padded to 64): up to 384 elements the query block is
+// resident in shared memory, wider rows stream its K-chunks through the ring (batch_tc.cu, STREAM_A)
+constexpr uint32_t TC_MAX_DIM = 2048;
+
 struct TcState {
     bool usable = false;
     uint32_t KP = 0;               // K padded to a multiple of 64 bf16 (one 128-byte swizzle row)
