@@ -239,7 +239,7 @@ int vl_index_set_mode(vl_index* h, int mode);
 int vl_index_set_pos_base(vl_index* h, uint64_t base);
 /* Counters since creation: [0] kernels launched, [1] searches served by the certified fast path,
  * [2] queries re-run on the exact path, [3] bytes H2D, [4] bytes D2H, [5] last HNSW visited,
- * [6] single-query scans served from the bf16 mirror of the rows (AUTO mode, 128/256/384-d, all four metrics),
+ * [6] single-query scans served from the bf16 mirror of the rows (AUTO mode, 128/256/384/768/1024/1536-d, all four metrics),
  * [7] single-query host searches that were combined with concurrent callers into a batched launch,
  * [8] queries whose certificate did not hold after a bf16 scan (mirror / tensor cores) and that were re-run at the
  *     next level (larger over-selection K', then the fp32 arena, then the exact path),

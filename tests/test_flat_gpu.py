@@ -555,9 +555,10 @@ def test_bf16_mirror_single_query_scan(vl, oracle_mod):
     assert t.stats()["exact_queries"] == before["exact_queries"]
 
 
-@pytest.mark.parametrize("dim", [128, 256])
+@pytest.mark.parametrize("dim", [128, 256, 768, 1024, 1536])
 def test_bf16_mirror_scan_other_widths(vl, oracle_mod, dim):
-    """The bf16-mirror single-query scan also serves 128- and 256-element rows (NCH = 1, 2)."""
+    """The bf16-mirror single-query scan also serves 128- and 256-element rows (NCH = 1, 2) and the widths of larger
+    embedding models (768 / 1024 / 1536 elements: NCH = 6 / 8 / 12, query still in registers)."""
     n, k = 12000, 10
     rows = oracle_mod.synth_rows(42, 0, n, dim)
     q = oracle_mod.synth_rows(43, 0, 3, dim)

@@ -469,7 +469,7 @@ int run_exact_one(vl_index* h, Slot& s, const FlatView& v, const float* d_query,
     return VL_OK;
 }
 
-// Single-query scans read the bf16 mirror of the rows when one applies (AUTO mode, 128/256/384-d, all four metrics):
+// Single-query scans read the bf16 mirror of the rows when one applies (AUTO mode, 128/256/384/768/1024/1536-d, all four metrics):
 // half the HBM bytes per query; the candidates are re-scored in f64 and certified with the bf16 bound exactly
 // as in the tensor-core batched path.  Brings the mirror up to date (lazily, like tc_prepare for batches) and
 // returns its pointers; `*mirror` stays null when the fp32 scan has to be used.

@@ -127,7 +127,7 @@ flat_scan_kernel(const void* __restrict__ rows_v, const float* __restrict__ aux,
     constexpr int TILE = (SCAN_THREADS / 32) * R;
     constexpr int LIMIT = SCAN_CAP - SCAN_TILES_PER_CHECK * TILE;
     constexpr int OWN_SHIFT = BF16 ? 1 : 2;              // owner lanes: every 2nd (16 rows) / 4th (8 rows)
-    static_assert(!BF16 || (NCH >= 1 && NCH <= 3), "the bf16 mirror variant serves rows of 128 / 256 / 384 elements");
+    static_assert(!BF16 || (NCH >= 1 && NCH <= 12), "the bf16 mirror variant serves rows of 128·NCH elements, query in registers");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
     float4* s_q = reinterpret_cast<float4*>(smem_raw + SCAN_CAP * sizeof(uint64_t));
@@ -415,7 +415,8 @@ cudaError_t launch_flat_scan(const FlatView& v, const float* d_queries, uint32_t
     }
 }
 
-// single-query scan over the bf16 mirror; requires pitch (== the mirror's padded width) of 128 / 256 / 384 elements
+// single-query scan over the bf16 mirror; requires pitch (== the mirror's padded width) of 128 / 256 / 384 / 768 / 1024 /
+// 1536 elements (the widths of common embedding models)
 template <int METRIC>
 static cudaError_t launch_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
                                uint32_t nq, const ScanWork& w, bool pipelined, cudaStream_t s) {
@@ -423,11 +424,16 @@ static cudaError_t launch_bf16(const FlatView& v, const void* mirror, const floa
         case 128: return launch_one<METRIC, 1, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
         case 256: return launch_one<METRIC, 2, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
         case 384: return launch_one<METRIC, 3, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        case 768: return launch_one<METRIC, 6, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        case 1024: return launch_one<METRIC, 8, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
+        case 1536: return launch_one<METRIC, 12, true>(mirror, sq_norm, v.n, v.pitch, d_queries, nq, w, pipelined, s);
         default: return cudaErrorNotSupported;
     }
 }
 
-bool flat_scan_bf16_supports(uint32_t pitch) { return pitch == 128 || pitch == 256 || pitch == 384; }
+bool flat_scan_bf16_supports(uint32_t pitch) {
+    return pitch == 128 || pitch == 256 || pitch == 384 || pitch == 768 || pitch == 1024 || pitch == 1536;
+}
 
 cudaError_t launch_flat_scan_bf16(const FlatView& v, const void* mirror, const float* sq_norm, const float* d_queries,
                                   uint32_t nq, int metric, const ScanWork& w, bool pipelined, cudaStream_t s) {

@@ -93,7 +93,7 @@ cudaError_t launch_flat_finalize(const FlatView& v, const float* d_queries, uint
                                  cudaStream_t s, const CertAux& aux = CertAux());
 size_t flat_scan_smem_bytes(uint32_t pitch);
 int flat_scan_max_grid_x(int device, uint32_t pitch);
-bool flat_scan_bf16_supports(uint32_t pitch);   // rows of 128 / 256 / 384 elements
+bool flat_scan_bf16_supports(uint32_t pitch);   // rows of 128 / 256 / 384 / 768 / 1024 / 1536 elements
 int flat_scan_bf16_max_grid_x(int device);   // the bf16 kernel keeps 2 CTAs per SM resident (124 registers)
 
 // exact path: every row scored in f64 in reference order
