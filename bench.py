@@ -440,6 +440,7 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also time the other metrics / batch modes at N > 1")
     ap.add_argument("--hnsw-rows", type=int, default=1_000_000, help="HNSW section size (0 = skip; rank 0, N=1 only)")
     ap.add_argument("--hnsw-efc", type=int, default=400, help="ef_construction (reference default: 400)")
+    ap.add_argument("--wide-rows", type=int, default=500_000, help="rows of the 768-d leg (0 = skip; rank 0, N=1 only)")
     ap.add_argument("--config5-rows", type=int, default=100_000_000,
                     help="BASELINE config 5 leg: total rows of the sharded B=1024, k=100 batch search (0 = skip); at "
                          "N = 1 one shard of the 8-GPU configuration (rows/8) is measured")
@@ -851,6 +852,51 @@ def main():
             cl.close()
         except Exception as e:  # noqa: BLE001
             e2e_extra["clustered_1024"] = {"error": repr(e)}
+
+    # ---- wide rows (768-d: BERT-base-sized embeddings; the reference's DEFAULT_VECTOR_DIMENSION, lib.rs:142) -----------
+    # rows wider than 384 elements: the tensor-core batch streams its query chunks through the TMA ring, single queries
+    # scan the bf16 mirror.  Checked against the product's own exact f64 path (VL_MODE_EXACT) on 8 queries.
+    if rank == 0 and world == 1 and args.wide_rows > 0:
+        try:
+            wd, wn = 768, args.wide_rows
+            wi = ShardedFlatIndex(wd, rank=0, world=1, device=local_rank)
+            wi.fill_synthetic(42, wn)
+            wi.local.set_pipelined(True)
+            src = vl.FlatIndex(wd, device=local_rank)
+            src.fill_synthetic(43, 1024, first_row=1000)
+            wq_h = np.ascontiguousarray(src.export()[1], dtype=np.float32)
+            src.close()
+            d_wq = torch.from_numpy(wq_h).to(dev)
+            w0 = wi.local.stats()
+            res = {}
+
+            def wb():
+                res["r"] = wi.search_device(d_wq, k, metric)
+            wb(); wb()
+            torch.cuda.synchronize()
+            wfailed = int((res["r"][3] & 1).sum().item())
+            ms_b = timed(wb, 10) / 10
+
+            def ws():
+                for qi in range(256):
+                    wi.search_device(d_wq[qi:qi + 1], k, metric)
+            ws()
+            us_s = timed(ws, 2) / 2 / 256 * 1e3
+            w1 = wi.local.stats()
+            a_ids, a_sc, _ = wi.local.search_batch(wq_h[:8], k, metric)
+            wi.local.set_mode(vl.Mode.Exact)
+            x_ids, x_sc, _ = wi.local.search_batch(wq_h[:8], k, metric)
+            e2e_extra["wide_rows_768"] = {
+                "workload": f"flat {wn} x {wd} f32, {args.metric}, k={k}", "batch_1024_ms": ms_b,
+                "batch_1024_tflops": 2.0 * 1024 * wn * wd / (ms_b * 1e-3) / 1e12, "batch_cert_failed_of_1024": wfailed,
+                "tensor_queries": w1["tensor_queries"] - w0["tensor_queries"],
+                "single_query_us_pipelined": us_s, "single_query_GBps_at_2B_per_element": wn * wd * 2 / (us_s * 1e-6) / 1e9,
+                "bf16_mirror_scans": w1["bf16_scans"] - w0["bf16_scans"],
+                "equals_exact_f64_path_on_8_queries": bool(np.array_equal(a_ids, x_ids) and
+                                                           np.array_equal(a_sc.view(np.uint64), x_sc.view(np.uint64)))}
+            wi.local.close()
+        except Exception as e:  # noqa: BLE001
+            e2e_extra["wide_rows_768"] = {"error": repr(e)}
 
     # ---- BASELINE config 5: 100M x 384 row-sharded, B = 1024, k = 100 (strong scaling over N) ------------------
     if args.config5_rows > 0:
