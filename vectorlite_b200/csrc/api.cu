@@ -585,6 +585,10 @@ static int run_pass(vl_index* h, Slot& s, const FlatView& v, const float* querie
     CU(cudaMemcpyAsync(s.d_q, s.h_q, qbytes, cudaMemcpyHostToDevice, s.stream));
     h->stats[ST_H2D] += qbytes;
     SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
+    // small batches (the combiner's cohorts of concurrent single-query callers): the rescore kernel writes its
+    // results straight into the pinned host mirror (UVA zero-copy) — no D2H copy operation, one synchronize
+    const bool zero_copy = batched && !cfg.exact && m <= 128;
+    if (zero_copy) out = SearchOut{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
     if (cfg.exact) {
         for (uint32_t q = 0; q < m; ++q) {
             st = run_exact_one(h, s, v, s.d_q + static_cast<size_t>(q) * h->pitch, metric, k, q, s.stream);
@@ -606,8 +610,13 @@ static int run_pass(vl_index* h, Slot& s, const FlatView& v, const float* querie
             CU(cudaStreamSynchronize(s.stream));
         } else {
             CU(launch_batch_flat(v, s.d_q, m, k, metric, cfg.Kp, bw, out, nullptr, &nl, s.stream, cfg.kp_base));
+            if (zero_copy) CU(cudaStreamSynchronize(s.stream));
         }
         h->stats[ST_LAUNCHES] += nl;
+        if (zero_copy) {
+            h->stats[ST_D2H] += static_cast<size_t>(m) * (k * 16 + 8);
+            return VL_OK;
+        }
     } else {
         // few queries: the finalize kernel writes its (tiny) results straight into the pinned host mirror (UVA
         // zero-copy), which saves the D2H copy operation on the latency path

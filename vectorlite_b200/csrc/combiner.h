@@ -42,6 +42,19 @@ public:
         queue_.push_back(&me);
         while (!me.done) {
             if (leader_) {
+                // A batch is in flight (a few hundred µs on the device).  Waking through the condition variable costs a
+                // futex round trip plus a reschedule per caller — tens of µs that the NEXT batch waits for, since its
+                // leader gathers the re-forming cohort first.  When the callers fit the host's cores, wait for the
+                // running batch by polling (bounded: spin_us, default 400 µs) and only then block.
+                if (spin_us() > 0 && expect_ <= cores()) {
+                    lk.unlock();
+                    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us());
+                    while (!me.done.load(std::memory_order_acquire) && leader_.load(std::memory_order_acquire) &&
+                           std::chrono::steady_clock::now() < deadline)
+                        cpu_relax();
+                    lk.lock();
+                    if (me.done || !leader_) continue;
+                }
                 cv_.wait(lk);
                 continue;
             }
@@ -127,8 +140,25 @@ private:
     struct Pending {
         const float* q; uint32_t k; int metric; uint32_t ef;
         uint64_t* ids; double* scores; uint32_t* count;
-        int rc = VL_OK; bool done = false; std::string err;
+        int rc = VL_OK; std::atomic<bool> done{false}; std::string err;
     };
+    static int spin_us() {
+        static const int us = [] { const char* e = std::getenv("VL_COMBINE_SPIN_US"); return e ? std::max(0, atoi(e)) : 400; }();
+        return us;
+    }
+    static size_t cores() {
+        static const size_t n = std::max(1u, std::thread::hardware_concurrency());
+        return n;
+    }
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#elif defined(__aarch64__)
+        asm volatile("yield" ::: "memory");
+#else
+        std::this_thread::yield();
+#endif
+    }
     static int wait_us() {
         static const int us = [] { const char* e = std::getenv("VL_COMBINE_WAIT_US"); return e ? std::max(0, atoi(e)) : 100; }();
         return us;
@@ -136,7 +166,7 @@ private:
     std::mutex mu_;
     std::condition_variable cv_;
     std::vector<Pending*> queue_;
-    bool leader_ = false;
+    std::atomic<bool> leader_{false};
     size_t expect_ = 1;   // size of the batch that just completed: how many callers the next leader may wait for
 };
 
