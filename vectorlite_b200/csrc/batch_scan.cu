@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(256) batch_select_kernel(uint64_t* cand, uint3
 // Threshold estimation (tensor path, large stores): tau[q] = the Kp-th largest of the G group maxima written by the
 // SCAN_GROUPMAX stage — Kp disjoint groups each hold a row scoring >= it, so it is a valid lower bound of the Kp-th
 // best score of the store.  One warp per query; the exact Kp-th largest is built bit by bit on the orderable
-// pattern (32 count-and-vote steps over <= 32 values per lane).
+// pattern (32 count-and-vote steps over NV = G / 32 values per lane; G = 512 → 16 compares per step, not 64).
+template <int NV>
 __global__ void __launch_bounds__(256) batch_tau_kernel(const float* __restrict__ gmax, uint32_t G, int Kp, float* tau,
                                                         uint32_t nq) {
     const int lane = threadIdx.x & 31;
@@ -248,9 +249,10 @@ __global__ void __launch_bounds__(256) batch_tau_kernel(const float* __restrict_
     pdl_wait();
     if (threadIdx.x == 0) pdl_launch_dependents();
     if (q >= nq) return;
-    uint32_t v[GMAX_STRIDE / 32];
+    static_assert(NV * 32 <= static_cast<int>(GMAX_STRIDE), "group maxima per query");
+    uint32_t v[NV];
 #pragma unroll
-    for (int i = 0; i < static_cast<int>(GMAX_STRIDE / 32); ++i) {
+    for (int i = 0; i < NV; ++i) {
         const uint32_t g = static_cast<uint32_t>(i) * 32 + lane;
         v[i] = g < G ? f32_orderable(__ldcg(gmax + static_cast<size_t>(q) * GMAX_STRIDE + g)) : 0u;
     }
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(256) batch_tau_kernel(const float* __restrict_
         const uint32_t c = T | (1u << bit);
         int cnt = 0;
 #pragma unroll
-        for (int i = 0; i < static_cast<int>(GMAX_STRIDE / 32); ++i) cnt += v[i] >= c;
+        for (int i = 0; i < NV; ++i) cnt += v[i] >= c;
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
         if (cnt >= Kp) T = c;
     }
@@ -313,7 +315,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int METRIC>
+// NBUF: depth of the cp.async chunk ring.  2 keeps the CTA small (9 per SM: a 1024-query batch in one wave); a few
+// queries (the combiner's cohorts) are latency-bound instead — 12 chunk loads one DRAM round trip apart — and run with 4.
+template <int METRIC, int NBUF>
 __global__ void batch_rescore_stream_kernel(FinalizeParams p, const uint32_t* count, const uint32_t* qflags,
                                             uint32_t capq, int KpR) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -322,7 +326,7 @@ __global__ void batch_rescore_stream_kernel(FinalizeParams p, const uint32_t* co
     double* s_exact = reinterpret_cast<double*>(s_keys + KpR);                // [KpR]
     double* s_qd = s_exact + KpR;                                             // [pitch]
     uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_qd + p.pitch);            // [KpR]
-    float* s_tile = reinterpret_cast<float*>(s_pos + KpR);                    // [2][KpR][TS]
+    float* s_tile = reinterpret_cast<float*>(s_pos + KpR);                    // [NBUF][KpR][TS]
     __shared__ double s_qnorm, s_qn2;
     __shared__ int s_nan;
     const uint32_t qi = blockIdx.x;
@@ -352,55 +356,98 @@ __global__ void batch_rescore_stream_kernel(FinalizeParams p, const uint32_t* co
 
     // ---- (2) exact f64 rescore ----------------------------------------------------------------------
     const int nchunks = static_cast<int>((p.dim + CH - 1) / CH);
+    // Fixed thread → (row, 16-byte column) assignment for the chunk loads: W4 threads per row, nthreads / W4 rows per
+    // pass, the row pointers of this thread's (<= 8) passes computed ONCE — the per-chunk issue is then one predicated
+    // cp.async per pass (it used to redo an integer division and a 64-bit multiply per 16 bytes, ~12 of this kernel's
+    // 23 µs at 16 queries).
+    constexpr int MAXP = 8;
+    const int W4 = CH >> 2;
+    const int lrow = tid / W4, lcc = tid - lrow * W4, rpp = nthreads / W4;
+    const float* rp[MAXP];
+#pragma unroll
+    for (int u = 0; u < MAXP; ++u) {
+        const int r = lrow + u * rpp;
+        rp[u] = (lrow < rpp && r < nc) ? p.rows + static_cast<size_t>(s_pos[r]) * p.pitch + lcc * 4 : nullptr;
+    }
     auto issue = [&](int c, int buf) {
         const uint32_t c0 = static_cast<uint32_t>(c) * CH;
         const int w4 = (min(static_cast<uint32_t>(CH), p.dim - c0) + 3) >> 2;
-        float* dst = s_tile + static_cast<size_t>(buf) * KpR * TS;
-        const int total = nc * w4;
-        for (int i = tid; i < total; i += nthreads) {
-            const int r = i / w4, cc = i - r * w4;
-            cp_async16(dst + r * TS + cc * 4, p.rows + static_cast<size_t>(s_pos[r]) * p.pitch + c0 + cc * 4);
+        float* dst = s_tile + static_cast<size_t>(buf) * KpR * TS + lrow * TS + lcc * 4;
+        if (lcc < w4) {
+#pragma unroll
+            for (int u = 0; u < MAXP; ++u)
+                if (rp[u]) cp_async16(dst + u * rpp * TS, rp[u] + c0);
         }
         cp_async_commit();
     };
     double a0 = 0.0, a1 = 0.0, qn2 = 0.0;
-    issue(0, 0);
+#pragma unroll
+    for (int c = 0; c < NBUF - 1; ++c) {   // NBUF − 1 groups in flight before the first wait (empty ones past the end)
+        if (c < nchunks) issue(c, c); else cp_async_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) issue(c + 1, (c + 1) & 1); else cp_async_commit();
-        cp_async_wait<1>();
+        if (c + NBUF - 1 < nchunks) issue(c + NBUF - 1, (c + NBUF - 1) % NBUF); else cp_async_commit();
+        cp_async_wait<NBUF - 1>();
         __syncthreads();
         const uint32_t c0 = static_cast<uint32_t>(c) * CH;
         const int w = static_cast<int>(min(static_cast<uint32_t>(CH), p.dim - c0));
         if (tid < nc) {
-            const float4* t4 = reinterpret_cast<const float4*>(s_tile + (static_cast<size_t>(c & 1) * KpR + tid) * TS);
+            const float4* t4 = reinterpret_cast<const float4*>(s_tile + (static_cast<size_t>(c % NBUF) * KpR + tid) * TS);
             const double* yq = s_qd + c0;
-            for (int j4 = 0; j4 * 4 < w; ++j4) {
-                const float4 v = t4[j4];
-                const float xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = j4 * 4 + e;
-                    if (j < w) {
-                        const double x = static_cast<double>(xs[e]), y = yq[j];
-                        if (METRIC == COSINE) {
-                            a0 = __dadd_rn(a0, __dmul_rn(x, y));
-                            a1 = __dadd_rn(a1, __dmul_rn(x, x));
-                        } else if (METRIC == EUCLIDEAN) {
-                            const double d = __dsub_rn(x, y);
-                            a0 = __dadd_rn(a0, __dmul_rn(d, d));
-                        } else if (METRIC == MANHATTAN) {
-                            a0 = __dadd_rn(a0, fabs(__dsub_rn(x, y)));
-                        } else {
-                            a0 = __dadd_rn(a0, __dmul_rn(x, y));
-                        }
-                    }
+            // one element of the reference's chains (lib.rs:425-572): same operations in the same order, no FMA
+            auto step = [&](float xf, double y) {
+                const double x = static_cast<double>(xf);
+                if (METRIC == COSINE) {
+                    a0 = __dadd_rn(a0, __dmul_rn(x, y));
+                    a1 = __dadd_rn(a1, __dmul_rn(x, x));
+                } else if (METRIC == EUCLIDEAN) {
+                    const double d = __dsub_rn(x, y);
+                    a0 = __dadd_rn(a0, __dmul_rn(d, d));
+                } else if (METRIC == MANHATTAN) {
+                    a0 = __dadd_rn(a0, fabs(__dsub_rn(x, y)));
+                } else {
+                    a0 = __dadd_rn(a0, __dmul_rn(x, y));
                 }
+            };
+            // Straight-line blocks of 16 elements (no bounds checks, 128-bit shared loads): the kernel is one serial
+            // f64 add chain per candidate, so what matters is that nothing but the DADD latency sits between two
+            // links — the checked per-element loop spent ~120 cycles per element (17 instructions, a branch each).
+            int j = 0;
+            for (; j + 16 <= w; j += 16) {
+                float4 v[4];
+                double2 y2[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = t4[(j >> 2) + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y2[u] = *reinterpret_cast<const double2*>(yq + j + 2 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    step(v[u].x, y2[2 * u].x);
+                    step(v[u].y, y2[2 * u].y);
+                    step(v[u].z, y2[2 * u + 1].x);
+                    step(v[u].w, y2[2 * u + 1].y);
+                }
+            }
+            if (j < w) {   // tail of the last chunk (dim not a multiple of 16)
+                const float* t1 = reinterpret_cast<const float*>(t4);
+                for (; j < w; ++j) step(t1[j], yq[j]);
             }
         } else if (tid == nthreads - 1) {   // query-only chain Σy² (cosine: lib.rs:433; others: certificate)
             const double* yq = s_qd + c0;
-            for (int j = 0; j < w; ++j) qn2 = __dadd_rn(qn2, __dmul_rn(yq[j], yq[j]));
+            int j = 0;
+            for (; j + 16 <= w; j += 16) {
+                double2 y2[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y2[u] = *reinterpret_cast<const double2*>(yq + j + 2 * u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    qn2 = __dadd_rn(qn2, __dmul_rn(y2[u].x, y2[u].x));
+                    qn2 = __dadd_rn(qn2, __dmul_rn(y2[u].y, y2[u].y));
+                }
+            }
+            for (; j < w; ++j) qn2 = __dadd_rn(qn2, __dmul_rn(yq[j], yq[j]));
         }
-        __syncthreads();   // buffer (c & 1) may be refilled by the next iteration's issue
+        __syncthreads();   // buffer (c % NBUF) may be refilled by the next iteration's issue
     }
     if (tid == nthreads - 1) {
         s_qn2 = qn2;
@@ -426,15 +473,15 @@ __global__ void batch_rescore_stream_kernel(FinalizeParams p, const uint32_t* co
     rank_and_certify(p, qi, nc, s_keys, s_exact, s_pos, &s_qnorm, &s_nan, qflags[qi]);
 }
 
-static size_t rescore_stream_smem(int KpR, int CH, uint32_t pitch) {
+static size_t rescore_stream_smem(int KpR, int CH, uint32_t pitch, int nbuf) {
     return static_cast<size_t>(KpR) * (8 + 8 + 4) + static_cast<size_t>(pitch) * 8 +
-           2ull * KpR * (CH + 4) * sizeof(float);
+           static_cast<size_t>(nbuf) * KpR * (CH + 4) * sizeof(float);
 }
 
-template <int METRIC>
+template <int METRIC, int NBUF>
 static cudaError_t launch_rescore_stream(const FinalizeParams& p, const BatchWork& w, uint32_t nq, int KpR,
                                          size_t smem, cudaStream_t s) {
-    auto kern = batch_rescore_stream_kernel<METRIC>;
+    auto kern = batch_rescore_stream_kernel<METRIC, NBUF>;
     if (smem > 40 * 1024) {   // dynamic + the kernel's static shared memory must stay under the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
@@ -540,8 +587,10 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, batch_tau_kernel, static_cast<const float*>(w.gmax), G, Kp, w.tau, nq)) != cudaSuccess)
-            return e;
+        e = G <= 512u ? cudaLaunchKernelEx(&cfg, batch_tau_kernel<16>, static_cast<const float*>(w.gmax), G, Kp, w.tau, nq)
+                      : cudaLaunchKernelEx(&cfg, batch_tau_kernel<static_cast<int>(GMAX_STRIDE / 32)>,
+                                           static_cast<const float*>(w.gmax), G, Kp, w.tau, nq);
+        if (e != cudaSuccess) return e;
         nl += 2;
         // VL_BATCH_STAGES=m (experiments): balanced schedule — the filtered stages end at S_eq·r, S_eq·r², … n with the
         // same ratio r = (n / S_eq)^(1/m).  Measured at 1M × 384, B = 1024 (profiles/r02_batch_schedule_sweeps.txt):
@@ -609,13 +658,16 @@ cudaError_t launch_batch_flat(const FlatView& v, const float* d_queries, uint32_
         // (16-column chunks would let the CTA fit beside a resident scan CTA of a chained next batch — measured
         // SLOWER, 0.732 vs 0.705 ms per 1024-query batch: the gathers then compete with the MMA stage's TMA stream)
         p.CH = KpR <= 64 ? 32 : 16;
-        const size_t smem = rescore_stream_smem(KpR, p.CH, v.pitch);
+        const bool deep = nq <= 296;   // at most two CTAs per SM: latency-bound, four chunk loads in flight
+        const size_t smem = rescore_stream_smem(KpR, p.CH, v.pitch, deep ? 4 : 2);
+#define VL_RESCORE(M) (deep ? launch_rescore_stream<M, 4>(p, w, nq, KpR, smem, s) : launch_rescore_stream<M, 2>(p, w, nq, KpR, smem, s))
         switch (metric) {
-            case COSINE: e = launch_rescore_stream<COSINE>(p, w, nq, KpR, smem, s); break;
-            case EUCLIDEAN: e = launch_rescore_stream<EUCLIDEAN>(p, w, nq, KpR, smem, s); break;
-            case MANHATTAN: e = launch_rescore_stream<MANHATTAN>(p, w, nq, KpR, smem, s); break;
-            default: e = launch_rescore_stream<DOT>(p, w, nq, KpR, smem, s); break;
+            case COSINE: e = VL_RESCORE(COSINE); break;
+            case EUCLIDEAN: e = VL_RESCORE(EUCLIDEAN); break;
+            case MANHATTAN: e = VL_RESCORE(MANHATTAN); break;
+            default: e = VL_RESCORE(DOT); break;
         }
+#undef VL_RESCORE
         if (e != cudaSuccess) return e;
     } else {
         batch_rescore_kernel<<<nq, FIN_THREADS, rescore_smem(Kp, CH), s>>>(p, w.count, w.qflags, w.capq);
