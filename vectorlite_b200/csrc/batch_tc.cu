@@ -481,7 +481,9 @@ batch_scan_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     float thr = tau;
                     if (METRIC == EUCLIDEAN) {
                         const float xm = __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, __float_as_uint(xn_lane)));
-                        thr = 0.5f * (tau + xm) - (4e-7f * (fabsf(tau) + xm) + 1e-30f);
+                        // (a lane without a query carries tau = +inf: inf − inf would make the threshold NaN and send
+                        // every chunk of that lane down the survivor path — 2x the batch time at 16 queries)
+                        thr = tau < INFINITY ? 0.5f * (tau + xm) - (4e-7f * (fabsf(tau) + xm) + 1e-30f) : INFINITY;
                     }
                     // Fast reject: the chunk's NaN-propagating maximum (16 three-input FMNMX3 for 32 scores, two
                     // independent chains) against the threshold.  Only when some lane of the warp has a candidate (or a
