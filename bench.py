@@ -826,6 +826,7 @@ def main():
             cl.search_batch(cq[:1], k, metric)
             s0 = cl.stats()
             lone = native_callers(cl, cq, k, metric, 0, 1, 2048)
+            native_callers(cl, cq, k, metric, 0, E2E_CALLERS, 4096)   # warm-up like the main e2e leg (scratch at the larger K')
             many = native_callers(cl, cq, k, metric, 0, E2E_CALLERS, 16384)
             s1 = cl.stats()
             tb = []
