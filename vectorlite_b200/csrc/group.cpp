@@ -14,7 +14,9 @@
 // inside vl_index_search.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <deque>
 #include <mutex>
 #include <string>
@@ -37,7 +39,7 @@ struct Call {
     std::vector<std::string> err;
     std::mutex mu;
     std::condition_variable cv;
-    uint32_t remaining = 0;
+    std::atomic<uint32_t> remaining{0};
 };
 
 struct Task {
@@ -55,7 +57,32 @@ struct vl_group {
     std::condition_variable cv;
     std::deque<Task> queue;
     bool stop = false;
+    std::atomic<int> pending{0};     // tasks in `queue` (read by polling helpers without the lock)
+    std::atomic<int> spinners{0};    // helpers currently polling
+    std::atomic<bool> stopping{false};
     vl::Combiner comb;   // concurrent single-query callers → ONE fan-out of a small batch to all shards
+
+    // A fan-out every few hundred µs: waking the helpers through the condition variable costs a futex round trip and
+    // a reschedule per shard and per batch — comparable to the device time of a small batch.  Up to one helper per
+    // remote shard therefore keeps polling for the next task for a bounded time (VL_GROUP_SPIN_US, default 400 µs)
+    // before it blocks; the caller polls the completion count the same way.  Only when helpers + callers fit the cores.
+    static int spin_us() {
+        static const int us = [] { const char* e = std::getenv("VL_GROUP_SPIN_US"); return e ? std::max(0, atoi(e)) : 400; }();
+        return us;
+    }
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#elif defined(__aarch64__)
+        asm volatile("yield" ::: "memory");
+#else
+        std::this_thread::yield();
+#endif
+    }
+    int max_spinners() const {
+        const int cores = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+        return std::max(0, std::min(static_cast<int>(shards.size()) - 1, cores / 2));
+    }
 
     void run_shard(Call* c, uint32_t s) {
         c->ids[s].resize(static_cast<size_t>(c->nq) * c->k);
@@ -69,16 +96,39 @@ struct vl_group {
     void helper_loop() {
         for (;;) {
             Task t;
+            bool got = false;
             {
                 std::unique_lock<std::mutex> lk(mu);
+                if (!queue.empty()) {
+                    t = queue.front();
+                    queue.pop_front();
+                    pending.fetch_sub(1, std::memory_order_relaxed);
+                    got = true;
+                } else if (stop) {
+                    return;
+                }
+            }
+            if (!got) {
+                if (spin_us() > 0 && spinners.fetch_add(1) < max_spinners()) {
+                    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us());
+                    while (pending.load(std::memory_order_acquire) == 0 && !stopping.load(std::memory_order_relaxed) &&
+                           std::chrono::steady_clock::now() < deadline)
+                        cpu_relax();
+                    spinners.fetch_sub(1);
+                    if (pending.load(std::memory_order_acquire) > 0) continue;   // try to take it
+                } else if (spin_us() > 0) {
+                    spinners.fetch_sub(1);
+                }
+                std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return stop || !queue.empty(); });
-                if (queue.empty()) return;   // stop
-                t = queue.front();
-                queue.pop_front();
+                continue;
             }
             run_shard(t.call, t.shard);
-            std::lock_guard<std::mutex> lk(t.call->mu);
-            if (--t.call->remaining == 0) t.call->cv.notify_one();
+            {   // decrement UNDER the call's mutex: the caller (which polls `remaining`, then takes this mutex before it
+                // lets the Call go out of scope) cannot destroy it while this thread is still inside
+                std::lock_guard<std::mutex> lk(t.call->mu);
+                if (t.call->remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) t.call->cv.notify_one();
+            }
         }
     }
 };
@@ -111,6 +161,7 @@ void vl_group_destroy(vl_group* g) {   // the shards stay alive: they belong to 
     {
         std::lock_guard<std::mutex> lk(g->mu);
         g->stop = true;
+        g->stopping = true;
     }
     g->cv.notify_all();
     for (auto& t : g->helpers) t.join();
@@ -159,12 +210,18 @@ static int group_search_impl(vl_group* g, const float* queries, uint32_t nq, uin
     {
         std::lock_guard<std::mutex> lk(g->mu);
         for (size_t i = 1; i < live.size(); ++i) g->queue.push_back(Task{&c, live[i]});
+        g->pending.fetch_add(static_cast<int>(live.size()) - 1, std::memory_order_release);
     }
     g->cv.notify_all();
     g->run_shard(&c, live[0]);
+    if (vl_group::spin_us() > 0) {   // the other shards finish within µs of this one: poll before blocking
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(vl_group::spin_us());
+        while (c.remaining.load(std::memory_order_acquire) != 0 && std::chrono::steady_clock::now() < deadline)
+            vl_group::cpu_relax();
+    }
     {
         std::unique_lock<std::mutex> lk(c.mu);
-        c.cv.wait(lk, [&] { return c.remaining == 0; });
+        c.cv.wait(lk, [&] { return c.remaining.load(std::memory_order_acquire) == 0; });
     }
     for (uint32_t s : live)
         if (c.rc[s] != VL_OK) {   // every shard sees the same query: report the first failure (dimension, NaN, …)
