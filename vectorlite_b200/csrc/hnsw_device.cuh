@@ -30,6 +30,8 @@ struct HnswParams {
     uint32_t rerank = 0;                  // beam entries re-scored in f64 before the top k are taken (>= k; = k when the
                                           // traversal's distances are fp32; 4k..64+ when they come from the bf16 mirror,
                                           // whose rounding (~1e-3 on a cosine) reorders near-ties among the best entries)
+    uint32_t merge = 0;                   // CTAs of >= 4 warps (search): the pool stays sorted, a step's survivors are merged
+                                          // in by the whole CTA (rank counting) instead of inserted one by one by warp 0
     uint32_t score_mode = 0;              // 0: exact flat similarity, 1: the reference's quantised score (hnsw.rs:478,51-75)
     uint64_t* out_ids;
     double* out_scores;

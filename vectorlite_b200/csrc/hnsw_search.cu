@@ -47,7 +47,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_k
     uint16_t* s_vis = reinterpret_cast<uint16_t*>(s_beam + p.beam_cap);
     unsigned long long* s_ck = reinterpret_cast<unsigned long long*>(s_vis + p.vis_mask + 1);   // candidate keys of this step
     uint32_t* s_cid = reinterpret_cast<uint32_t*>(s_ck + p.cand_cap);
-    __shared__ int s_nc, s_size, s_done;
+    // merge mode (CTAs of >= 4 warps, search): second pool buffer + the compacted survivors of a step
+    unsigned long long* s_beam2 = reinterpret_cast<unsigned long long*>(s_cid + p.cand_cap);
+    unsigned long long* s_surv = s_beam2 + p.beam_cap;
+    const bool merge_mode = WARPS >= 4 && !BUILD && p.merge != 0u;
+    __shared__ int s_nc, s_size, s_done, s_nlive;
     __shared__ float s_invq;
     // result staging reuses the traversal's scratch (dead by then): exact scores over the candidate keys,
     // result nodes over the candidate ids (cand_cap >= k), quantised scores (reference score mode) over the
@@ -202,6 +206,29 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_k
                 // pick first (shared memory only), then fetch: the adjacency rows of all picked entries are
                 // requested together, so a step waits for ONE global-memory round trip instead of `expand`
                 uint32_t node_e[MAXE];
+                if (merge_mode && ef > 1u) {
+                    // the pool is SORTED (merged by the whole CTA at the end of every step): the entries to expand are
+                    // simply the first `expand` ones without the expanded flag — one ballot per 32 entries
+#pragma unroll
+                    for (int e = 0; e < MAXE; ++e) node_e[e] = HNSW_NONE;
+                    if (lane == 0) s_nlive = 0;
+                    for (int i0 = 0; i0 < size && picked < expand; i0 += 32) {
+                        const int i = i0 + lane;
+                        const unsigned long long kk = i < size ? s_beam[i] : 1ull;
+                        unsigned m = __ballot_sync(0xFFFFFFFFu, !(kk & 1ull));
+                        while (m && picked < expand) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t node = __shfl_sync(0xFFFFFFFFu, static_cast<uint32_t>(kk >> 1) & 0x7FFFFFFFu, src);
+#pragma unroll
+                            for (int e = 0; e < MAXE; ++e)
+                                if (e == picked) node_e[e] = node;
+                            if (lane == src) s_beam[i] = kk | 1ull;
+                            ++picked;
+                        }
+                    }
+                    __syncwarp();
+                } else {
 #pragma unroll
                 for (int e = 0; e < MAXE; ++e) {
                     node_e[e] = HNSW_NONE;
@@ -218,6 +245,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_k
                     node_e[e] = static_cast<uint32_t>(best) & 0x7FFFFFFFu;
                     if (lane == 0) s_beam[bi] |= 1ull;
                     __syncwarp();
+                }
                 }
                 const uint32_t* adj_e[MAXE];
                 if (lvl == 0) {
@@ -265,14 +293,72 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_k
             // ---- all warps: distances, 8 candidates per warp per round; candidates that cannot enter
             // the pool (not closer than its current worst entry) are dropped right here
             const unsigned long long worst_now = s_worst;
+            const bool merging = merge_mode && ef > 1u;
             for (int g0 = warp * 8; g0 < nc; g0 += WARPS * 8) {
                 const int cnt = min(8, nc - g0);
                 score8(s_cid + g0, cnt, s_ck + g0);
                 __syncwarp();
-                if (lane < cnt && (s_ck[g0 + lane] >> 1) >= worst_now) s_ck[g0 + lane] = ~0ull;
+                if (merging) {   // survivors are compacted as they are scored (order irrelevant: keys are unique per node)
+                    const unsigned long long key = lane < cnt ? s_ck[g0 + lane] : ~0ull;
+                    const bool live = lane < cnt && (key >> 1) < worst_now;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&s_nlive, __popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (live) s_surv[base + __popc(m & ((1u << lane) - 1u))] = key;
+                } else if (lane < cnt && (s_ck[g0 + lane] >> 1) >= worst_now) {
+                    s_ck[g0 + lane] = ~0ull;
+                }
             }
             n_eval += (tid == 0) ? nc : 0;
             __syncthreads();
+            if (merging) {
+                // ---- whole CTA: merge the sorted pool with this step's survivors by rank counting -----------------------
+                // (warp 0 used to insert them one by one, re-deriving the pool's worst entry after each: ~300 cycles per
+                // survivor, ~200 survivors in the steps that fill the pool — tens of µs of a lone query's latency)
+                const int size = s_size, L = s_nlive;
+                auto lower_bound_pool = [&](unsigned long long k1) {   // first pool index with (key >> 1) >= k1
+                    int lo = 0, hi = size;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((s_beam[mid] >> 1) < k1) lo = mid + 1; else hi = mid;
+                    }
+                    return lo;
+                };
+                // pass A: drop exact duplicates (the visited cache is lossy): of a pool entry, or of an earlier survivor.
+                // Writing ~0 while others still compare is benign: whoever equals a dropped key is dropped by the same witness.
+                for (int i = tid; i < L; i += THREADS) {
+                    const unsigned long long k1 = s_surv[i] >> 1;
+                    const int lb = lower_bound_pool(k1);
+                    bool dup = lb < size && (s_beam[lb] >> 1) == k1;
+                    for (int j = 0; j < i && !dup; ++j) dup = (s_surv[j] >> 1) == k1;
+                    if (dup) s_surv[i] = ~0ull;
+                }
+                __syncthreads();
+                // pass B: rank = entries of the other list below + own position; the first ef ranks form the new pool
+                int dropped = 0;
+                for (int e = tid; e < size + L; e += THREADS) {
+                    const unsigned long long key = e < size ? s_beam[e] : s_surv[e - size];
+                    if (key == ~0ull) { ++dropped; continue; }
+                    const unsigned long long k1 = key >> 1;
+                    int r = e < size ? e : lower_bound_pool(k1);
+                    for (int j = 0; j < L; ++j) r += (s_surv[j] >> 1) < k1;   // (~0 >> 1 is never below a key)
+                    if (r < static_cast<int>(ef)) s_beam2[r] = key;
+                }
+                if (dropped) atomicSub(&s_nlive, dropped);
+                __syncthreads();
+                {
+                    unsigned long long* t = s_beam; s_beam = s_beam2; s_beam2 = t;
+                }
+                if (tid == 0) {
+                    const int ns = min(static_cast<int>(ef), size + s_nlive);
+                    s_size = ns;
+                    s_worst = ns == static_cast<int>(ef) ? (s_beam[ns - 1] >> 1) : ~0ull;
+                    s_worst_idx = ns - 1;
+                }
+                __syncthreads();
+                continue;
+            }
             // ---- warp 0: insert the survivors (append while the pool is filling, else replace the worst)
             if (warp == 0) {
                 int size = s_size;
@@ -420,7 +506,7 @@ static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStre
 
 // beam / visited-cache sizing shared by search and construction; returns the dynamic smem bytes
 static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg, uint32_t k, uint32_t pitch,
-                        bool wide = false) {
+                        bool wide = false, bool merge = false) {
     const bool query_in_smem = pitch != 384;   // launch_warps: pitch 384 runs the register-resident (NCH = 3) kernels
     p.ef = W;
     uint32_t bcap = 64;
@@ -448,8 +534,10 @@ static size_t size_pool(HnswParams& p, uint32_t W, uint32_t M0, uint32_t max_deg
     if (cc < p.refine) cc = p.refine;    // ... and so does the fp32 refinement of the beam's head
     if (cc < 8) cc = 8;
     p.cand_cap = (cc + 7u) & ~7u;
+    p.merge = merge ? 1u : 0u;   // second pool buffer + compacted survivors (whole-CTA rank merge)
     return (query_in_smem ? static_cast<size_t>(pitch) * 4 : 0) + static_cast<size_t>(bcap) * 8 +
-           static_cast<size_t>(cap) * 2 + static_cast<size_t>(p.cand_cap) * 12;
+           static_cast<size_t>(cap) * 2 + static_cast<size_t>(p.cand_cap) * 12 +
+           (merge ? (static_cast<size_t>(bcap) + p.cand_cap) * 8 : 0);
 }
 
 // construction-time search (hnsw_build.cu): node order[i]'s row is query i; greedy descent from the entry
@@ -513,8 +601,10 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     p.refine = 0;
     if (rows_bf16 && pitch == 384)
         p.refine = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(4ull * k, 64), std::min<uint64_t>(W, HN_REFINE_MAX)));
-    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch,
-                                  hnsw_cta_warps(static_cast<uint32_t>(W), nq) >= 16);
+    const int cta_warps = hnsw_cta_warps(static_cast<uint32_t>(W), nq);
+    static const bool no_merge = std::getenv("VL_HNSW_NO_MERGE") != nullptr;
+    const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch, cta_warps >= 16,
+                                  cta_warps >= 4 && !no_merge);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, false>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN, false>(p, nq, smem, stream);
