@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import vectorlite_b200 as vl
-n, nq, dim = int(os.environ.get("N", 200000)), 4096, 384
+n, nq, dim = int(os.environ.get("N", 200000)), int(os.environ.get("NQ", 4096)), 384
 flat = vl.FlatIndex(dim); flat.fill_synthetic(42, n, clusters=1024)
 qi = vl.FlatIndex(dim); qi.fill_synthetic(43, nq, clusters=1024)
 ids, rows = flat.export(); q = qi.export()[1]

@@ -30,7 +30,7 @@
 namespace vl {
 
 template <int METRIC, int NCH, bool BUILD, int WARPS, bool BF16>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_kernel(HnswParams p) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : (WARPS == 2 ? 16 : (WARPS == 4 ? 8 : 1))) hnsw_search_kernel(HnswParams p) {
     static_assert(!BF16 || (NCH > 0 && !BUILD), "bf16 gathers: register-resident query, search mode only");
     constexpr int THREADS = WARPS * 32;
     // Entries expanded per step.  A step costs two dependent global round trips (adjacency rows, then the
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : 1) hnsw_search_k
     // merge mode (CTAs of >= 4 warps, search): second pool buffer + the compacted survivors of a step
     unsigned long long* s_beam2 = reinterpret_cast<unsigned long long*>(s_cid + p.cand_cap);
     unsigned long long* s_surv = s_beam2 + p.beam_cap;
-    const bool merge_mode = WARPS >= 4 && !BUILD && p.merge != 0u;
+    const bool merge_mode = WARPS >= 2 && !BUILD && p.merge != 0u;
     __shared__ int s_nc, s_size, s_done, s_nlive;
     __shared__ float s_invq;
     // result staging reuses the traversal's scratch (dead by then): exact scores over the candidate keys,
@@ -475,27 +475,29 @@ static int launch_warps(const HnswParams& p, uint32_t nq, size_t smem, cudaStrea
     return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }
 
-// CTA width: narrow CTAs (1–2 warps) keep more queries resident per SM and spend less time at CTA barriers
-// while warp 0 runs the serial pool maintenance; wide beams amortise better over 4 warps.
-static int hnsw_cta_warps(uint32_t beam, uint32_t nq) {
+// CTA width.  Search (the whole-CTA rank merge keeps pool maintenance off warp 0, so extra warps only add gather
+// parallelism): measured on 1M x 384, beam 80 (scripts/hnsw_probe.py, registers capped so that 32 warps stay resident
+// per SM whatever the width) — 1 024 queries: 0.76 / 1.27 / 1.55 M q/s with 1 / 2 / 4 warps per query; 4 096: 1.65 /
+// 2.02 / 1.97; 16 384: 2.35 / 2.64 / 2.37.  A query that finishes sooner beats a query that is merely resident.
+// Few queries: latency matters, a whole 16-warp CTA per query scores the up-to-256 candidates of a step in one round
+// of gathers (scripts/hnsw_latency.py: 168 / 263 / 310 us per call at nq = 1 / 16 / 128).
+// Construction keeps the one-warp kernel it was tuned with (profiles/r01_hnsw_tune.jsonl).
+static int hnsw_cta_warps(uint32_t beam, uint32_t nq, bool build = false) {
     if (const char* e = std::getenv("VL_HNSW_WARPS")) {
         const int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16) return w;
     }
-    // measured on 1M x 384 (scripts/hnsw_tune.py, profiles/r01_hnsw_tune.jsonl): with thousands of queries in
-    // flight one warp per query wins at every beam width (1.42M vs 0.85M q/s at beam 80)
-    // few queries: latency matters, use a whole CTA per query — 16 warps score the up-to-128 candidates of a step in
-    // one round of gathers (scripts/hnsw_latency.py, 1M x 384, beam 80: 370 / 701 / 955 µs per call at nq = 1 / 16 /
-    // 128 vs 439 / 847 / 1299 µs with 4 warps)
-    (void)beam;
-    return nq <= 296 ? 16 : (nq < 1024 ? 4 : 1);
+    if (build) return nq <= 296 ? 16 : (nq < 1024 ? 4 : 1);
+    // (beams above 512 entries: the 64 threads of a 2-warp CTA spend longer on the rank merge than warp 0 did inserting —
+    // beam 2048 at 4 096 queries: 49 K vs 59 K q/s — so those keep the one-warp kernel)
+    return nq <= 296 ? 16 : (nq < 2400 ? 4 : (beam <= 512 ? 2 : 1));
 }
 
 template <int METRIC, bool BUILD>
 static int launch_metric(const HnswParams& p, uint32_t nq, size_t smem, cudaStream_t s) {
     // (a register-resident sorted pool — ballot-ranked insertion, shfl_up shifts — was measured and is NOT
     // faster than this shared-memory pool at any beam width: profiles/r01_hnsw_tune.jsonl, "regpool" rows)
-    switch (hnsw_cta_warps(p.ef, nq)) {
+    switch (hnsw_cta_warps(p.ef, nq, BUILD)) {
         case 1: return launch_warps<METRIC, BUILD, 1>(p, nq, smem, s);
         case 2: return launch_warps<METRIC, BUILD, 2>(p, nq, smem, s);
         case 8: return launch_warps<METRIC, BUILD, 8>(p, nq, smem, s);
@@ -604,7 +606,7 @@ int hnsw_launch_search(const HnswDeviceGraph& g, const float* d_rows, uint32_t p
     const int cta_warps = hnsw_cta_warps(static_cast<uint32_t>(W), nq);
     static const bool no_merge = std::getenv("VL_HNSW_NO_MERGE") != nullptr;
     const size_t smem = size_pool(p, static_cast<uint32_t>(W), g.M0, std::max(g.M, g.M0), k, pitch, cta_warps >= 16,
-                                  cta_warps >= 4 && !no_merge);
+                                  cta_warps >= 2 && !no_merge);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, false>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN, false>(p, nq, smem, stream);
