@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 32 : (WARPS == 2 ? 16
     // merge mode (CTAs of >= 4 warps, search): second pool buffer + the compacted survivors of a step
     unsigned long long* s_beam2 = reinterpret_cast<unsigned long long*>(s_cid + p.cand_cap);
     unsigned long long* s_surv = s_beam2 + p.beam_cap;
-    const bool merge_mode = WARPS >= 2 && !BUILD && p.merge != 0u;
+    const bool merge_mode = WARPS >= 2 && p.merge != 0u;
     __shared__ int s_nc, s_size, s_done, s_nlive;
     __shared__ float s_invq;
     // result staging reuses the traversal's scratch (dead by then): exact scores over the candidate keys,
@@ -487,7 +487,10 @@ static int hnsw_cta_warps(uint32_t beam, uint32_t nq, bool build = false) {
         const int w = atoi(e);
         if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16) return w;
     }
-    if (build) return nq <= 296 ? 16 : (nq < 1024 ? 4 : 1);
+    if (build) {
+        static const bool build2 = std::getenv("VL_HNSW_BUILD_ONE_WARP") == nullptr;
+        return nq <= 296 ? 16 : (nq < 1024 ? 4 : (build2 && beam <= 512 ? 2 : 1));
+    }
     // (beams above 512 entries: the 64 threads of a 2-warp CTA spend longer on the rank merge than warp 0 did inserting —
     // beam 2048 at 4 096 queries: 49 K vs 59 K q/s — so those keep the one-warp kernel)
     return nq <= 296 ? 16 : (nq < 2400 ? 4 : (beam <= 512 ? 2 : 1));
@@ -560,7 +563,10 @@ int hnsw_launch_build_search(const HnswDeviceGraph& g, const float* d_rows, uint
     p.out_ids = nullptr; p.out_scores = nullptr; p.out_counts = d_out_counts; p.visited = nullptr;
     p.order = d_order; p.stop_level = level; p.entry_only = entry_only ? 1u : 0u;
     p.out_keys = d_out_keys; p.out_stride = out_stride;
-    const size_t smem = size_pool(p, ef, level == 0 ? g.M0 : g.M, std::max(g.M, g.M0), 0, pitch);
+    static const bool no_merge = std::getenv("VL_HNSW_NO_MERGE") != nullptr;
+    const int cta_warps = hnsw_cta_warps(ef, nq, true);
+    const size_t smem = size_pool(p, ef, level == 0 ? g.M0 : g.M, std::max(g.M, g.M0), 0, pitch, false,
+                                  cta_warps >= 2 && !no_merge);
     switch (metric) {
         case COSINE: return launch_metric<COSINE, true>(p, nq, smem, stream);
         case EUCLIDEAN: return launch_metric<EUCLIDEAN, true>(p, nq, smem, stream);
