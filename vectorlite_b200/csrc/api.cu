@@ -587,7 +587,8 @@ static int run_pass(vl_index* h, Slot& s, const FlatView& v, const float* querie
     SearchOut out{s.d_ids, s.d_scores, nullptr, s.d_counts, s.d_flags};
     // small batches (the combiner's cohorts of concurrent single-query callers): the rescore kernel writes its
     // results straight into the pinned host mirror (UVA zero-copy) — no D2H copy operation, one synchronize
-    const bool zero_copy = batched && !cfg.exact && m <= 128;
+    static const bool no_zero_copy = getenv("VL_DISABLE_ZERO_COPY") != nullptr;
+    const bool zero_copy = batched && !cfg.exact && m <= 128 && !no_zero_copy;
     if (zero_copy) out = SearchOut{s.h_ids, s.h_scores, nullptr, s.h_counts, s.h_flags};
     if (cfg.exact) {
         for (uint32_t q = 0; q < m; ++q) {

@@ -46,7 +46,7 @@ public:
                 // futex round trip plus a reschedule per caller — tens of µs that the NEXT batch waits for, since its
                 // leader gathers the re-forming cohort first.  When the callers fit the host's cores, wait for the
                 // running batch by polling (bounded: spin_us, default 400 µs) and only then block.
-                if (spin_us() > 0 && expect_ <= cores()) {
+                if (spin_us() > 0 && reserved_ <= 3 && expect_ + reserved_ <= cores() + cores() / 4) {
                     lk.unlock();
                     const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us());
                     while (!me.done.load(std::memory_order_acquire) && leader_.load(std::memory_order_acquire) &&
@@ -131,6 +131,12 @@ public:
         return me.rc;
     }
 
+    // host threads that work for the running batch besides its leader (a shard group's helper threads).  Measured with
+    // 16 callers (scripts/group_e2e.py): polling waiters gain 9 % / 10 % with 1 / 3 helpers (2 / 4 GPUs, 16-core host)
+    // and LOSE 39 % with 7 (8 GPUs, 32-core host: 270 K vs 439 K q/s x shards) although cores are left over — so
+    // polling is kept to handles and groups of at most 4 shards.
+    void reserve_cores(size_t n) { reserved_ = n; }
+
     static bool enabled() {
         static const bool on = std::getenv("VL_DISABLE_COMBINER") == nullptr;
         return on;
@@ -168,6 +174,7 @@ private:
     std::vector<Pending*> queue_;
     std::atomic<bool> leader_{false};
     size_t expect_ = 1;   // size of the batch that just completed: how many callers the next leader may wait for
+    size_t reserved_ = 0;
 };
 
 }  // namespace vl
