@@ -63,7 +63,8 @@ typedef enum vl_index_type { VL_INDEX_FLAT = 0, VL_INDEX_HNSW = 1 } vl_index_typ
  *       summation order → optimality certificate; a query whose certificate fails is re-run on
  *       the EXACT path.  Both paths return identical, oracle-exact results.
  * EXACT: every row scored in f64 in reference order on the device, stable radix select. */
-/* AUTO: approximate scans may read the bf16 mirror of the rows (tensor-core batches; single-query scans at 384-d) —
+/* AUTO: approximate scans may read the bf16 mirror of the rows (tensor-core batches for rows up to 2048 elements;
+ * single-query scans at 128 / 256 / 384 / 768 / 1024 / 1536-d) —
  * results stay bit-exact through the f64 rescore + certificate.  FP32: scans read the fp32 arena only.  EXACT: every
  * row scored in f64. */
 typedef enum vl_mode { VL_MODE_AUTO = 0, VL_MODE_EXACT = 1, VL_MODE_FP32 = 2 } vl_mode;
