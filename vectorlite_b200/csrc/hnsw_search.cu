@@ -5,15 +5,19 @@
 // Appendix C): upper layers are walked greedily (beam 1), layer 0 with a beam of `ef`.
 //
 //  - the query lives in registers (12 floats per lane at 384-d), every warp owns a copy;
-//  - the beam is an unsorted pool of 64-bit keys (orderable fp32 distance | node<<1 | expanded) in
-//    shared memory: warp 0 selects the closest unexpanded entry and replaces the worst entry with
-//    warp-wide argmin / argmax reductions (no binary search, no shifting), sorted once at the end;
+//  - the beam is a pool of 64-bit keys (orderable fp32 distance | node<<1 | expanded) in shared memory.
+//    CTAs of two or more warps (every search launch except very wide beams at large query counts) keep it
+//    SORTED: the survivors of a step are compacted while they are scored and merged in by the whole CTA
+//    (rank counting against the other list, exact duplicates dropped), and the entries to expand are read
+//    off its front with one ballot.  One-warp CTAs keep the older unsorted pool: warp 0 selects the
+//    closest unexpanded entry and replaces the worst entry with warp-wide argmin / argmax reductions,
+//    sorted once at the end;
 //  - visited set: a direct-mapped, lossy tag cache in shared memory (no probing, no overflow).
 //    Losing a tag only costs a redundant distance evaluation: a re-evaluated node is either
 //    rejected by the beam threshold or found as an exact duplicate key at its insertion point;
 //  - neighbour distances are warp-cooperative: each warp scores 8 neighbours at a time, every lane
-//    streaming 3×128-bit loads per 384-d row (whole 1536-B rows, fully coalesced) and the 8 sums
-//    reduced with the transposed butterfly of the flat scan;
+//    streaming whole rows (384-d: 3×64-bit loads per row from the bf16 mirror, 3×128-bit from the fp32
+//    arena; fully coalesced) and the 8 sums reduced with the transposed butterfly of the flat scan;
 //  - the final k candidates are re-scored in f64 with the reference's flat formulae
 //    (src/lib.rs:425-572) so HNSW scores equal Flat scores for the same ids (the reference's
 //    quantised /1000 score quirk, hnsw.rs:478 + 51-75, is deliberately not reproduced);
