@@ -72,7 +72,7 @@ def test_convert_kats(oracle_mod, kats):
 
 def test_cpp_matches_python_random(oracle_mod):
     rng = np.random.default_rng(7)
-    for dim in (1, 3, 17, 384):
+    for dim in (1, 3, 17, 384, 768, 1536):   # the oracle at the widths the wide-row GPU tests use
         rows = rng.standard_normal((40, dim)).astype(np.float32)
         rows[3] = 0.0               # zero row → cosine 0.0 branch
         rows[5] = rows[4]           # exact duplicate → tie resolved by position
